@@ -1,0 +1,603 @@
+"""GPU parity: every CUDA path of libthor_b200.so, called through its C ABI, against the plain-C oracle on the same
+seeded inputs (bit-exact).  Where oracle/_ref travelled to the box, the compiled reference is checked too."""
+import ctypes as C
+import numpy as np
+import pytest
+
+from _libs import oracle, ref, aligned, P, sdt, sfx, rand_plane
+from _refstructs import Frame as HFrame, random_blkinfo
+
+pytestmark = pytest.mark.gpu
+O = oracle()
+BD = [(0, 8), (1, 10)]
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import thor_b200 as t
+    t.init(0)
+    return t
+
+
+def dptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (A) drop-in symbols
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_dropin_sad_family(tb, hbd, bd):
+    rng = np.random.default_rng(101)
+    s = sfx(hbd)
+    L = tb.lib
+    for smooth in (False, True):
+        refp = rand_plane(rng, 200, 256, bd, hbd, smooth)
+        for (w, h) in [(8, 8), (8, 4), (16, 16), (16, 8), (32, 32), (64, 64), (128, 128), (64, 32), (16, 32)]:
+            size = max(w, h)
+            org = aligned((size, size), sdt(hbd))
+            oy, ox = int(rng.integers(8, 60)), int(rng.integers(8, 100))
+            org[...] = refp[oy:oy + size, ox:ox + size] if smooth else rng.integers(0, 1 << bd, (size, size))
+            for _ in range(2):
+                y, x = oy + int(rng.integers(-3, 4)), ox + int(rng.integers(-3, 4))
+                b = P(refp, y * 256 + x)
+                assert getattr(L, "sad_calc_simd_" + s)(P(org), b, size, 256, w, h) == getattr(O, "orc_sad_" + s)(P(org), b, size, 256, w, h)
+                assert getattr(L, "sad_calc_simd_unaligned_" + s)(P(refp, (y + 1) * 256 + x + 1), b, 256, 256, w, h) == \
+                    getattr(O, "orc_sad_" + s)(P(refp, (y + 1) * 256 + x + 1), b, 256, 256, w, h)
+                if w == h:
+                    assert getattr(L, "ssd_calc_simd_" + s)(P(org), b, size, 256, w) == getattr(O, "orc_ssd_" + s)(P(org), b, size, 256, w, h)
+                x0, x1 = C.c_int(9), C.c_int(9)
+                assert getattr(L, "widesad_calc_simd_" + s)(P(org), b, size, 256, w, h, C.byref(x0)) == \
+                    getattr(O, "orc_widesad_" + s)(P(org), b, size, 256, w, h, C.byref(x1))
+                assert x0.value == x1.value
+                xs = [C.c_int(0) for _ in range(4)]
+                got = getattr(L, "sad_calc_fasthalf_simd_" + s)(P(org), b, size, 256, w, h, C.byref(xs[0]), C.byref(xs[1]))
+                want = getattr(O, "orc_sad_fasthalf_" + s)(P(org), b, size, 256, w, h, C.byref(xs[2]), C.byref(xs[3]))
+                assert (got, xs[0].value, xs[1].value) == (want, xs[2].value, xs[3].value)
+                for (fx, fy) in [(0, 0), (2, 0), (0, -2), (-2, 2)]:
+                    xs = [C.c_int(fx if i % 2 == 0 else fy) for i in range(4)]
+                    got = getattr(L, "sad_calc_fastquarter_simd_" + s)(P(org), b, size, 256, w, h, C.byref(xs[0]), C.byref(xs[1]))
+                    want = getattr(O, "orc_sad_fastquarter_" + s)(P(org), b, size, 256, w, h, C.byref(xs[2]), C.byref(xs[3]))
+                    assert (got, xs[0].value, xs[1].value) == (want, xs[2].value, xs[3].value)
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_dropin_interp_avg(tb, hbd, bd):
+    rng = np.random.default_rng(102)
+    s = sfx(hbd)
+    L = tb.lib
+    refp = rand_plane(rng, 200, 256, bd, hbd)
+    for (w, h) in [(4, 4), (8, 8), (4, 8), (16, 16), (32, 32), (64, 64), (128, 128), (16, 8)]:
+        for bip in (0, 1, 2):
+            for (xo, yo) in [(1, 0), (0, 3), (2, 2), (1, 3), (3, 1), (2, 0), (2, 1)]:
+                y, x = int(rng.integers(8, 40)), int(rng.integers(8, 60))
+                a = aligned((h, w + 8), sdt(hbd), fill=7); b = aligned((h, w + 8), sdt(hbd), fill=7)
+                getattr(O, "orc_interp_luma_" + s)(w, h, xo, yo, P(a), w + 8, P(refp, y * 256 + x), 256, bip, bd)
+                getattr(L, "get_inter_prediction_luma_simd_" + s)(w, h, xo, yo, P(b), w + 8, P(refp, y * 256 + x), 256, bip, bd)
+                assert (a == b).all(), (w, h, bip, xo, yo)
+    for (w, h) in [(4, 4), (8, 8), (2, 2), (16, 16), (64, 64), (8, 4)]:
+        for (xo, yo) in [(1, 0), (0, 5), (4, 4), (7, 3), (2, 6)]:
+            y, x = int(rng.integers(8, 40)), int(rng.integers(8, 60))
+            a = aligned((h, w), sdt(hbd)); b = aligned((h, w), sdt(hbd))
+            getattr(O, "orc_interp_chroma_" + s)(w, h, xo, yo, P(a), w, P(refp, y * 256 + x), 256, bd)
+            getattr(L, "get_inter_prediction_chroma_simd_" + s)(w, h, xo, yo, P(b), w, P(refp, y * 256 + x), 256, bd)
+            assert (a == b).all()
+    for size in (4, 8, 16, 64):
+        p0 = rand_plane(rng, size, size + 16, bd, hbd); p1 = rand_plane(rng, size, size + 16, bd, hbd)
+        o0 = aligned((size, size + 16), sdt(hbd), fill=0); o1 = aligned((size, size + 16), sdt(hbd), fill=0)
+        getattr(O, "orc_block_avg_" + s)(P(o0), P(p0), P(p1), size + 16, size + 16, size + 16, size, size)
+        getattr(L, "block_avg_simd_" + s)(P(o1), P(p0), P(p1), size + 16, size + 16, size + 16, size, size)
+        assert (o0 == o1).all()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_dropin_transform_quant(tb, bd):
+    rng = np.random.default_rng(103)
+    L = tb.lib
+    lim = (1 << bd) - 1
+    for size in (4, 8, 16, 32, 64, 128):
+        for fast in (0, 1):
+            for amp in (lim, 25, 3):
+                blk = aligned((size, size), np.int16)
+                blk[...] = rng.integers(-amp, amp + 1, (size, size))
+                c0 = aligned((size, size), np.int16, fill=0); c1 = aligned((size, size), np.int16, fill=0)
+                O.orc_transform(P(blk), P(c0), size, fast, bd)
+                L.transform_simd(P(blk), P(c1), size, fast, bd)
+                q = min(size, 16)
+                assert (c0[:q, :q] == c1[:q, :q]).all(), (size, fast, amp)
+                for qp in (12, 27, 32, 39, 51):
+                    for typ in (0, 2):
+                        q0 = aligned((q * q,), np.int16, fill=0); q1 = aligned((q * q,), np.int16, fill=0)
+                        cb0 = O.orc_quantize(P(c0), P(q0), qp, size, typ, None)
+                        cb1 = L.tb_quantize(P(c0), P(q1), qp, size, typ)
+                        assert cb0 == cb1 and (q0 == q1).all(), (size, qp, typ, amp)
+                    r0 = aligned((size, size), np.int16, fill=0); r1 = aligned((size, size), np.int16, fill=0)
+                    O.orc_dequantize(P(q0), P(r0), qp, size, None)
+                    L.tb_dequantize(P(q1), P(r1), qp, size)
+                    assert (r0 == r1).all()
+                    if size <= 32:
+                        assert O.orc_check_nz_area(P(r0), size) == L.check_nz_area(P(r0), size)
+                    b0 = aligned((size, size), np.int16, fill=0); b1 = aligned((size, size), np.int16, fill=0)
+                    O.orc_inverse_transform(P(r0), P(b0), size, bd)
+                    if size < 64:  # the reference routes 64/128 through inverse_transform() in transform.c (32x32 kernel + replication)
+                        L.inverse_transform_simd(P(r0), P(b1), size, bd)
+                        assert (b0 == b1).all(), (size, qp)
+    for size in (4, 8, 16):
+        for _ in range(60):
+            blk = aligned((size, size), np.int16)
+            blk[...] = rng.integers(-int(rng.choice([2, 6, 40])), 41, (size, size))
+            thr = int(rng.integers(1, 60))
+            assert O.orc_calc_cbp(P(blk), size, thr) == L.calc_cbp_simd(P(blk), size, thr)
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_dropin_filters(tb, hbd, bd):
+    rng = np.random.default_rng(104)
+    s = sfx(hbd)
+    L = tb.lib
+    w, h = 200, 136
+    f = HFrame(w, h, bd, hbd, 32, 32)
+    f.randomize(rng)
+    org = f.copy()
+    org.y[...] = np.clip(f.y.astype(int) + rng.integers(-6, 7, f.y.shape), 0, (1 << bd) - 1)
+    for (sx, sy) in [(8, 8), (4, 4), (8, 4)]:
+        for bt in (0, 1, 2, 4, 8, 5, 10, 15):
+            x0, y0 = 8 * int(rng.integers(1, 10)), 8 * int(rng.integers(1, 8))
+            d0 = aligned((h, w), sdt(hbd), fill=0); d1 = aligned((h, w), sdt(hbd), fill=0)
+            st, dmp = 2 << (bd - 8), bd - 4 + 2
+            getattr(O, "orc_clpf_block_" + s)(P(f.Y, f.origin(0)), P(d0), f.sy, w, x0, y0, sx, sy, bt, st, dmp)
+            if bt:
+                getattr(L, "clpf_block%d_%s" % (sx, s))(P(f.Y, f.origin(0)), P(d1), f.sy, w, x0, y0, sy, bt, st, dmp)
+            else:
+                getattr(L, "clpf_block%d_noclip_%s" % (sx, s))(P(f.Y, f.origin(0)), P(d1), f.sy, w, x0, y0, sy, st, dmp)
+            assert (d0 == d1).all(), (sx, sy, bt)
+    for _ in range(25):
+        x0, y0 = 8 * int(rng.integers(0, w // 8)), 8 * int(rng.integers(0, h // 8))
+        strength = int(rng.choice([1, 2, 4])) << (bd - 8)
+        a = (C.c_int * 2)(0, 0); c = (C.c_int * 2)(3, 4)
+        args = (P(f.Y, f.origin(0)), P(org.Y, org.origin(0)), x0, y0, w, h, org.sy, f.sy)
+        getattr(O, "orc_detect_clpf_" + s)(*args, C.byref(a, 0), C.byref(a, 4), strength, bd - 8, 8, bd - 4 + 2)
+        getattr(L, "detect_clpf_simd_" + s)(*args, C.byref(c, 0), C.byref(c, 4), strength, bd - 8, 8, bd - 4 + 2)
+        assert [c[0], c[1]] == [3 + 2 * a[0], 4 + 2 * a[1]]
+        m0 = (C.c_int * 4)(1, 2, 3, 4); m1 = (C.c_int * 4)(1, 2, 3, 4)
+        getattr(O, "orc_detect_multi_clpf_" + s)(*args, m0, bd - 8, 8, bd - 4 + 2)
+        getattr(L, "detect_multi_clpf_simd_" + s)(*args, m1, bd - 8, 8, bd - 4 + 2)
+        assert list(m0) == list(m1)
+        v0, v1 = C.c_int32(0), C.c_int32(0)
+        p = P(f.Y, f.origin(0) + y0 * f.sy + x0)
+        assert getattr(O, "orc_cdef_find_dir_" + s)(p, f.sy, C.byref(v0), bd - 8) == getattr(L, "cdef_find_dir_simd_" + s)(p, f.sy, C.byref(v1), bd - 8)
+        assert v0.value == v1.value
+    cs = bd - 8
+    dirs = np.zeros((8, 2), np.int32)
+    for trial in range(40):
+        bs = int(rng.choice([4, 8]))
+        plane = 0 if bs == 8 else 1
+        pw, ph = (w, h) if plane == 0 else (w // 2, h // 2)
+        x0, y0 = bs * int(rng.integers(0, pw // bs)), bs * int(rng.integers(0, ph // bs))
+        bt = (1 if x0 == 0 else 0) | (4 if y0 == 0 else 0) | (2 if x0 == pw - bs else 0) | (8 if y0 == ph - bs else 0)
+        t0 = aligned((12, 32), np.uint16, fill=0)
+        getattr(O, "orc_cdef_prepare_input_" + s)(bs, bs, x0, y0, bt, 2, P(t0, 2 * 32 + 16), 32, P(f.full(plane), f.origin(plane)), f.stride(plane))
+        pri = int(rng.integers(0, 16)) << cs; sec = int(rng.choice([0, 1, 2, 4])) << cs
+        d = int(rng.integers(0, 8))
+        pd = max(int(np.log2(pri >> cs)) if pri >> cs else 0, 5 - plane) + cs; sd = 5 - plane + cs
+        o0 = aligned((bs, bs), sdt(hbd), fill=0); o1 = aligned((bs, bs), sdt(hbd), fill=0)
+        dp = lambda o: (P(o), None) if not hbd else (None, P(o))
+        O.orc_cdef_filter_block(*dp(o0), bs, P(t0, 2 * 32 + 16), 32, pri, sec, d, pd, sd, bs, cs)
+        L.cdef_filter_block_simd(*dp(o1), bs, P(t0, 2 * 32 + 16), 32, pri, sec, d, pd, sd, bs, P(dirs), cs)
+        assert (o0 == o1).all(), (bs, pri, sec, d, bt)
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_cfl(tb, hbd, bd):
+    rng = np.random.default_rng(105)
+    s = sfx(hbd)
+    hit = 0
+    for n in (8, 16, 32, 64):
+        for trial in range(12):
+            y = rand_plane(rng, n, n, bd, hbd, smooth=True)
+            ry = aligned((n, n + 8), sdt(hbd))
+            ry[...] = np.clip(np.pad(y.astype(int), ((0, 0), (0, 8)), mode="edge") + rng.integers(-40, 41, (n, n + 8)) * (trial % 3), 0, (1 << bd) - 1)
+            k = float(rng.uniform(-1.5, 1.5))
+            ys = y.astype(int).reshape(n // 2, 2, n // 2, 2).sum(axis=(1, 3)) // 4
+            u0 = aligned((n // 2, n // 2), sdt(hbd)); v0 = aligned((n // 2, n // 2), sdt(hbd))
+            u0[...] = np.clip(ys * k + (1 << (bd - 1)) * (1 - k) + rng.integers(-3, 4, ys.shape), 0, (1 << bd) - 1)
+            v0[...] = np.clip(ys * -k + (1 << (bd - 1)) * (1 + k) + rng.integers(-30, 31, ys.shape), 0, (1 << bd) - 1)
+            u1 = aligned(u0.shape, sdt(hbd)); u1[...] = u0; v1 = aligned(v0.shape, sdt(hbd)); v1[...] = v0
+            ub = u0.copy()
+            getattr(O, "orc_cfl_" + s)(P(y), P(u0), P(v0), P(ry), n, n, n + 8, 1, bd)
+            tb.lib.tb_improve_uv_prediction(2 if hbd else 1, P(y), P(u1), P(v1), P(ry), n, n, n + 8, 1, bd)
+            assert (u0 == u1).all() and (v0 == v1).all()
+            hit += int((ub != u0).any())
+    assert hit > 5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (B) batched entry points on resident frames
+# ------------------------------------------------------------------------------------------------------------------
+def make_frames(tb, rng, w, h, bd, hbd, shift=(2, -3)):
+    """host reference frame (padded by the oracle) + current frame, and their device twins (reference padded on the GPU)"""
+    s = sfx(hbd)
+    href = HFrame(w, h, bd, hbd)
+    href.randomize(rng)
+    cur = HFrame(w, h, bd, hbd)
+    cur.y[...] = np.clip(np.roll(href.y.astype(int), shift, axis=(0, 1)) + rng.integers(-4, 5, href.y.shape), 0, (1 << bd) - 1)
+    cur.u[...] = href.u; cur.v[...] = href.v
+    esz = 2 if hbd else 1
+    drec = tb.Frame(w, h, esz); dref = tb.Frame(w, h, esz); dcur = tb.Frame(w, h, esz)
+    drec.upload(href.y, href.u, href.v)
+    tb.check(tb.lib.tb_create_reference_frame(dref.h, drec.h))
+    dcur.upload(cur.y, cur.u, cur.v)
+    for p, (pw, ph, padh) in enumerate(((w, h, 160), (w // 2, h // 2, 80), (w // 2, h // 2, 80))):
+        getattr(O, "orc_pad_plane_" + s)(P(href.full(p), href.origin(p)), href.stride(p), pw, ph, padh, padh)
+    return href, cur, dref, dcur, drec
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_reference_frame_and_pad(tb, hbd, bd):
+    rng = np.random.default_rng(106)
+    w, h = 192, 136
+    href, cur, dref, dcur, drec = make_frames(tb, rng, w, h, bd, hbd)
+    esz = 2 if hbd else 1
+    # read back the whole padded luma/chroma planes of the GPU reference frame and compare with the oracle's padding
+    for p in range(3):
+        ptr, st = dref.plane(p)
+        pw, ph, pad = (w, h, 160) if p == 0 else (w // 2, h // 2, 80)
+        assert st == href.stride(p)
+        nbytes = (ph + 2 * pad) * st * esz
+        raw = np.empty(nbytes, np.uint8)
+        tb.check(tb.lib.tb_memcpy_d2h(raw.ctypes.data, ptr - (pad * st + pad) * esz, nbytes))
+        got = raw.view(sdt(hbd)).reshape(ph + 2 * pad, st)[:, :pw + 2 * pad]
+        want = href.full(p)[:ph + 2 * pad, :pw + 2 * pad]
+        assert (got == want).all(), p
+    # pad in place == idempotent second application
+    tb.check(tb.lib.tb_pad_frame(dref.h))
+    ptr, st = dref.plane(0)
+    raw = np.empty((h + 320) * st * esz, np.uint8)
+    tb.check(tb.lib.tb_memcpy_d2h(raw.ctypes.data, ptr - (160 * st + 160) * esz, raw.nbytes))
+    assert (raw.view(sdt(hbd)).reshape(h + 320, st)[:, :w + 320] == href.Y[:h + 320, :w + 320]).all()
+    # 2x2 down-scaling
+    small = tb.Frame(w // 2, h // 2, esz)
+    tb.check(tb.lib.tb_scale_down2x2(dref.h, small.h))
+    y, _, _ = small.download()
+    want = aligned((h // 2, w // 2), sdt(hbd))
+    getattr(O, "orc_scale_down2x2_" + sfx(hbd))(P(href.Y, href.origin(0)), href.sy, P(want), w // 2, w // 2, h // 2)
+    assert (y == want).all()
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_batch_sad(tb, hbd, bd):
+    rng = np.random.default_rng(107)
+    s = sfx(hbd)
+    w, h = 256, 192
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    esz = 2 if hbd else 1
+    rptr, rst = dref.plane(0); optr, ost = dcur.plane(0)
+    n = 600
+    items = np.zeros(n, tb.SAD_ITEM)
+    want = np.zeros(n, np.uint32); wantx = np.zeros(n, np.int32); want64 = np.zeros(n, np.uint64)
+    shapes = [(4, 4), (4, 8), (8, 4), (8, 8), (16, 8), (8, 16), (16, 16), (32, 32), (64, 64), (128, 128), (64, 32)]
+    meta = []
+    for i in range(n):
+        bw, bh = shapes[i % len(shapes)]
+        x = 4 * int(rng.integers(0, (w - bw) // 4 + 1)); y = 4 * int(rng.integers(0, (h - bh) // 4 + 1))
+        dx, dy = int(rng.integers(-150, 150)), int(rng.integers(-150, 150))
+        dx = int(np.clip(x + dx, -140, w + 140 - bw)) - x; dy = int(np.clip(y + dy, -140, h + 140 - bh)) - y
+        items[i] = (optr + (y * ost + x) * esz, rptr + ((y + dy) * rst + x + dx) * esz, ost, rst, bw, bh, 0)
+        meta.append((x, y, dx, dy, bw, bh))
+    d_items = tb.DevBuf.from_array(items)
+    d_out = tb.DevBuf(4 * n); d_out2 = tb.DevBuf(4 * n); d_out64 = tb.DevBuf(8 * n)
+    for kind in (0, 1, 2):
+        tb.check(tb.lib.tb_sad_batch(d_items.ptr, n, esz, kind, d_out.ptr, d_out2.ptr, d_out64.ptr))
+        got = d_out.download(np.uint32, n); got2 = d_out2.download(np.int32, n); got64 = d_out64.download(np.uint64, n)
+        for i, (x, y, dx, dy, bw, bh) in enumerate(meta):
+            a = P(cur.Y, cur.origin(0) + y * cur.sy + x); b = P(href.Y, href.origin(0) + (y + dy) * href.sy + x + dx)
+            if kind == 0:
+                assert got[i] == getattr(O, "orc_sad_" + s)(a, b, cur.sy, href.sy, bw, bh), i
+            elif kind == 1:
+                xo = C.c_int(0)
+                assert got[i] == getattr(O, "orc_widesad_" + s)(a, b, cur.sy, href.sy, bw, bh, C.byref(xo)) and got2[i] == xo.value, i
+            else:
+                assert got64[i] == getattr(O, "orc_ssd_" + s)(a, b, cur.sy, href.sy, bw, bh), i
+
+
+def build_me_items(tb, rng, n, w, h, cur, href, dcur, dref, esz, sizes=(8, 16, 32, 64), speed=0):
+    rptr, rst = dref.plane(0); optr, ost = dcur.plane(0)
+    items = np.zeros(n, tb.ME_ITEM)
+    cands = []
+    meta = []
+    for i in range(n):
+        size = int(rng.choice(sizes))
+        part = int(rng.integers(0, 4))
+        bw, bh, ox, oy = size, size, 0, 0
+        if part == 1: bh = size // 2; oy = int(rng.integers(0, 2)) * bh
+        if part == 2: bw = size // 2; ox = int(rng.integers(0, 2)) * bw
+        if part == 3: bw = bh = size // 2; ox = int(rng.integers(0, 2)) * bw; oy = int(rng.integers(0, 2)) * bh
+        xpos = int(rng.integers(0, w // size)) * size; ypos = int(rng.integers(0, h // size)) * size
+        sign = int(rng.integers(0, 2))
+        nc = int(rng.integers(0, 9))
+        if speed != 0 and nc == 0:
+            nc = 1
+        cc = rng.integers(-12, 12, (nc, 2)).astype(np.int16)
+        mvc = rng.integers(-40, 40, 2); mvp = rng.integers(-40, 40, 2)
+        lam = float(rng.uniform(2.0, 60.0))
+        items[i] = (optr + ((ypos + oy) * ost + xpos + ox) * esz, rptr + ((ypos + oy) * rst + xpos + ox) * esz, ost, rst, xpos, ypos, size, bw, bh, sign,
+                    mvc[0], mvc[1], mvp[0], mvp[1], sum(len(c) for c in cands), nc, lam)
+        cands.append(cc)
+        meta.append((size, bw, bh, ox, oy, xpos, ypos, sign, cc, mvc, mvp, lam))
+    call = np.concatenate(cands + [np.zeros((1, 2), np.int16)]).astype(np.int16)
+    return items, call, meta
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+@pytest.mark.parametrize("speed,bip", [(0, 1), (0, 0), (1, 0), (2, 0), (1, 1)])
+def test_batch_motion_estimate(tb, hbd, bd, speed, bip):
+    rng = np.random.default_rng(108 + speed * 7 + bip)
+    s = sfx(hbd)
+    w, h = 256, 192
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    n = 160
+    items, call, meta = build_me_items(tb, rng, n, w, h, cur, href, dcur, dref, esz, speed=speed)
+    d_items = tb.DevBuf.from_array(items); d_c = tb.DevBuf.from_array(call); d_out = tb.DevBuf(8 * n)
+    tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, d_c.ptr, esz, bd, speed, bip, w, h, d_out.ptr))
+    got = d_out.download(tb.ME_RESULT, n)
+    bad = []
+    for i, (size, bw, bh, ox, oy, xpos, ypos, sign, cc, mvc, mvp, lam) in enumerate(meta):
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur.y[ypos:ypos + size, xpos:xpos + size]
+        m0 = (C.c_int16 * 2)(0, 0)
+        cands = (C.c_int16 * (2 * max(len(cc), 1)))(*[int(v) for v in cc.reshape(-1)] or [0, 0])
+        cost = getattr(O, "orc_motion_estimate_" + s)(P(org, oy * size + ox), P(href.Y, href.origin(0) + (ypos + oy) * href.sy + xpos + ox), size, href.sy, bw, bh, m0,
+                                                       (C.c_int16 * 2)(int(mvc[0]), int(mvc[1])), (C.c_int16 * 2)(int(mvp[0]), int(mvp[1])), C.c_double(lam), speed, bd,
+                                                       sign, w, h, xpos, ypos, cands, len(cc), bip)
+        if (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])) != (cost & 0xffffffff, m0[0], m0[1]):
+            bad.append((i, size, bw, bh, sign, (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])), (cost, m0[0], m0[1])))
+    assert not bad, bad[:8]
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_batch_interp(tb, hbd, bd):
+    rng = np.random.default_rng(109)
+    s = sfx(hbd)
+    w, h = 256, 192
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    n = 400
+    items = np.zeros(n, tb.INTERP_ITEM)
+    out = tb.DevBuf(n * 64 * 64 * esz)
+    meta = []
+    for i in range(n):
+        chroma = int(i % 3 == 2)
+        size = int(rng.choice([4, 8, 16, 32, 64] if not chroma else [4, 8, 16, 32]))
+        bw, bh = size, size
+        if i % 5 == 1: bw //= 2
+        if i % 5 == 2: bh //= 2
+        bw, bh = max(bw, 4 if not chroma else 2), max(bh, 4 if not chroma else 2)
+        pw, ph = (w, h) if not chroma else (w // 2, h // 2)
+        xpos = int(rng.integers(0, pw // size)) * size; ypos = int(rng.integers(0, ph // size)) * size
+        sign = int(rng.integers(0, 2))
+        # luma-resolution MV, clipped like the callers do (common/inter_prediction.c:209)
+        mv = (C.c_int16 * 2)(int(rng.integers(-600, 600)), int(rng.integers(-600, 600)))
+        lx, ly = (xpos, ypos) if not chroma else (xpos * 2, ypos * 2)
+        O.orc_clip_mv(mv, ly, lx, w, h, bw << chroma, bh << chroma, sign)
+        ptr, st = dref.plane(1 if chroma else 0)
+        items[i] = (ptr + (ypos * st + xpos) * esz, out.ptr + i * 64 * 64 * esz, st, bw, xpos, ypos, mv[0], mv[1], bw, bh, sign, chroma, pw, ph, 0)
+        meta.append((chroma, bw, bh, xpos, ypos, sign, mv[0], mv[1], pw, ph))
+    d_items = tb.DevBuf.from_array(items)
+    for bip in (0, 1):
+        tb.check(tb.lib.tb_interp_batch(d_items.ptr, n, esz, bd, bip))
+        got = out.download(sdt(hbd), (n, 64 * 64))
+        for i, (chroma, bw, bh, xpos, ypos, sign, mvx, mvy, pw, ph) in enumerate(meta):
+            want = aligned((bh, bw), sdt(hbd))
+            mv = (C.c_int16 * 2)(mvx, mvy)
+            pl = 1 if chroma else 0
+            src = P(href.full(pl), href.origin(pl) + ypos * href.stride(pl) + xpos)
+            if chroma:
+                getattr(O, "orc_get_inter_prediction_chroma_" + s)(P(want), src, bw, bh, href.stride(pl), bw, mv, sign, pw, ph, xpos, ypos, bd)
+            else:
+                getattr(O, "orc_get_inter_prediction_luma_" + s)(P(want), src, bw, bh, href.stride(pl), bw, mv, sign, bip, pw, ph, xpos, ypos, bd)
+            assert (got[i, :bw * bh].reshape(bh, bw) == want).all(), (i, meta[i])
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_batch_txfm_chain(tb, hbd, bd):
+    rng = np.random.default_rng(110)
+    s = sfx(hbd)
+    w, h = 256, 256
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, drec = make_frames(tb, rng, w, h, bd, hbd)
+    n = 300
+    items = np.zeros(n, tb.TXFM_ITEM)
+    optr, ost = dcur.plane(0); pptr, pst = dref.plane(0)
+    recbuf = tb.DevBuf(n * 128 * 128 * esz if n * 128 * 128 * esz < (1 << 28) else 1 << 28)
+    cqbuf = tb.DevBuf(n * 256 * 2)
+    meta = []
+    sizes = [4, 8, 16, 32, 64, 128]
+    recofs = 0
+    for i in range(n):
+        size = sizes[i % 6] if i % 12 < 11 else 4
+        x = 4 * int(rng.integers(0, (w - size) // 4 + 1)); y = 4 * int(rng.integers(0, (h - size) // 4 + 1))
+        px, py = x + int(rng.integers(-4, 5)), y + int(rng.integers(-4, 5))
+        qp = int(rng.choice([10, 22, 30, 32, 37, 44, 51])); typ = int(rng.integers(0, 4)); fast = int(rng.integers(0, 2))
+        items[i] = (optr + (y * ost + x) * esz, pptr + (py * pst + px) * esz, recbuf.ptr + recofs * esz, cqbuf.ptr + i * 512, ost, pst, size, size, qp, typ, fast)
+        meta.append((size, x, y, px, py, qp, typ, fast, recofs))
+        recofs += size * size
+    d_items = tb.DevBuf.from_array(items); d_out = tb.DevBuf(16 * n)
+    tb.check(tb.lib.tb_txfm_chain_batch(d_items.ptr, n, esz, bd, d_out.ptr))
+    res = d_out.download(tb.TXFM_RESULT, n)
+    rec = recbuf.download(sdt(hbd), (recofs,))
+    cq = cqbuf.download(np.int16, (n, 256))
+    ncbp = 0
+    for i, (size, x, y, px, py, qp, typ, fast, ro) in enumerate(meta):
+        q = min(size, 16)
+        org = P(cur.Y, cur.origin(0) + y * cur.sy + x); prd = P(href.Y, href.origin(0) + py * href.sy + px)
+        blk = aligned((size, size), np.int16); cf = aligned((size, size), np.int16, fill=0); cq0 = aligned((q * q,), np.int16, fill=0)
+        getattr(O, "orc_residual_" + s)(P(blk), prd, org, size, href.sy, cur.sy)
+        O.orc_transform(P(blk), P(cf), size, fast, bd)
+        cbp = O.orc_quantize(P(cf), P(cq0), qp, size, typ, None)
+        want = aligned((size, size), sdt(hbd))
+        if cbp:
+            rc = aligned((size, size), np.int16, fill=0); rb = aligned((size, size), np.int16)
+            O.orc_dequantize(P(cq0), P(rc), qp, size, None)
+            O.orc_inverse_transform(P(rc), P(rb), size, bd)
+            getattr(O, "orc_reconstruct_" + s)(P(rb), prd, P(want), size, href.sy, size, bd)
+        else:
+            want[...] = href.Y[160 + py:160 + py + size, 160 + px:160 + px + size]
+        ssd = getattr(O, "orc_ssd_" + s)(org, P(want), cur.sy, size, size, size)
+        assert int(res[i]["cbp"]) == cbp, (i, size, qp)
+        assert (cq[i, :q * q] == cq0).all(), (i, size, qp, typ)
+        assert (rec[ro:ro + size * size].reshape(size, size) == want).all(), (i, size, qp)
+        assert int(res[i]["ssd"]) == ssd, (i, size)
+        ncbp += cbp
+    assert 0 < ncbp < n
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_batch_intra(tb, hbd, bd):
+    rng = np.random.default_rng(111)
+    s = sfx(hbd)
+    w, h = 256, 192
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, drec = make_frames(tb, rng, w, h, bd, hbd)
+    ptr, st = drec.plane(0)
+    n = 500
+    items = np.zeros(n, tb.INTRA_ITEM)
+    out = tb.DevBuf(n * 64 * 64 * esz)
+    meta = []
+    for i in range(n):
+        size = int(rng.choice([4, 8, 16, 32, 64]))
+        xpos = int(rng.integers(0, w // size)) * size; ypos = int(rng.integers(0, h // size)) * size
+        if i % 7 == 0: xpos = 0
+        if i % 11 == 0: ypos = 0
+        mode = i % 10
+        ur = int(rng.integers(0, 2)) if (ypos > 0 and xpos + size < w) else 0
+        dl = int(rng.integers(0, 2)) if (xpos > 0 and ypos + size < h) else 0
+        items[i] = (ptr + (ypos * st + xpos) * esz, out.ptr + i * 64 * 64 * esz, st, xpos, ypos, size, mode, ur, dl)
+        meta.append((size, xpos, ypos, mode, ur, dl))
+    d_items = tb.DevBuf.from_array(items)
+    tb.check(tb.lib.tb_intra_batch(d_items.ptr, n, esz, bd))
+    got = out.download(sdt(hbd), (n, 64 * 64))
+    for i, (size, xpos, ypos, mode, ur, dl) in enumerate(meta):
+        left = aligned((264,), sdt(hbd), fill=0); top = aligned((264,), sdt(hbd), fill=0); tl = aligned((1,), sdt(hbd), fill=0)
+        getattr(O, "orc_make_top_and_left_" + s)(P(left), P(top), P(tl), P(href.Y, href.origin(0) + ypos * href.sy + xpos), href.sy, None, 0, 0, 0, ypos, xpos, size, ur,
+                                                  dl, 0, bd)
+        want = aligned((size, size), sdt(hbd))
+        getattr(O, "orc_intra_pred_" + s)(P(left), P(top), int(tl[0]), ypos, xpos, size, P(want), size, mode, bd)
+        assert (got[i, :size * size].reshape(size, size) == want).all(), (i, meta[i])
+
+
+def run_filters(tb, rng, w, h, bd, hbd, qp=33):
+    """deblock -> CDEF (3 planes) -> CLPF (3 planes) on the GPU and in the oracle; returns (gpu planes, oracle frame)"""
+    s = sfx(hbd)
+    esz = 2 if hbd else 1
+    f = HFrame(w, h, bd, hbd, 32, 32)
+    f.randomize(rng)
+    org = f.copy()
+    for p in range(3):
+        org.plane(p)[...] = np.clip(f.plane(p).astype(int) + rng.integers(-5, 6, f.plane(p).shape), 0, (1 << bd) - 1)
+    bi, _ = random_blkinfo(rng, w, h)
+    drec = tb.Frame(w, h, esz, 32); dscr = tb.Frame(w, h, esz, 32); dorg = tb.Frame(w, h, esz, 32)
+    drec.upload(f.y, f.u, f.v); dorg.upload(org.y, org.u, org.v)
+    dbi = tb.DevBuf.from_array(bi)
+    stages = {}
+    # --- deblock
+    tb.check(tb.lib.tb_deblock_frame(drec.h, dbi.ptr, qp, bd))
+    getattr(O, "orc_deblock_y_" + s)(P(f.Y, f.origin(0)), f.sy, P(bi), w, h, qp, bd)
+    getattr(O, "orc_deblock_uv_" + s)(P(f.U, f.origin(1)), P(f.V, f.origin(1)), f.sc, P(bi), w, h, 1, O.orc_chroma_qp(qp), bd)
+    stages["deblock"] = (drec.download(), [f.plane(p).copy() for p in range(3)])
+    # --- CLPF detect sums on the deblocked frame
+    nb = (w // 8) * (h // 8)
+    dsum = tb.DevBuf(16 * nb)
+    tb.check(tb.lib.tb_clpf_detect_frame(drec.h, dorg.h, dbi.ptr, 0, bd, qp, dsum.ptr))
+    gs = dsum.download(np.int32, (nb, 4))
+    ws = np.zeros((nb, 4), np.int32)
+    for b in range(nb):
+        x0, y0 = (b % (w // 8)) * 8, (b // (w // 8)) * 8
+        if bi[y0 // 4, x0 // 4]["mode"] != 0:
+            m = (C.c_int * 4)(0, 0, 0, 0)
+            getattr(O, "orc_detect_multi_clpf_" + s)(P(f.Y, f.origin(0)), P(org.Y, org.origin(0)), x0, y0, w, h, org.sy, f.sy, m, bd - 8, 8, bd - 4 + (qp >> 4))
+            ws[b] = list(m)
+    stages["detect"] = (gs, ws)
+    # --- CDEF
+    nfb = ((w + 63) // 64) * ((h + 63) // 64)
+    pri = rng.integers(0, 16, (2, nfb)).astype(np.int8); sec = rng.integers(0, 4, (2, nfb)).astype(np.int8)
+    dpri = [tb.DevBuf.from_array(pri[k]) for k in range(2)]; dsec = [tb.DevBuf.from_array(sec[k]) for k in range(2)]
+    ddv = tb.DevBuf(nfb * 2 * 64 * 4)
+    dirs = np.zeros((nfb, 64), np.int32); vars_ = np.zeros((nfb, 64), np.int32)
+    for plane in range(3):
+        tb.check(tb.lib.tb_cdef_frame(drec.h, dscr.h, dbi.ptr, dpri[int(plane > 0)].ptr, dsec[int(plane > 0)].ptr, 5, 5, ddv.ptr, bd, plane))
+        src = f.full(plane)
+        dst = src.copy()
+        getattr(O, "orc_cdef_plane_" + s)(P(src, f.origin(plane)), P(dst, f.origin(plane)), f.stride(plane), w, h, P(bi), w // 4, 1, plane, P(pri[int(plane > 0)]),
+                                          P(sec[int(plane > 0)]), 5, 5, P(dirs), P(vars_), bd)
+        src[...] = dst
+    stages["cdef"] = (drec.download(), [f.plane(p).copy() for p in range(3)])
+    # --- CLPF
+    for plane, (fbl, strength) in enumerate(((6, 2), (4, 1), (4, 4))):
+        tb.check(tb.lib.tb_clpf_frame(drec.h, dscr.h, dbi.ptr, None, fbl, strength, bd, plane, qp))
+        src = f.full(plane)
+        dst = src.copy()
+        pw, ph = (w, h) if plane == 0 else (w // 2, h // 2)
+        getattr(O, "orc_clpf_plane_" + s)(P(src, f.origin(plane)), P(dst, f.origin(plane)), f.stride(plane), pw, ph, P(bi), w // 4, int(plane != 0), None, fbl, strength,
+                                          bd, plane, qp)
+        src[...] = dst
+    stages["clpf"] = (drec.download(), [f.plane(p).copy() for p in range(3)])
+    return stages
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+@pytest.mark.parametrize("dims", [(192, 136), (320, 192)])
+def test_frame_filters(tb, hbd, bd, dims):
+    rng = np.random.default_rng(112)
+    stages = run_filters(tb, rng, dims[0], dims[1], bd, hbd)
+    for name in ("deblock", "cdef", "clpf"):
+        got, want = stages[name]
+        for p in range(3):
+            assert (got[p] == want[p]).all(), (name, p, int((got[p] != want[p]).sum()))
+    gs, ws = stages["detect"]
+    assert (gs == ws).all()
+
+
+def test_frame_filters_1080p(tb):
+    """BASELINE size: the whole in-loop filter chain on a 1920x1080 frame, bit-exact against the oracle."""
+    rng = np.random.default_rng(113)
+    stages = run_filters(tb, rng, 1920, 1080, 8, 0, qp=35)
+    for name in ("deblock", "cdef", "clpf"):
+        got, want = stages[name]
+        for p in range(3):
+            assert (got[p] == want[p]).all(), (name, p)
+    assert (stages["detect"][0] == stages["detect"][1]).all()
+
+
+def test_me_1080p_properties(tb):
+    """Full-size, size-independent properties of the motion search on a 1920x1080 frame pair: (i) a pure global
+    translation of the reference is recovered exactly with zero SAD, (ii) results do not depend on batch order."""
+    rng = np.random.default_rng(114)
+    w, h, bd, hbd, esz = 1920, 1080, 8, 0, 1
+    href = HFrame(w, h, bd, hbd)
+    href.randomize(rng, smooth=False)
+    getattr(O, "orc_pad_plane_lbd")(P(href.Y, href.origin(0)), href.sy, w, h, 160, 160)
+    cur = HFrame(w, h, bd, hbd)
+    # cur(y,x) = ref(y+2, x-3)  <=>  MV = (-3*4, +2*4) quarter-pels
+    cur.y[...] = href.Y[160 + 2:160 + 2 + h, 160 - 3:160 - 3 + w]
+    drec = tb.Frame(w, h, esz); dref = tb.Frame(w, h, esz); dcur = tb.Frame(w, h, esz)
+    drec.upload(href.y, href.u, href.v); dcur.upload(cur.y, cur.u, cur.v)
+    tb.check(tb.lib.tb_create_reference_frame(dref.h, drec.h))
+    rptr, rst = dref.plane(0); optr, ost = dcur.plane(0)
+    blocks = [(x, y) for y in range(0, h - 15, 16) for x in range(0, w, 16)]
+    n = len(blocks)
+    items = np.zeros(n, tb.ME_ITEM)
+    for i, (x, y) in enumerate(blocks):
+        items[i] = (optr + (y * ost + x) * esz, rptr + (y * rst + x) * esz, ost, rst, x, y, 16, 16, 16, 0, 0, 0, 0, 0, 0, 0, 4.0)
+    cands = tb.DevBuf.from_array(np.zeros((1, 2), np.int16))
+    d_items = tb.DevBuf.from_array(items); d_out = tb.DevBuf(8 * n)
+    tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, cands.ptr, esz, bd, 0, 1, w, h, d_out.ptr))
+    r1 = d_out.download(tb.ME_RESULT, n)
+    assert (r1["mvx"] == -12).all() and (r1["mvy"] == 8).all()
+    bits_cost = O.orc_quote_mv_bits(8, -12)
+    assert (r1["cost"] == int(4.0 * bits_cost + 0.5)).all()
+    perm = rng.permutation(n)
+    d_items.upload(items[perm])
+    tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, cands.ptr, esz, bd, 0, 1, w, h, d_out.ptr))
+    r2 = d_out.download(tb.ME_RESULT, n)
+    assert (r2 == r1[perm]).all()

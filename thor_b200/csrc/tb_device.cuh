@@ -1,0 +1,1048 @@
+// tb_device.cuh — warp-level device routines of the Thor hot path for sm_100a.
+//
+// Execution model: ONE WARP PER WORK ITEM (coding / prediction / transform block, or one motion search).  Small
+// blocks are packed several-probes-per-warp inside the routines so all 32 lanes stay busy.  Samples are handled as
+// 32-bit words (4 x u8 or 2 x u16): VABSDIFF4.U8.ACC does the byte SAD, unaligned reference words are assembled
+// from two aligned loads with a funnel shift.  Integer arithmetic follows the reference bit for bit; the only
+// floating-point expression on the path (lambda * bits + 0.5, enc/encode_block.c:550) is evaluated with explicit
+// round-to-nearest double mul/add so it cannot be contracted into an FMA.
+//
+// Every routine cites the reference function whose results it reproduces (paths relative to /root/reference).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int ilog2(int x) { return 31 - __clz(x); }                       // common/simd.h:86
+__device__ __forceinline__ int iabs(int x) { return x < 0 ? -x : x; }
+__device__ __forceinline__ int iclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int sat_px(int v, int maxv) { return v < 0 ? 0 : (v > maxv ? maxv : v); }  // common/global.h:128
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(FULL, v); }
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// sum over aligned groups of `g` lanes (g power of two <= 32); every lane of a group gets the group's sum
+__device__ __forceinline__ uint32_t group_sum(uint32_t v, int g) {
+  for (int o = g >> 1; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 32-bit word access to sample rows.  PW = samples per word.
+// ---------------------------------------------------------------------------------------------------------------
+template <class S> struct Word { static constexpr int PW = 4 / (int)sizeof(S); };
+
+// 32-bit load from a pointer with only sample alignment: two aligned loads + funnel shift (SHF.R.W).
+__device__ __forceinline__ uint32_t ldw_any(const void *p) {
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+  unsigned sh = (unsigned)(a & 3) * 8;
+  uint32_t lo = q[0];
+  if (sh == 0) return lo;
+  return __funnelshift_r(lo, q[1], sh);
+}
+template <class S> __device__ __forceinline__ uint32_t word_sad(uint32_t a, uint32_t b) {
+  return sizeof(S) == 1 ? __vsadu4(a, b) : __vsadu2(a, b);
+}
+template <class S> __device__ __forceinline__ int word_px(uint32_t w, int i) {
+  return sizeof(S) == 1 ? (int)((w >> (8 * i)) & 0xff) : (int)((w >> (16 * i)) & 0xffff);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a1: SAD of a w x h block.  enc/encode_block.c:417-428 / enc/enc_kernels.c:36-81.
+// `o` must be 4-byte aligned with an even word pitch (original blocks always are); `r` arbitrary.
+// Lanes sub..sub+nl-1 of a group share the block; returns this lane's partial sum.
+// ---------------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, int rs, int w, int h, int sub, int nl) {
+  constexpr int PW = Word<S>::PW;
+  const int lw = ilog2(w / PW);  // words per row = 1 << lw
+  const int nwords = h << lw;
+  uint32_t acc = 0;
+  for (int wi = sub; wi < nwords; wi += nl) {
+    int row = wi >> lw, col = (wi & ((1 << lw) - 1)) * PW;
+    uint32_t a = *(const uint32_t *)(o + row * os + col);
+    uint32_t b = ldw_any(r + row * rs + col);
+    acc += word_sad<S>(a, b);
+  }
+  return acc;
+}
+// whole warp on one block
+template <class S> __device__ __forceinline__ uint32_t warp_sad(const S *o, int os, const S *r, int rs, int w, int h) {
+  return warp_sum(sad_partial<S>(o, os, r, rs, w, h, lane_id(), 32));
+}
+
+// SADs of up to 32 reference positions of the same block: lane i supplies the sample offset `roff` of position i
+// (i < n); lane i receives SAD i.  Blocks of fewer than 32 words are evaluated 32/words positions at a time.
+template <class S>
+__device__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+  constexpr int PW = Word<S>::PW;
+  const int lane = lane_id();
+  const int nwords = (w / PW) * h;
+  uint32_t out = 0;
+  if (nwords >= 32) {
+    for (int p = 0; p < n; p++) {
+      int off = __shfl_sync(FULL, roff, p);
+      uint32_t s = warp_sum(sad_partial<S>(o, os, r + off, rs, w, h, lane, 32));
+      if (lane == p) out = s;
+    }
+  } else {
+    const int g = 32 / nwords;  // positions per pass; nwords is a power of two in {2,4,8,16}
+    const int sub = lane & (nwords - 1), grp = lane / nwords;
+    for (int base = 0; base < n; base += g) {
+      int p = base + grp;
+      int off = __shfl_sync(FULL, roff, p & 31);
+      uint32_t s = (p < n) ? sad_partial<S>(o, os, r + off, rs, w, h, sub, nwords) : 0u;
+      s = group_sum(s, nwords);
+      uint32_t got = __shfl_sync(FULL, s, ((lane - base) * nwords) & 31);
+      if (lane >= base && lane < base + g && lane < n) out = got;
+    }
+  }
+  return out;
+}
+
+// a3: SSD.  enc/encode_block.c:455-465
+template <class S> __device__ __forceinline__ uint64_t warp_ssd(const S *a, int as, const S *b, int bs, int w, int h) {
+  uint64_t acc = 0;
+  const int lw = ilog2(w);
+  for (int p = lane_id(); p < (h << lw); p += 32) {
+    int row = p >> lw, col = p & (w - 1);
+    int d = (int)a[row * as + col] - (int)b[row * bs + col];
+    acc += (uint64_t)(uint32_t)(d * d);
+  }
+  return warp_sum64(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a6: MV helpers.  enc/encode_block.c:467-515, common/inter_prediction.c:51-63
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mv_len(int d) {
+  int a = iabs(d);
+  if (a < 1) return 2;
+  if (a < 2) return 4;
+  if (a < 4) return 5;
+  if (a < 36) return 5 + ((a - 4) >> 3) + 1;
+  return 10 + ((a - 36) >> 4) + 1;
+}
+__device__ __forceinline__ int quote_mv_bits(int dy, int dx) { return mv_len(dx) + mv_len(dy); }
+
+__device__ __forceinline__ void clip_mv(int &mvx, int &mvy, int ypos, int xpos, int fw, int fh, int bw, int bh, int sign) {
+  const int ext = 160 - 16;  // PADDING_Y - 16, common/global.h:62
+  int y = sign ? -mvy : mvy, x = sign ? -mvx : mvx;
+  if (ypos + y / 4 < -ext) y = 4 * (-ext - ypos);
+  if (ypos + y / 4 + bh > fh + ext) y = 4 * (fh + ext - ypos - bh);
+  if (xpos + x / 4 < -ext) x = 4 * (-ext - xpos);
+  if (xpos + x / 4 + bw > fw + ext) x = 4 * (fw + ext - xpos - bw);
+  // results are stored back into int16_t mv_t fields by the reference
+  mvy = (int)(int16_t)(sign ? -y : y);
+  mvx = (int)(int16_t)(sign ? -x : x);
+}
+// lambda * bits + 0.5 in ISO-C double arithmetic (no contraction), truncated like the reference's casts
+__device__ __forceinline__ uint32_t mv_cost(double lambda, int bits) {
+  return (uint32_t)(int)__dadd_rn(__dmul_rn(lambda, (double)bits), 0.5);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a7/a8: interpolation taps.  common/common_kernels.c:1905-1928
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ int8_t c_luma_taps[2][4][6] = {
+    {{0, 0, 64, 0, 0, 0}, {1, -7, 55, 19, -5, 1}, {1, -7, 38, 38, -7, 1}, {1, -5, 19, 55, -7, 1}},
+    {{0, 0, 64, 0, 0, 0}, {2, -10, 59, 17, -5, 1}, {1, -8, 39, 39, -8, 1}, {1, -5, 17, 59, -10, 2}}};
+__constant__ int8_t c_chroma_taps[8][4] = {{0, 64, 0, 0},  {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-4, 44, 28, -4},
+                                           {-4, 36, 36, -4}, {-4, 28, 44, -4}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
+
+// One luma sample at fractional position (xf,yf) in quarter-pels; ip = integer position.
+// common/inter_prediction.c:146-180.  bip = sequence-level enable_bipred value (0/1/2).
+template <class S> __device__ __forceinline__ int luma_sample(const S *ip, int is, int xf, int yf, int bip, int maxv) {
+  if (xf == 2 && yf == 2 && bip < 2) {
+    int s = (int)ip[-is] + ip[-is + 1] + ip[-1] + ip[2] + ip[is - 1] + ip[is + 2] + ip[2 * is] + ip[2 * is + 1] +
+            2 * ((int)ip[0] + ip[1] + ip[is] + ip[is + 1]);
+    return sat_px((s + 8) >> 4, maxv);
+  }
+  const int8_t *fv = c_luma_taps[bip ? 1 : 0][yf], *fh = c_luma_taps[bip ? 1 : 0][xf];
+  int sum;
+  if (xf == 0) {
+    sum = 0;
+#pragma unroll
+    for (int m = 0; m < 6; m++) sum += fv[m] * (int)ip[(m - 2) * is];
+    sum *= 64;
+  } else if (yf == 0) {
+    sum = 0;
+#pragma unroll
+    for (int n = 0; n < 6; n++) sum += fh[n] * (int)ip[n - 2];
+    sum *= 64;
+  } else {
+    sum = 0;
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+      int col = 0;
+#pragma unroll
+      for (int m = 0; m < 6; m++) col += fv[m] * (int)ip[(m - 2) * is + n - 2];
+      sum += fh[n] * col;
+    }
+  }
+  return sat_px((sum + 2048) >> 12, maxv);
+}
+// common/inter_prediction.c:94-114
+template <class S> __device__ __forceinline__ int chroma_sample(const S *ip, int is, int xf, int yf, int maxv) {
+  const int8_t *fh = c_chroma_taps[xf], *fv = c_chroma_taps[yf];
+  int sum = 0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    int row = 0;
+#pragma unroll
+    for (int n = 0; n < 4; n++) row += fh[n] * (int)ip[(m - 1) * is + n - 1];
+    sum += fv[m] * row;
+  }
+  return sat_px((sum + 2048) >> 12, maxv);
+}
+
+// Integer part + fraction of an MV with the reference's normative clamp (lower bounds use xpos on both axes).
+// common/inter_prediction.c:121-131 (luma, shift 2) and :71-81 (chroma, shift 3).
+__device__ __forceinline__ void split_mv(int mvx, int mvy, int sign, int shift, int pic_w, int pic_h, int xpos, int ypos, int w, int h,
+                                         int &hor_int, int &ver_int, int &xf, int &yf) {
+  int x = sign ? -mvx : mvx, y = sign ? -mvy : mvy;
+  int mask = (1 << shift) - 1;
+  yf = y & mask;
+  xf = x & mask;
+  ver_int = y >> shift;
+  hor_int = x >> shift;
+  ver_int = min(ver_int, pic_h - ypos);
+  ver_int = max(ver_int, -xpos - h);
+  hor_int = min(hor_int, pic_w - xpos);
+  hor_int = max(hor_int, -xpos - w);
+}
+
+// Whole-warp prediction of one block into dst (common/inter_prediction.c:117-183 / :65-115).
+template <class S>
+__device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int chroma, int bip, int pic_w,
+                            int pic_h, int xpos, int ypos, int bitdepth) {
+  int hi, vi, xf, yf;
+  split_mv(mvx, mvy, sign, chroma ? 3 : 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
+  const S *ip = ref + vi * rs + hi;
+  const int maxv = (1 << bitdepth) - 1, lw = ilog2(w);
+  for (int p = lane_id(); p < (h << lw); p += 32) {
+    int row = p >> lw, col = p & (w - 1);
+    const S *q = ip + row * rs + col;
+    int v;
+    if (xf == 0 && yf == 0) v = q[0];
+    else v = chroma ? chroma_sample<S>(q, rs, xf, yf, maxv) : luma_sample<S>(q, rs, xf, yf, bip, maxv);
+    dst[row * ds + col] = (S)v;
+  }
+}
+
+// SAD between the original block and the luma prediction at a fractional MV, without materialising the prediction
+// (the 8 half-pel + 8 quarter-pel probes of enc/encode_block.c:625-663).
+template <class S>
+__device__ uint32_t warp_sad_subpel(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w,
+                                    int pic_h, int xpos, int ypos, int bitdepth) {
+  int hi, vi, xf, yf;
+  split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
+  const S *ip = ref + vi * rs + hi;
+  const int maxv = (1 << bitdepth) - 1, lw = ilog2(w);
+  uint32_t acc = 0;
+  for (int p = lane_id(); p < (h << lw); p += 32) {
+    int row = p >> lw, col = p & (w - 1);
+    const S *q = ip + row * rs + col;
+    int v = (xf == 0 && yf == 0) ? (int)q[0] : luma_sample<S>(q, rs, xf, yf, bip, maxv);
+    acc += (uint32_t)iabs((int)o[row * os + col] - v);
+  }
+  return warp_sum(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a4: bilinear sub-pel SAD approximations.  enc/encode_block.c:174-283 and :286-414.
+// up = (a+b+1)>>1, dn = (a+b)>>1.  Results: acc[0..7] in the reference's comparison order.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int up2(int a, int b) { return (a + b + 1) >> 1; }
+__device__ __forceinline__ int dn2(int a, int b) { return (a + b) >> 1; }
+
+// order: top, down, right, left, tl, tr, br, bl
+template <class S>
+__device__ uint32_t warp_sad_fasthalf(const S *a, int as, const S *b, int bs, int w, int h, int &bx, int &by) {
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int lw = ilog2(w);
+  for (int p = lane_id(); p < (h << lw); p += 32) {
+    int row = p >> lw, col = p & (w - 1);
+    const S *r = b + row * bs + col;
+    int o = a[row * as + col];
+#define PX(dy, dx) ((int)r[(dy) * bs + (dx)])
+    int hL = up2(PX(0, -1), PX(0, 0)), hR = up2(PX(0, 0), PX(0, 1));
+    int hLu = up2(PX(-1, -1), PX(-1, 0)), hRu = up2(PX(-1, 0), PX(-1, 1));
+    int hLd = up2(PX(1, -1), PX(1, 0)), hRd = up2(PX(1, 0), PX(1, 1));
+    int vUm = up2(PX(-2, -1), PX(1, -1)), vU0 = up2(PX(-2, 0), PX(1, 0)), vUp = up2(PX(-2, 1), PX(1, 1));
+    int vDm = up2(PX(-1, -1), PX(2, -1)), vD0 = up2(PX(-1, 0), PX(2, 0)), vDp = up2(PX(-1, 1), PX(2, 1));
+    int wLu = up2(PX(-1, -2), PX(-1, 1)), wL0 = up2(PX(0, -2), PX(0, 1)), wLd = up2(PX(1, -2), PX(1, 1));
+    int wRu = up2(PX(-1, -1), PX(-1, 2)), wR0 = up2(PX(0, -1), PX(0, 2)), wRd = up2(PX(1, -1), PX(1, 2));
+    int ptl = dn2(dn2(dn2(vUm, vU0), dn2(wLu, wL0)), dn2(hLu, hL));
+    int ptr = dn2(dn2(dn2(vU0, vUp), dn2(wR0, wRu)), dn2(hRu, hR));
+    int pbl = dn2(dn2(dn2(vD0, vDm), dn2(wL0, wLd)), dn2(hLd, hL));
+    int pbr = dn2(dn2(dn2(vD0, vDp), dn2(wR0, wRd)), dn2(hR, hRd));
+    acc[0] += iabs(o - up2(PX(0, 0), PX(-1, 0)));
+    acc[1] += iabs(o - up2(PX(0, 0), PX(1, 0)));
+    acc[2] += iabs(o - hR);
+    acc[3] += iabs(o - hL);
+    acc[4] += iabs(o - ptl);
+    acc[5] += iabs(o - ptr);
+    acc[6] += iabs(o - pbr);
+    acc[7] += iabs(o - pbl);
+#undef PX
+  }
+  const int8_t xs[8] = {0, 0, 2, -2, -2, 2, 2, -2}, ys[8] = {-2, 2, 0, 0, -2, -2, 2, 2};
+  uint32_t best = 0;
+  int bi = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t s = warp_sum(acc[k]);
+    if (k == 0 || s < best) { best = s; bi = k; }
+  }
+  bx = xs[bi];
+  by = ys[bi];
+  return best;
+}
+
+// order: top, tl, tr, left, right, bl, down, br.  fx, fy: half-pel offset found so far (selects the formula set)
+template <class S>
+__device__ uint32_t warp_sad_fastquarter(const S *o, int os, const S *r, int rs, int w, int h, int fx, int fy, int &bx, int &by) {
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int lw = ilog2(w);
+  for (int p = lane_id(); p < (h << lw); p += 32) {
+    int row = p >> lw, col = p & (w - 1);
+    const S *q = r + row * rs + col;
+    int org = o[row * os + col];
+    int a = q[0], d = q[1], f = q[rs], e = q[rs + 1];
+    int vtop, vtl, vtr, vleft, vright, vbl, vdown, vbr;
+    if (fx & fy) {
+      int ad = up2(a, d), de = up2(d, e), af = up2(a, f), fe = up2(f, e);
+      vtl = dn2(ad, af); vtop = dn2(de, a); vtr = dn2(ad, de); vleft = dn2(ad, f);
+      vright = dn2(ad, e); vbl = dn2(af, fe); vdown = dn2(de, f); vbr = dn2(de, fe);
+    } else if (fx) {
+      int b = q[-rs], c = q[-rs + 1];
+      int ad = up2(a, d), de = up2(d, e), dc = up2(d, c), af = up2(a, f), ab = up2(a, b);
+      vtl = dn2(ad, ab); vtop = dn2(dc, a); vtr = dn2(ad, dc); vleft = dn2(ad, a);
+      vright = dn2(ad, d); vbl = dn2(ad, af); vdown = dn2(af, d); vbr = dn2(ad, de);
+    } else if (fy) {
+      int g = q[rs - 1], hh = q[-1];
+      int ad = up2(a, d), af = up2(a, f), fe = up2(f, e), ah = up2(a, hh), gf = up2(g, f);
+      vtl = dn2(ah, af); vtop = dn2(af, a); vtr = dn2(ad, af); vleft = dn2(gf, a);
+      vright = dn2(ad, f); vbl = dn2(af, gf); vdown = dn2(af, f); vbr = dn2(af, fe);
+    } else {
+      int b = q[-rs], hh = q[-1];
+      int ad = up2(a, d), af = up2(a, f), ah = up2(a, hh), ab = up2(a, b);
+      vtl = dn2(ah, ab); vtop = dn2(ab, a); vtr = dn2(ad, ab); vleft = dn2(ah, a);
+      vright = dn2(ad, a); vbl = dn2(ah, af); vdown = dn2(af, a); vbr = dn2(af, ad);
+    }
+    acc[0] += iabs(org - vtop);   acc[1] += iabs(org - vtl);
+    acc[2] += iabs(org - vtr);    acc[3] += iabs(org - vleft);
+    acc[4] += iabs(org - vright); acc[5] += iabs(org - vbl);
+    acc[6] += iabs(org - vdown);  acc[7] += iabs(org - vbr);
+  }
+  const int8_t xs[8] = {0, -1, 1, -1, 1, -1, 0, 1}, ys[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  uint32_t best = 0;
+  int bi = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t s = warp_sum(acc[k]);
+    if (k == 0 || s < best) { best = s; bi = k; }
+  }
+  bx = xs[bi];
+  by = ys[bi];
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a5: motion_estimate.  enc/encode_block.c:517-711.  One warp runs one search; every stage evaluates its probes
+// in parallel across lanes and picks the winner with the reference's sequential tie rule (first strict minimum).
+// ---------------------------------------------------------------------------------------------------------------
+struct MeCtx {
+  int size, width, height, sign, s, xpos, ypos, fw, fh, bitdepth, speed, bip;
+  int mvpx, mvpy;
+  double lambda;
+};
+
+// first-minimum over lanes < n of key (cost); returns winning lane (or -1 if n == 0) and its cost
+__device__ __forceinline__ int warp_first_min(uint32_t cost, int n, uint32_t &best) {
+  uint32_t c = lane_id() < n ? cost : 0xffffffffu;
+  uint32_t m = __reduce_min_sync(FULL, c);
+  unsigned who = __ballot_sync(FULL, c == m && lane_id() < n);
+  best = m;
+  return who ? __ffs(who) - 1 : -1;
+}
+
+template <class S>
+__device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs, const MeCtx &c, int mvcx, int mvcy, const int16_t *cand,
+                                     int ncand, int &out_mvx, int &out_mvy, uint32_t &out_cost) {
+  const int lane = lane_id();
+  const int s = c.s, shift = c.bitdepth - 8;
+  uint32_t min_sad = 1u << 31;  // MAX_UINT32, common/global.h:63
+  int optx = 0, opty = 0;
+  int refx = ((mvcx + 2) >> 2) << 2, refy = ((mvcy + 2) >> 2) << 2;
+  refx = (int)(int16_t)refx;
+  refy = (int)(int16_t)refy;
+
+  // ---- telescope search: 5x5 grids at steps 32,16,8,4 quarter-pels (:531-561)
+  if ((c.size == 16 && c.bip) || c.speed == 0) {
+    for (int step = 32; step >= 4; step >>= 1) {
+      // sequential visiting order: k (y) outer, l (x) inner; the centre is skipped for step < 32
+      int idx = lane;
+      if (step < 32 && idx >= 12) idx++;  // 24 probes, hole at grid index 12
+      int n = step < 32 ? 24 : 25;
+      int k = (idx / 5 - 2) * step, l = (idx % 5 - 2) * step;
+      int cx = (int)(int16_t)(refx + l), cy = (int)(int16_t)(refy + k);
+      clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
+      uint32_t sad;
+      if (step == 32 && c.size == 16 && c.speed == 1) {
+        // widesad at every grid point: best of x offsets -3,-1,0,1,3 (first minimum), enc/encode_block.c:430-453
+        const int offs[5] = {-3, -1, 0, 1, 3};
+        uint32_t b = 0xffffffffu;
+        int bxo = 0;
+        int base = s * (cx >> 2) + s * (cy >> 2) * rs;
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+          uint32_t v = multi_sad<S>(orig, os, ref, rs, c.width, c.height, base + offs[t], n);
+          if (v < b) { b = v; bxo = offs[t]; }
+        }
+        sad = b;
+        cx = (int)(int16_t)(cx + (s * bxo << 2));
+      } else {
+        sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+      }
+      uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
+      uint32_t best;
+      int w = warp_first_min(cost, n, best);
+      if (best < min_sad) {
+        min_sad = best;
+        optx = __shfl_sync(FULL, cx, w);
+        opty = __shfl_sync(FULL, cy, w);
+      }
+      refx = optx;
+      refy = opty;
+    }
+  }
+
+  // ---- candidate search (:564-581); 16x16 blocks use the five-position wide SAD
+  for (int base = 0; base < ncand; base += 32) {
+    int n = min(32, ncand - base);
+    int cx = 0, cy = 0;
+    if (lane < n) {
+      cx = (int)(int16_t)(cand[2 * (base + lane)] << 2);
+      cy = (int)(int16_t)(cand[2 * (base + lane) + 1] << 2);
+    }
+    clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
+    uint32_t sad;
+    int pos = s * (cx >> 2) + s * (cy >> 2) * rs;
+    if (c.size == 16) {
+      const int offs[5] = {-3, -1, 0, 1, 3};
+      uint32_t b = 0xffffffffu;
+      int bxo = 0;
+#pragma unroll
+      for (int t = 0; t < 5; t++) {
+        uint32_t v = multi_sad<S>(orig, os, ref, rs, c.width, c.height, pos + offs[t], n);
+        if (v < b) { b = v; bxo = offs[t]; }
+      }
+      sad = b;
+      cx = (int)(int16_t)(cx + (s * bxo << 2));
+    } else {
+      sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, pos, n);
+    }
+    uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
+    uint32_t best;
+    int w = warp_first_min(cost, n, best);
+    if (w >= 0 && best < min_sad) {
+      min_sad = best;
+      optx = __shfl_sync(FULL, cx, w);
+      opty = __shfl_sync(FULL, cy, w);
+    }
+  }
+  refx = optx;
+  refy = opty;
+
+  // ---- hexagon refinement (:583-616): visit dir = start..end cyclically; first strict minimum wins
+  {
+    const int maxsteps = (c.size <= 16 || c.speed == 0) ? 6 : 0;
+    int start = 0, end = 5;
+    for (int step = 1; step < maxsteps; step++) {
+      const int diy[6] = {1, 2, 1, -1, -2, -1}, dix[6] = {-1, 0, 1, 1, 0, -1};
+      int n = ((end - start + 6) % 6) + 1;  // number of directions visited
+      int dir = (start + lane) % 6;
+      int cx = (int)(int16_t)(refx + diy[dir] * 4), cy = (int)(int16_t)(refy + dix[dir] * 4);
+      clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
+      uint32_t sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+      uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
+      uint32_t best;
+      int w = warp_first_min(cost, n, best);
+      int best_dir = -1;
+      if (best < min_sad) {
+        min_sad = best;
+        optx = __shfl_sync(FULL, cx, w);
+        opty = __shfl_sync(FULL, cy, w);
+        best_dir = (start + w) % 6;
+      }
+      refx = optx;
+      refy = opty;
+      start = best_dir ? best_dir - 1 : 5;
+      end = start + 2;
+      end -= (end >= 6) * 6;
+      if (best_dir < 0) break;
+    }
+  }
+
+  int ydh = 0, xdh = 0, ydq = 0, xdq = 0;
+  uint32_t cmin = min_sad;
+  if (c.speed == 0) {
+    // ---- true half-pel then quarter-pel probes (:625-663)
+    const int8_t hm[9] = {0, 0, -2, 2, 0, -2, -2, 2, 2}, hn[9] = {0, -2, 0, 0, 2, -2, 2, -2, 2};
+    const int8_t qm[9] = {0, 0, -1, 1, 0, -1, -1, 1, 1}, qn[9] = {0, -1, 0, 0, 1, -1, 1, -1, 1};
+    for (int i = 1; i <= 8; i++) {
+      int cy = (int)(int16_t)(refy + hm[i]), cx = (int)(int16_t)(refx + hn[i]);
+      uint32_t sad = warp_sad_subpel<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+      uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
+      if (cost < cmin) { cmin = cost; ydh = hm[i]; xdh = hn[i]; }
+    }
+    optx = (int)(int16_t)(optx + xdh);
+    opty = (int)(int16_t)(opty + ydh);
+    for (int i = 1; i <= 8; i++) {
+      int cy = (int)(int16_t)(opty + qm[i]), cx = (int)(int16_t)(optx + qn[i]);
+      uint32_t sad = warp_sad_subpel<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+      uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
+      if (cost < cmin) { cmin = cost; ydq = qm[i]; xdq = qn[i]; }
+    }
+  } else {
+    // ---- bilinear approximations (:664-703)
+    int rx = (int)(int16_t)(refx * s), ry = (int)(int16_t)(refy * s);
+    int spx, spy;
+    uint32_t sad = warp_sad_fasthalf<S>(orig, os, ref + (rx >> 2) + (ry >> 2) * rs, rs, c.width, c.height, spx, spy);
+    uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(ry + s * spy - c.mvpy, rx + s * spx - c.mvpx));
+    if (cost < cmin) { cmin = cost; xdh = s * spx; ydh = s * spy; }
+    spx = xdh;
+    spy = ydh;
+    rx = (int)(int16_t)(optx + s * spx);
+    ry = (int)(int16_t)(opty + s * spy);
+    optx = (int)(int16_t)(optx + xdh);
+    opty = (int)(int16_t)(opty + ydh);
+    int qx, qy;
+    sad = warp_sad_fastquarter<S>(orig, os, ref + s * (rx >> 2) + s * (ry >> 2) * rs, rs, c.width, c.height, spx, spy, qx, qy);
+    cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(ry + s * qy - c.mvpy, rx + s * qx - c.mvpx));
+    if (cost < cmin) { cmin = cost; xdq = s * qx; ydq = s * qy; }
+  }
+  out_mvx = (int)(int16_t)(optx + xdq);
+  out_mvy = (int)(int16_t)(opty + ydq);
+  out_cost = cmin < min_sad ? cmin : min_sad;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a10/a11: integer DCT.  common/transform.c:245-308 (forward), :411-494 (inverse).
+// Matrix M_N[i][j] = +-T[fold((2j+1)*i*32/N mod 128)] (HEVC core transform); kept in constant memory because every
+// lane of a warp reads the same coefficient in the inner loops (broadcast).
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ int8_t c_T[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                               61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+__device__ __forceinline__ int dct_coef(int lN, int i, int j) {  // N = 1 << lN
+  int m = ((2 * j + 1) * i * (32 >> lN)) & 127;
+  if (m > 64) m = 128 - m;
+  return m > 32 ? -(int)c_T[64 - m] : (int)c_T[m];
+}
+
+// per-warp scratch: in[32*33] + tmp[16*33] int16 (padded pitch 33 -> conflict-free column access)
+struct TxScratch {
+  int16_t in[32 * 33];
+  int16_t tmp[16 * 33];
+  int16_t cq[256];
+  int16_t rc[256];
+};
+
+// Forward transform of `size` x `size` residual (row pitch = size, in global or shared memory) into sc.rc-style
+// compact qsize x qsize output `coef` (pitch qsize).  Returns nothing; all lanes participate.
+__device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, int fast, int bitdepth, TxScratch &sc, int16_t *coef) {
+  const int lane = lane_id();
+  int size1 = size, scale = 1;
+  if (size > (32 >> fast)) { size1 = 32 >> fast; scale = size / size1; }
+  const int l1 = ilog2(size1), qsize = min(size, 16);
+  // load (with box-sum down-scaling for large blocks, saturating like common/transform.c:261-278)
+  for (int p = lane; p < size1 * size1; p += 32) {
+    int i = p >> l1, j = p & (size1 - 1);
+    int v;
+    if (scale == 1) v = block[i * bpitch + j];
+    else {
+      int sum = 0;
+      for (int m = 0; m < scale; m++)
+        for (int n = 0; n < scale; n++) sum = iclip(sum + block[(i * scale + m) * bpitch + j * scale + n], -16384, 16383);
+      v = sum;
+    }
+    sc.in[i * 33 + j] = (int16_t)v;
+  }
+  __syncwarp();
+  const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
+  const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
+  // 1st dimension: tmp[i][j] = (sum_k M[i][k] * in[j][k] + add1) >> shift1, i < qsize, j < size1
+  for (int p = lane; p < qsize * size1; p += 32) {
+    int i = p >> l1, j = p & (size1 - 1);
+    int sum = 0;
+    for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.in[j * 33 + k];
+    sc.tmp[i * 33 + j] = (int16_t)((sum + add1) >> shift1);
+  }
+  __syncwarp();
+  // 2nd dimension: coef[i][j] = (sum_k M[i][k] * tmp[j][k] + add2) >> shift2, i, j < qsize
+  const int lq = ilog2(qsize);
+  for (int p = lane; p < qsize * qsize; p += 32) {
+    int i = p >> lq, j = p & (qsize - 1);
+    int sum = 0;
+    for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.tmp[j * 33 + k];
+    coef[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
+  }
+  __syncwarp();
+}
+
+// Inverse transform from compact qsize x qsize coefficients (pitch cpitch) to a size x size residual block
+// (pitch bpitch; size <= 32 core, 64/128 by sample replication, common/transform.c:467-494).
+__device__ void warp_inv_transform(const int16_t *coef, int cpitch, int size, int bitdepth, TxScratch &sc, int16_t *block, int bpitch) {
+  const int lane = lane_id();
+  const int core = min(size, 32), rep = size / core, lc = ilog2(core), qsize = min(size, 16);
+  const int shift2 = 20 - bitdepth, add2 = 1 << (shift2 - 1);
+  // 1st dimension: tmp[i][j] = clip16((sum_k M[k][j] * coef[k][i] + 64) >> 7), i < qsize, j < core
+  for (int p = lane; p < qsize * core; p += 32) {
+    int i = p >> lc, j = p & (core - 1);
+    int sum = 0;
+    for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)coef[k * cpitch + i];
+    sc.tmp[i * 33 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+  }
+  __syncwarp();
+  // 2nd dimension: out[i][j] = clip16((sum_k M[k][j] * tmp[k][i] + add2) >> shift2), i, j < core
+  for (int p = lane; p < core * core; p += 32) {
+    int i = p >> lc, j = p & (core - 1);
+    int sum = 0;
+    for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)sc.tmp[k * 33 + i];
+    int v = iclip((sum + add2) >> shift2, -32768, 32767);
+    if (rep == 1) block[i * bpitch + j] = (int16_t)v;
+    else
+      for (int m = 0; m < rep; m++)
+        for (int n = 0; n < rep; n++) block[(i * rep + m) * bpitch + j * rep + n] = (int16_t)v;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a12: quantize.  enc/encode_block.c:84-160.  coef: compact qsize x qsize (raster).  The level_mode hysteresis is a
+// two-state machine along the zig-zag scan; each lane simulates its 8-position chunk for both start states, a warp
+// scan composes the state maps, then each lane replays its chunk from the true start state.
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ uint16_t c_quant[6] = {26214, 23302, 20560, 18396, 16384, 14564};  // common/common_tables.c:72
+__constant__ uint16_t c_dequant[6] = {40, 45, 51, 57, 64, 72};                  // common/common_tables.c:73
+
+// scan index of raster position (r,c) in an n x n zig-zag (common/common_tables.c:29-62), closed form
+__device__ __forceinline__ int zigzag_index(int r, int c, int n) {
+  int d = r + c;
+  int before = d < n ? d * (d + 1) / 2 : n * n - (2 * n - 1 - d) * (2 * n - d) / 2;  // samples on earlier diagonals
+  int lo = d < n ? 0 : d - (n - 1);  // smallest row index on this diagonal
+  // odd diagonals run top-right -> bottom-left (row ascending), even ones the other way
+  int k = (d & 1) ? (r - lo) : ((d < n ? d : n - 1) - r);
+  return before + k;
+}
+
+__device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc) {
+  const int lane = lane_id();
+  const int intra = (coeff_type >> 1) & 1, qsize = min(size, 16), nq = qsize * qsize, lq = ilog2(qsize);
+  const int64_t scale = c_quant[qp % 6];
+  const int shift2 = 21 - ilog2(size) + qp / 6;
+  int *scan = (int *)sc.in;  // reuse: 256 ints of scan-ordered coefficients (sc.in holds 32*33 int16 = 2112 B)
+  for (int p = lane; p < nq; p += 32) scan[zigzag_index(p >> lq, p & (qsize - 1), qsize)] = coef[p];
+  __syncwarp();
+  // last_pos: highest scan position whose level (with the "last" offset) is non-zero
+  const int64_t off_last = (int64_t)(intra ? 38 : -26) << (shift2 - 8);
+  int last = -1;
+  for (int p = lane; p < nq; p += 32) {
+    int64_t l64 = (int64_t)iabs(scan[p]) * scale + off_last;
+    int lev = (int)((l64 > 0 ? l64 : -l64) >> shift2);
+    if (lev) last = p;  // p ascending per lane -> keeps the lane's maximum
+  }
+  last = (int)__reduce_max_sync(FULL, (unsigned)(last + 1)) - 1;
+  const int off0 = intra ? 102 : 51, off1 = intra ? 115 : 90;
+  // chunk = 8 consecutive scan positions per lane (256/32)
+  const int per = (nq + 31) / 32, p0 = lane * per;
+  unsigned map = 0;  // bit s = end state when the chunk is entered in state s
+  for (int st = 0; st < 2; st++) {
+    int mode = st;
+    for (int t = 0; t < per; t++) {
+      int p = p0 + t;
+      if (p > last || p >= nq) break;
+      int64_t ac = scale * iabs(scan[p]);
+      int level0 = (int)(ac >> shift2);
+      int off = ((level0 > (1 - mode)) ? off1 : off0) << (shift2 - 8);
+      int level = (int)((ac + off) >> shift2);
+      if (mode) { if (level == 0) mode = 0; }
+      else if (level > 1) mode = 1;
+    }
+    map |= (unsigned)mode << st;
+  }
+  // inclusive scan of map composition: state after chunk L given state before chunk 0
+  // compose(f then g)(s) = g(f(s)); represent as 2-bit maps
+  unsigned incl = map;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned prev = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) {
+      unsigned r0 = (incl >> ((prev >> 0) & 1)) & 1, r1 = (incl >> ((prev >> 1) & 1)) & 1;
+      incl = r0 | (r1 << 1);
+    }
+  }
+  unsigned before = __shfl_up_sync(FULL, incl, 1);
+  int mode = lane == 0 ? 1 : (int)((before >> 1) & 1);  // initial level_mode = 1
+  int cbp = 0;
+  for (int t = 0; t < per; t++) {
+    int p = p0 + t;
+    if (p >= nq) break;
+    int q = 0;
+    if (p <= last) {
+      int cc = scan[p];
+      int64_t ac = scale * iabs(cc);
+      int level0 = (int)(ac >> shift2);
+      int off = ((level0 > (1 - mode)) ? off1 : off0) << (shift2 - 8);
+      int level = (int)((ac + off) >> shift2);
+      q = cc < 0 ? -level : level;
+      cbp |= level != 0;
+      if (mode) { if (level == 0) mode = 0; }
+      else if (level > 1) mode = 1;
+    }
+    sc.tmp[p] = (int16_t)q;  // scan order
+  }
+  __syncwarp();
+  for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[zigzag_index(p >> lq, p & (qsize - 1), qsize)];
+  __syncwarp();
+  return __any_sync(FULL, cbp);
+}
+
+// a13: dequantize.  common/common_block.c:45-73 (no weight matrix).  compact in, compact out (pitch qsize)
+__device__ void warp_dequantize(const int16_t *cq, int16_t *rc, int qp, int size) {
+  const int lshift = qp / 6, qsize = min(size, 16), rshift = ilog2(size) - 1;
+  const int64_t scale = c_dequant[qp % 6];
+  const int64_t add = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
+  for (int p = lane_id(); p < qsize * qsize; p += 32) {
+    int c = cq[p];
+    rc[p] = lshift >= rshift ? (int16_t)((c * scale) << (lshift - rshift)) : (int16_t)((c * scale + add) >> (rshift - lshift));
+  }
+  __syncwarp();
+}
+
+// a14: calc_cbp_simd semantics.  enc/enc_kernels.c:828-909 (int16 column sums; 4x4: odd + |even| per pair)
+__device__ int warp_calc_cbp(const int16_t *block, int size, int thr) {
+  const int lane = lane_id();
+  int hit = 0;
+  int16_t col = 0;
+  if (lane < size)
+    for (int i = 0; i < size; i++) col = (int16_t)(col + block[i * size + lane]);
+  int16_t a = (int16_t)(col < 0 ? -col : col);
+  if (size == 4) {
+    int odd = __shfl_down_sync(FULL, (int)col, 1);
+    if (lane < 4 && !(lane & 1)) hit = (odd + (int)a) > thr;
+  } else if (lane < size)
+    hit = a > (int16_t)thr;
+  return __any_sync(FULL, hit);
+}
+
+// common/common_kernels.c:127-161
+__device__ int warp_check_nz_area(const int16_t *coeff, int size) {
+  const int qs = min(size, 16), lq = ilog2(qs);
+  int ndc = 0, n4 = 0, n8 = 0;
+  for (int p = lane_id(); p < qs * qs; p += 32) {
+    int i = p >> lq, j = p & (qs - 1);
+    if (coeff[i * size + j]) {
+      if (i || j) ndc = 1;
+      if (i >= 4 || j >= 4) n4 = 1;
+      if (i >= 8 || j >= 8) n8 = 1;
+    }
+  }
+  ndc = __any_sync(FULL, ndc);
+  n4 = __any_sync(FULL, n4);
+  n8 = __any_sync(FULL, n8);
+  if (size == 4) return ndc ? 3 : 0;
+  if (size == 8) return !ndc ? 0 : (!n4 ? 1 : 2);
+  return !ndc ? 0 : (!n4 ? 1 : (!n8 ? 2 : 3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a15: intra prediction.  common/intra_prediction.c:57-428.  left/top hold 2*size samples (shared memory).
+// ---------------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ void warp_make_top_and_left(S *left, S *top, S &top_left, const S *rec_frame, int fstride, const S *rblock, int rbstride, int i, int j,
+                                       int ypos, int xpos, int size, int cb_upright, int cb_downleft, int tb_split, int bitdepth) {
+  const int lane = lane_id();
+  const S mid = (S)(128 << (bitdepth - 8));
+  int downleft, upright;
+  if (!tb_split) { downleft = cb_downleft; upright = cb_upright; }
+  else {
+    downleft = (j == 0 && (i == 0 || cb_downleft)) ? 1 : 0;
+    upright = (j == 0 || (i == 0 && cb_upright)) ? 1 : 0;
+  }
+  const int leftlen = downleft ? size + 1 : size, toplen = upright ? size + 1 : size;
+  S tl = mid;
+  if (ypos + i == 0) {
+    for (int k = lane; k < 2 * size; k += 32) top[k] = mid;
+  } else {
+    const S *src = (i == 0) ? rec_frame - fstride + j : rblock - rbstride;
+    S val = src[toplen - 1];
+    for (int k = lane; k < 2 * size; k += 32) top[k] = k < toplen ? src[k] : (k >= size ? val : src[k]);
+    if (xpos > 0) tl = (i == 0) ? rec_frame[-fstride + j - 1] : ((j > 0) ? rblock[-rbstride - 1] : rec_frame[(i - 1) * fstride - 1]);
+    else tl = src[0];
+  }
+  if (xpos + j == 0) {
+    for (int k = lane; k < 2 * size; k += 32) left[k] = mid;
+  } else {
+    const S *base = (j == 0) ? rec_frame + i * fstride - 1 : rblock - 1;
+    const int st = (j == 0) ? fstride : rbstride;
+    S val = base[(leftlen - 1) * st];
+    for (int k = lane; k < 2 * size; k += 32) left[k] = k < leftlen ? base[k * st] : (k >= size ? val : base[k * st]);
+  }
+  __syncwarp();
+  if (ypos + i == 0) tl = left[0];
+  top_left = tl;
+}
+
+template <class S> __device__ __forceinline__ int f121(const S *in, int k, int len) {
+  int a = in[k > 0 ? k - 1 : 0], b = in[k], c = in[k < len - 1 ? k + 1 : len - 1];
+  return (a + 2 * b + c + 2) >> 2;
+}
+template <class S> __device__ __forceinline__ int f12221(const S *in, int k, int len) {  // planar pre-filter, int16 in the reference
+  int a = in[max(k - 2, 0)], b = in[max(k - 1, 0)], c = in[min(k + 1, len - 1)], d = in[min(k + 2, len - 1)];
+  return (int)(int16_t)(a + 2 * b + 2 * in[k] + 2 * c + d);
+}
+
+// filt: scratch of 4*size+1 samples for the 1-2-1 filtered arrays
+template <class S>
+__device__ void warp_intra_pred(const S *left, const S *top, S top_left, int ypos, int xpos, int size, S *pblock, int pstride, int mode, int bitdepth,
+                                S *filt) {
+  const int lane = lane_id(), ls = ilog2(size), maxv = (1 << bitdepth) - 1;
+  if (mode < 0 || mode > 9) mode = 0;
+  S *tF = filt, *lF = filt + 2 * size;
+  int tlF = 0, dc = 0;
+  int16_t ptlF = 0;
+  if (mode == 4 || mode == 7 || mode == 8) {
+    for (int k = lane; k < size; k += 32) { tF[k] = (S)f121<S>(top, k, size); lF[k] = (S)f121<S>(left, k, size); }
+    tlF = (int)(S)((2 * (int)top_left + left[0] + top[0] + 2) >> 2);
+  } else if (mode == 5 || mode == 6) {
+    for (int k = lane; k < 2 * size; k += 32) tF[k] = (S)f121<S>(top, k, 2 * size);
+  } else if (mode == 9) {
+    for (int k = lane; k < 2 * size; k += 32) lF[k] = (S)f121<S>(left, k, 2 * size);
+  } else if (mode == 0) {
+    const S *l = xpos != 0 ? left : top, *t = ypos != 0 ? top : left;
+    unsigned sum = 0;
+    for (int k = lane; k < size; k += 32) sum += (unsigned)t[k] + (unsigned)l[k];
+    sum = warp_sum(sum);
+    dc = (int)((sum + (unsigned)size) / (2u * (unsigned)size));
+  } else if (mode == 1) {
+    ptlF = (int16_t)(left[1] + 2 * left[0] + 2 * (int)top_left + 2 * top[0] + top[1]);
+  }
+  __syncwarp();
+  for (int p = lane; p < size * size; p += 32) {
+    int i = p >> ls, j = p & (size - 1), v, d;
+    switch (mode) {
+      case 0: v = dc; break;
+      case 1: v = sat_px((f12221<S>(left, i, size) + f12221<S>(top, j, size) - ptlF + 4) / 8, maxv); break;
+      case 2: v = left[i]; break;
+      case 3: v = top[j]; break;
+      case 4: d = i - j; v = d > 0 ? lF[d - 1] : (d == 0 ? tlF : tF[-d - 1]); break;
+      case 5: v = tF[i + j + 1]; break;
+      case 6: d = i + 2 * j; v = (d & 1) ? tF[(d + 1) / 2] : (tF[d / 2] + tF[d / 2 + 1]) >> 1; break;
+      case 7:
+        d = i - 2 * j;
+        if (d > 1) v = lF[d - 2];
+        else if (d == 1) v = tlF;
+        else if (d == 0) v = (tlF + tF[0]) >> 1;
+        else v = (d & 1) ? tF[(-d) / 2] : (tF[(-d) / 2] + tF[(-d) / 2 - 1]) >> 1;
+        break;
+      case 8:
+        d = 2 * i - j;
+        if (d < -1) v = tF[-d - 2];
+        else if (d == -1) v = tlF;
+        else if (d == 0) v = (tlF + lF[0]) >> 1;
+        else v = (d & 1) ? lF[d / 2] : (lF[d / 2] + lF[d / 2 - 1]) >> 1;
+        break;
+      default: d = 2 * i + j; v = (d & 1) ? lF[(d + 1) / 2] : (lF[d / 2] + lF[d / 2 + 1]) >> 1; break;
+    }
+    pblock[i * pstride + j] = (S)v;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a16: chroma-from-luma.  common/common_block.c:347-427 (4:2:0, sub = 1)
+// ---------------------------------------------------------------------------------------------------------------
+template <class S> __device__ void warp_cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride, int sub, int bitdepth) {
+  const int lane = lane_id(), nc = n >> sub, lognc = ilog2(nc), cs = cstride >> sub, maxv = (1 << bitdepth) - 1, ln = ilog2(n);
+  int64_t sq = 0;
+  for (int p = lane; p < n * n; p += 32) {
+    int i = p >> ln, j = p & (n - 1);
+    int d = (int)ry[i * stride + j] - (int)y[i * n + j];
+    sq += d * d;
+  }
+  sq = (int64_t)warp_sum64((uint64_t)sq);
+  if ((sq >> (2 * ln)) <= (64 << 2 * (bitdepth - 8))) return;
+  int64_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ysum usum vsum yy yu yv uu vv
+  for (int p = lane; p < nc * nc; p += 32) {
+    int i = p >> lognc, j = p & (nc - 1);
+    int us = u[i * cs + j], vs = v[i * cs + j];
+    int ys = sub ? ((int)y[(2 * i) * n + 2 * j] + y[(2 * i) * n + 2 * j + 1] + y[(2 * i + 1) * n + 2 * j] + y[(2 * i + 1) * n + 2 * j + 1] + 2) >> 2
+                 : (int)y[i * cstride + j];
+    acc[0] += ys; acc[1] += us; acc[2] += vs;
+    acc[3] += ys * ys; acc[4] += ys * us; acc[5] += ys * vs; acc[6] += us * us; acc[7] += vs * vs;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = (int64_t)warp_sum64((uint64_t)acc[k]);
+  const int sh = lognc * 2;
+  int64_t ysum = acc[0], usum = acc[1], vsum = acc[2];
+  int64_t ssyy = acc[3] - (ysum * ysum >> sh), ssuu = acc[6] - (usum * usum >> sh), ssvv = acc[7] - (vsum * vsum >> sh);
+  int64_t ssyu = acc[4] - (ysum * usum >> sh), ssyv = acc[5] - (ysum * vsum >> sh);
+  if (!ssyy) return;
+  for (int c = 0; c < 2; c++) {
+    int64_t sc = c ? ssyv : ssyu, scc = c ? ssvv : ssuu, csum = c ? vsum : usum;
+    S *dst = c ? v : u;
+    if (!(sc * sc * 2 > ssyy * scc)) continue;
+    int64_t a64 = (sc << 16) / ssyy;
+    int64_t b64 = ((csum << 16) - a64 * ysum) >> sh;
+    int64_t lim = (int64_t)1 << (31 - bitdepth);
+    int32_t a = (int32_t)(a64 < -lim ? -lim : (a64 > lim ? lim : a64));
+    int64_t bb = b64 + (1 << 15);
+    int64_t lo = -((int64_t)1 << 31), hi = ((int64_t)1 << 31) - 1;
+    int32_t b = (int32_t)(bb < lo ? lo : (bb > hi ? hi : bb));
+    for (int p = lane; p < nc * nc; p += 32) {
+      int i = p >> lognc, j = p & (nc - 1);
+      int out;
+      if (sub) {
+        const S *r0 = ry + (2 * i) * stride + 2 * j, *r1 = r0 + stride;
+        out = (sat_px((a * (int)r0[0] + b) >> 16, maxv) + sat_px((a * (int)r0[1] + b) >> 16, maxv) + sat_px((a * (int)r1[0] + b) >> 16, maxv) +
+               sat_px((a * (int)r1[1] + b) >> 16, maxv) + 2) >> 2;
+      } else
+        out = sat_px((a * (int)ry[i * stride + j] + b) >> 16, maxv);
+      dst[i * cs + j] = (S)out;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a18/a19 scalar pieces.  common/common_block.c:214-220, 315-321; common/common_frame.h:61-65
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int constrain(int diff, int threshold, unsigned damping) {
+  if (!threshold) return 0;
+  int a = iabs(diff);
+  int lim = max(0, threshold - (a >> (damping - (unsigned)ilog2(threshold))));
+  lim = min(a, lim);
+  return diff < 0 ? -lim : lim;
+}
+__device__ __forceinline__ int clpf_sample(int X, int A, int B, int C, int D, int E, int F, int G, int H, int s, unsigned dmp) {
+  int delta = constrain(A - X, s, dmp) + 3 * constrain(B - X, s, dmp) + constrain(C - X, s, dmp) + 3 * constrain(D - X, s, dmp) +
+              3 * constrain(E - X, s, dmp) + constrain(F - X, s, dmp) + 3 * constrain(G - X, s, dmp) + constrain(H - X, s, dmp);
+  return (8 + delta - (delta < 0)) >> 4;
+}
+__device__ __forceinline__ int adjust_strength(int strength, int var) {
+  int i = (var >> 6) ? min(ilog2(var >> 6), 12) : 0;
+  return var ? (strength * (4 + i) + 8) >> 4 : 0;
+}
+__constant__ int8_t c_cdef_dx[8][2] = {{1, 2}, {1, 2}, {1, 2}, {1, 2}, {1, 2}, {0, 1}, {0, 0}, {0, -1}};   // common/common_block.c:189-208
+__constant__ int8_t c_cdef_dy[8][2] = {{-1, -2}, {0, -1}, {0, 0}, {0, 1}, {1, 2}, {1, 2}, {1, 2}, {1, 2}};
+
+// One CDEF output sample from a uint16 staging tile `in` (pitch ss, 30000 = outside the frame).
+// common/common_block.c:224-281 (CDEF_FULL = 0)
+__device__ __forceinline__ int cdef_sample(const uint16_t *in, int ss, int pri_strength, int sec_strength, int dir, int pri_damping, int sec_damping,
+                                           int coeff_shift) {
+  const int sel = (pri_strength >> coeff_shift) & 1;
+  const int pt0 = sel ? 3 : 4, pt1 = sel ? 3 : 2, st0 = 2, st1 = 1;
+  int x = (int16_t)in[0], mx = x, mn = x, sum = 0;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    int o0 = c_cdef_dy[dir][k] * ss + c_cdef_dx[dir][k];
+    int o1 = c_cdef_dy[(dir + 2) & 7][k] * ss + c_cdef_dx[(dir + 2) & 7][k];
+    int o2 = c_cdef_dy[(dir + 6) & 7][k] * ss + c_cdef_dx[(dir + 6) & 7][k];
+    int pt = k ? pt1 : pt0, st = k ? st1 : st0;
+    int p[2] = {(int16_t)in[o0], (int16_t)in[-o0]};
+    int s4[4] = {(int16_t)in[o1], (int16_t)in[-o1], (int16_t)in[o2], (int16_t)in[-o2]};
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      sum += pt * constrain(p[t] - x, pri_strength, (unsigned)pri_damping);
+      if (p[t] != 30000) mx = max(mx, p[t]);
+      mn = min(mn, p[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      sum += st * constrain(s4[t] - x, sec_strength, (unsigned)sec_damping);
+      if (s4[t] != 30000) mx = max(mx, s4[t]);
+      mn = min(mn, s4[t]);
+    }
+  }
+  sum = (int)(int16_t)sum;
+  int y = x + ((8 + sum - (sum < 0)) >> 4);
+  return iclip(y, mn, mx);
+}
+
+// CDEF direction search on an 8x8 block, one warp.  common/common_block.c:94-167.  Returns dir; *var out.
+template <class S> __device__ int warp_cdef_find_dir(const S *img, int stride, int coeff_shift, int &var_out) {
+  // Each lane owns one or more line sums.  partial[d][n]: 8 directions x up to 15 lines = 120 sums -> 4 per lane.
+  const int lane = lane_id();
+  __shared__ int dummy;  // (keeps the function usable from kernels without dynamic smem)
+  (void)dummy;
+  // load the block into registers: lane l holds pixels (row l>>2, cols (l&3)*2, +1) -> 64 pixels over 32 lanes
+  int r = lane >> 2, c0 = (lane & 3) * 2;
+  int x0 = ((int)img[r * stride + c0] >> coeff_shift) - 128, x1 = ((int)img[r * stride + c0 + 1] >> coeff_shift) - 128;
+  // cost accumulation: every lane computes complete line sums by gathering pixels through shuffles would be
+  // shuffle-heavy; the block is only 64 samples, so each lane instead recomputes the line sums it owns from the
+  // two-sample registers of all lanes via 32 shuffles.
+  int32_t cost_part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+  // lane L < 15 owns line index L of every direction
+  int sums[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int src = 0; src < 32; src++) {
+    int a = __shfl_sync(FULL, x0, src), b = __shfl_sync(FULL, x1, src);
+    int i = src >> 2, j = (src & 3) * 2;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      int x = t ? b : a, jj = j + t;
+      if (i + jj == lane) sums[0] += x;
+      if (i + jj / 2 == lane) sums[1] += x;
+      if (i == lane) sums[2] += x;
+      if (3 + i - jj / 2 == lane) sums[3] += x;
+      if (7 + i - jj == lane) sums[4] += x;
+      if (3 - i / 2 + jj == lane) sums[5] += x;
+      if (jj == lane) sums[6] += x;
+      if (i / 2 + jj == lane) sums[7] += x;
+    }
+  }
+  // weights per line index for each direction class
+  if (lane < 15) {
+    int w045 = lane < 7 ? div_table[lane + 1] : (lane == 7 ? div_table[8] : div_table[15 - lane]);  // dirs 0 and 4: 15 lines
+    cost_part[0] = sums[0] * sums[0] * w045;
+    cost_part[4] = sums[4] * sums[4] * w045;
+    if (lane < 8) {
+      cost_part[2] = sums[2] * sums[2] * div_table[8];
+      cost_part[6] = sums[6] * sums[6] * div_table[8];
+    }
+    if (lane < 11) {
+      // odd directions: 11 lines; lines 3..7 weight div[8], lines j and 10-j (j<3) weight div[2j+2]
+      int wodd = (lane >= 3 && lane <= 7) ? div_table[8] : (lane < 3 ? div_table[2 * lane + 2] : div_table[2 * (10 - lane) + 2]);
+      cost_part[1] = sums[1] * sums[1] * wodd;
+      cost_part[3] = sums[3] * sums[3] * wodd;
+      cost_part[5] = sums[5] * sums[5] * wodd;
+      cost_part[7] = sums[7] * sums[7] * wodd;
+    }
+  }
+  int32_t cost[8];
+#pragma unroll
+  for (int d = 0; d < 8; d++) cost[d] = (int32_t)warp_sum((uint32_t)cost_part[d]);
+  int32_t best_cost = 0;
+  int best_dir = 0;
+#pragma unroll
+  for (int d = 0; d < 8; d++)
+    if (cost[d] > best_cost) { best_cost = cost[d]; best_dir = d; }
+  int32_t orth = 0;
+#pragma unroll
+  for (int d = 0; d < 8; d++)
+    if (d == ((best_dir + 4) & 7)) orth = cost[d];
+  var_out = (best_cost - orth) >> 10;
+  return best_dir;
+}
+
+}  // namespace tb
