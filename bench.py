@@ -1,0 +1,538 @@
+#!/usr/bin/env python
+"""bench.py — Thor per-block hot path on B200: encode-side hot-path throughput in Mpixel/s (1080p, HDB_high_efficiency mix).
+
+ONE STEP = one pass of the hot path over one 1920x1080 inter frame's worth of work, in the quantities the reference's
+RD loop generates for config_HDB_high_efficiency when no early termination fires (enc/encode_block.c:1835-2120,
+2401-2565): every coding block of size 8..128, 4 reference frames, 9 prediction-block motion searches per
+(block, reference) [a1,a2,a5,a7], the RD candidates' luma/chroma predictions [a7,a8], their residual -> DCT -> quant ->
+dequant -> inverse DCT -> reconstruct -> SSD chains [a3,a10-a13], the 10 intra predictors [a15], and the frame-level
+in-loop filters deblock -> CDEF -> CLPF(+detect sums) -> reference copy + padding [a17-a20].  Work items are synthetic
+(seeded) but are laid out exactly as the reference lays them out; every kernel is the parity-tested one.
+
+WHAT THIS NUMBER IS NOT: a complete encode.  The reference's serial RD control flow, bit counting (write_block) and
+bitstream writer run on the host between these calls and are not part of the timed region; the dependency chain between
+neighbouring blocks is removed by batching.  It is the throughput ceiling of the GPU hot path, reported beside the same
+item lists replayed through the reference's own CPU kernels (cpu_baseline / --impl reference).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            (torchrun for N>1: frames are sharded, no collective)
+  python bench.py --impl reference --steps 1 --warmup 0    (CPU arm: the reference's kernels on all host cores)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, BD, ESZ = 1920, 1080, 8, 1
+NREF = 4          # -max_num_ref 4  (config_HDB_high_efficiency.txt)
+QP = 35           # -qp 32 + dqpB0 3
+LAMBDA = (1.2 * 158.8437) ** 0.5   # sqrt(lambda_coeffB0 * squared_lambda_QP[35]) as passed to motion_estimate (encode_block.c:1981)
+NCAND = 8         # candidate MVs per (block, reference) (frame_info->mvcand grows up to 64 inside an SB)
+SIZES = (8, 16, 32, 64, 128)
+PIXELS = W * H
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload construction (host, numpy, seeded) — identical for the GPU arm and the CPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def synth_frames(rng, n):
+    """moving 8x8-block texture + low-frequency sinusoids + N(0,3) noise (SURVEY.md §8d synthetic input), 4:2:0"""
+    yy, xx = np.mgrid[0:H + 64, 0:W + 64]
+    tex = rng.integers(0, 64, ((H + 64) // 8 + 1, (W + 64) // 8 + 1)).astype(np.float32)
+    base = np.kron(tex, np.ones((8, 8), np.float32))[:H + 64, :W + 64] + 60 * np.sin(xx / 97.0) + 50 * np.cos(yy / 61.0) + 96
+    frames = []
+    for k in range(n):
+        dy, dx = 2 * k, 3 * k
+        y = np.clip(base[dy:dy + H, dx:dx + W] + rng.normal(0, 3, (H, W)), 0, 255).astype(np.uint8)
+        u = np.clip(128 + 30 * np.sin(xx[:H // 2, :W // 2] / 53.0 + k) + rng.normal(0, 2, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+        v = np.clip(128 + 30 * np.cos(yy[:H // 2, :W // 2] / 47.0 - k) + rng.normal(0, 2, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+        frames.append((y, u, v))
+    return frames
+
+
+def block_grid():
+    """(size, xpos, ypos) of every square coding block fully inside the frame, sizes 8..128 (process_block recursion)"""
+    out = []
+    for s in SIZES:
+        xs = np.arange(0, W - s + 1, s); ys = np.arange(0, H - s + 1, s)
+        gx, gy = np.meshgrid(xs, ys)
+        out.append(np.stack([np.full(gx.size, s), gx.ravel(), gy.ravel()], axis=1))
+    return np.concatenate(out).astype(np.int32)
+
+
+# the nine prediction blocks searched per (coding block, reference): PART_NONE, 2x HOR, 2x VER, 4x QUAD
+# (search_inter_prediction_params, enc/encode_block.c:1033-1098) as (wnum, hnum, ox, oy) in halves of the block size
+PBS = [(2, 2, 0, 0), (2, 1, 0, 0), (2, 1, 0, 1), (1, 2, 0, 0), (1, 2, 1, 0), (1, 1, 0, 0), (1, 1, 1, 0), (1, 1, 0, 1), (1, 1, 1, 1)]
+
+
+def build_me(tb, blocks, cur_ptr, cur_st, ref_ptrs, ref_st, rng, subsample=1):
+    nb = len(blocks)
+    size = np.repeat(blocks[:, 0], NREF * 9); xpos = np.repeat(blocks[:, 1], NREF * 9); ypos = np.repeat(blocks[:, 2], NREF * 9)
+    ref = np.tile(np.repeat(np.arange(NREF), 9), nb)
+    pb = np.tile(np.arange(9), nb * NREF)
+    pbt = np.array(PBS)
+    half = size // 2
+    bw = pbt[pb, 0] * half; bh = pbt[pb, 1] * half; ox = pbt[pb, 2] * half; oy = pbt[pb, 3] * half
+    n = len(size)
+    items = np.zeros(n, tb.ME_ITEM)
+    refp = np.asarray(ref_ptrs, np.uint64)[ref]
+    items["orig"] = np.uint64(cur_ptr) + ((ypos + oy).astype(np.uint64) * np.uint64(cur_st) + (xpos + ox).astype(np.uint64)) * np.uint64(ESZ)
+    items["ref"] = refp + ((ypos + oy).astype(np.uint64) * np.uint64(ref_st) + (xpos + ox).astype(np.uint64)) * np.uint64(ESZ)
+    items["ostride"] = cur_st; items["rstride"] = ref_st
+    items["xpos"] = xpos; items["ypos"] = ypos; items["size"] = size; items["width"] = bw; items["height"] = bh
+    items["sign"] = (ref == NREF - 1)  # one future reference, as in B frames
+    grp = np.repeat(np.arange(nb * NREF), 9)  # one (block, ref) group shares centre, predictor and candidate list
+    mvg = rng.integers(-24, 25, (nb * NREF, 4)).astype(np.int16)
+    items["mvc_x"] = mvg[grp, 0]; items["mvc_y"] = mvg[grp, 1]; items["mvp_x"] = mvg[grp, 2]; items["mvp_y"] = mvg[grp, 3]
+    items["cand_ofs"] = grp * NCAND; items["ncand"] = NCAND; items["lambda"] = LAMBDA
+    cands = rng.integers(-12, 13, (nb * NREF * NCAND, 2)).astype(np.int16)
+    if subsample > 1:
+        items = items[::subsample].copy()
+    return items, cands
+
+
+def tu_list(blocks):
+    """Transform blocks evaluated per coding block (mode_decision_rdo + encode_block, enc/encode_block.c:1340-1493, 1835-2120):
+    31 unsplit evaluations (luma size s, 2 chroma s/2) and 30 tb_split evaluations (4 luma s/2, 8 chroma s/4)."""
+    rows = []
+    for s in SIZES:
+        b = blocks[blocks[:, 0] == s]
+        def add(count, tsize, chroma, sub):
+            if tsize < 4:
+                return
+            # sub x sub transform blocks tile the coding block (in the TU's own plane)
+            k = np.arange(sub * sub)
+            tx = (k % sub) * tsize; ty = (k // sub) * tsize
+            bx = (b[:, 1] >> chroma)[:, None] + tx[None, :]; by = (b[:, 2] >> chroma)[:, None] + ty[None, :]
+            r = np.stack([np.full(bx.size, tsize), bx.ravel(), by.ravel(), np.full(bx.size, chroma)], axis=1)
+            rows.append(np.tile(r, (count, 1)))
+        add(31, s, 0, 1); add(62, s // 2, 1, 1)
+        add(30, s // 2, 0, 2); add(60, s // 4, 1, 2)
+    return np.concatenate(rows).astype(np.int32)
+
+
+def build_txfm(tb, tus, planes_cur, planes_ref, planes_rec, rng, subsample=1):
+    if subsample > 1:
+        tus = tus[::subsample]
+    n = len(tus)
+    size, x, y, chroma = tus[:, 0], tus[:, 1], tus[:, 2], tus[:, 3]
+    items = np.zeros(n, tb.TXFM_ITEM)
+    cp = np.array([planes_cur[0][0], planes_cur[1][0]], np.uint64)[chroma]; cs = np.array([planes_cur[0][1], planes_cur[1][1]])[chroma]
+    rp = np.array([planes_ref[0][0], planes_ref[1][0]], np.uint64)[chroma]; rs = np.array([planes_ref[0][1], planes_ref[1][1]])[chroma]
+    op = np.array([planes_rec[0][0], planes_rec[1][0]], np.uint64)[chroma]; os_ = np.array([planes_rec[0][1], planes_rec[1][1]])[chroma]
+    dx = rng.integers(-3, 4, n); dy = rng.integers(-3, 4, n)  # prediction = displaced reference block
+    items["orig"] = cp + (y.astype(np.uint64) * cs.astype(np.uint64) + x.astype(np.uint64)) * np.uint64(ESZ)
+    items["pred"] = (rp.astype(np.int64) + ((y + dy).astype(np.int64) * rs + (x + dx)) * ESZ).astype(np.uint64)
+    items["rec"] = op + (y.astype(np.uint64) * os_.astype(np.uint64) + x.astype(np.uint64)) * np.uint64(ESZ)
+    items["coeffq"] = 0
+    items["ostride"] = cs; items["pstride"] = rs; items["rstride"] = os_
+    items["size"] = size; items["qp"] = np.where(chroma == 1, 34, QP)  # chroma_qp[35] = 34
+    items["coeff_type"] = rng.integers(0, 2, n) * 2 + chroma; items["fast"] = 0
+    return items
+
+
+def build_interp(tb, blocks, ref_planes, out_ptr, rng, subsample=1):
+    """predictions of the inter RD candidates: per (block, ref): the 9 prediction blocks, luma + U + V"""
+    nb = len(blocks)
+    size = np.repeat(blocks[:, 0], NREF * 9); xpos = np.repeat(blocks[:, 1], NREF * 9); ypos = np.repeat(blocks[:, 2], NREF * 9)
+    ref = np.tile(np.repeat(np.arange(NREF), 9), nb); pb = np.tile(np.arange(9), nb * NREF)
+    pbt = np.array(PBS); half = size // 2
+    bw = pbt[pb, 0] * half; bh = pbt[pb, 1] * half; ox = pbt[pb, 2] * half; oy = pbt[pb, 3] * half
+    mv = rng.integers(-40, 41, (len(size), 2))
+    parts = []
+    ofs = 0
+    for plane in range(3):
+        c = 1 if plane else 0
+        w_, h_ = bw >> c, bh >> c
+        keep = (w_ >= (2 if c else 4)) & (h_ >= (2 if c else 4))
+        it = np.zeros(int(keep.sum()), tb.INTERP_ITEM)
+        px = (xpos + ox)[keep] >> c; py = (ypos + oy)[keep] >> c
+        ptrs = np.array([ref_planes[r][plane][0] for r in range(NREF)], np.uint64)[ref[keep]]
+        st = ref_planes[0][plane][1]
+        it["ref"] = ptrs + (py.astype(np.uint64) * np.uint64(st) + px.astype(np.uint64)) * np.uint64(ESZ)
+        area = (w_[keep] * h_[keep]).astype(np.int64)
+        start = ofs + np.concatenate([[0], np.cumsum(area)[:-1]])
+        ofs += int(area.sum())
+        it["dst"] = np.uint64(out_ptr) + start.astype(np.uint64) * np.uint64(ESZ)
+        it["rstride"] = st; it["dstride"] = w_[keep]
+        it["xpos"] = px; it["ypos"] = py; it["mvx"] = mv[keep, 0]; it["mvy"] = mv[keep, 1]
+        it["width"] = w_[keep]; it["height"] = h_[keep]; it["sign"] = (ref[keep] == NREF - 1); it["chroma"] = c
+        it["pic_w"] = W >> c; it["pic_h"] = H >> c
+        parts.append(it)
+    items = np.concatenate(parts)
+    if subsample > 1:
+        items = items[::subsample].copy()
+    return items, ofs
+
+
+def build_intra(tb, blocks, rec_ptr, rec_st, out_ptr, subsample=1):
+    """10 modes on the block and on its four tb_split quadrants (intra_rdo = 1, enc/encode_block.c:2073-2114)"""
+    rows = []
+    for s in SIZES:
+        b = blocks[blocks[:, 0] == s]
+        for (ts, sub) in ((s, 1), (s // 2, 2)):
+            if ts < 4:
+                continue
+            k = np.arange(sub * sub)
+            bx = b[:, 1][:, None] + (k % sub)[None, :] * ts; by = b[:, 2][:, None] + (k // sub)[None, :] * ts
+            r = np.stack([np.full(bx.size, ts), bx.ravel(), by.ravel()], axis=1)
+            rows.append(np.repeat(r, 10, axis=0))
+    r = np.concatenate(rows)
+    n = len(r)
+    items = np.zeros(n, tb.INTRA_ITEM)
+    size, x, y = r[:, 0], r[:, 1], r[:, 2]
+    area = (size * size).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(area)[:-1]])
+    items["rec"] = np.uint64(rec_ptr) + (y.astype(np.uint64) * np.uint64(rec_st) + x.astype(np.uint64)) * np.uint64(ESZ)
+    items["dst"] = np.uint64(out_ptr) + start.astype(np.uint64) * np.uint64(ESZ)
+    items["rstride"] = rec_st; items["xpos"] = x; items["ypos"] = y; items["size"] = size
+    items["mode"] = np.tile(np.arange(10), n // 10)
+    items["upright"] = ((y > 0) & (x + size < W)); items["downleft"] = ((x > 0) & (y + size < H))
+    total = int(area.sum())
+    if subsample > 1:
+        items = items[::subsample].copy()
+    return items, total
+
+
+def build_blkinfo(tb, rng):
+    bi = np.zeros((H // 4, W // 4), tb.BLKINFO)
+    for s, frac in ((64, 0.15), (32, 0.25), (16, 0.3), (8, 0.3)):
+        pass
+    # random quad-tree: 64x64 leaves split with p=0.6 down to 8x8
+    def fill(x, y, s):
+        if s > 8 and (rng.random() < 0.6 or x + s > W or y + s > H):
+            for dy in (0, s // 2):
+                for dx in (0, s // 2):
+                    if x + dx < W and y + dy < H:
+                        fill(x + dx, y + dy, s // 2)
+            return
+        mode = 0 if rng.random() < 0.3 else int(rng.integers(1, 5))
+        rec = np.zeros((), tb.BLKINFO)
+        rec["mode"] = mode; rec["size"] = s; rec["cbp_y"] = 0 if mode == 0 else int(rng.integers(0, 2))
+        rec["tb_split"] = int(rng.integers(0, 2)) if mode else 0
+        rec["pb_part"] = int(rng.integers(0, 4)) if mode in (2, 3) else 0
+        if mode != 1:
+            rec["mv0x"], rec["mv0y"] = int(rng.integers(-9, 10)), int(rng.integers(-9, 10))
+        bi[y // 4:min(H // 4, (y + s) // 4), x // 4:min(W // 4, (x + s) // 4)] = rec
+    for y0 in range(0, H, 64):
+        for x0 in range(0, W, 64):
+            fill(x0, y0, 64)
+    return bi
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import thor_b200 as tb
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tb.init(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    tb.check(tb.lib.tb_set_stream(C.c_void_p(stream.cuda_stream)))
+    L = tb.lib
+    rng = np.random.default_rng(2026 + rank)  # every rank encodes its own frame (frames shard with no data-path collective)
+
+    # ---- resident frames: current, 4 references (padded), reconstruction + scratch + "original" for the filters
+    fr = synth_frames(rng, NREF + 1)
+    cur = tb.Frame(W, H, ESZ); cur.upload(*fr[0])
+    refs = []
+    tmp = tb.Frame(W, H, ESZ)
+    for k in range(NREF):
+        tmp.upload(*fr[k + 1])
+        r = tb.Frame(W, H, ESZ)
+        tb.check(L.tb_create_reference_frame(r.h, tmp.h))
+        refs.append(r)
+    pristine = tb.Frame(W, H, ESZ); pristine.upload(*fr[1])  # un-filtered reconstruction, restored device-side every step
+    rec = tb.Frame(W, H, ESZ); rec.upload(*fr[1]); scratch = tb.Frame(W, H, ESZ); newref = tb.Frame(W, H, ESZ)
+    cand_rec = tb.Frame(W, H, ESZ)  # where RD candidates write their reconstructions
+
+    blocks = block_grid()
+    me_items, cands = build_me(tb, blocks, cur.plane(0)[0], cur.plane(0)[1], [r.plane(0)[0] for r in refs], refs[0].plane(0)[1], rng)
+    tus = tu_list(blocks)
+    tx_items = build_txfm(tb, tus, [cur.plane(0), cur.plane(1)], [refs[0].plane(0), refs[0].plane(1)], [cand_rec.plane(0), cand_rec.plane(1)], rng)
+    ip_probe, ip_total = build_interp(tb, blocks, [[r.plane(p) for p in range(3)] for r in refs], 0, np.random.default_rng(1), 1)
+    pred_buf = tb.DevBuf(ip_total * ESZ + 64)
+    ip_items, _ = build_interp(tb, blocks, [[r.plane(p) for p in range(3)] for r in refs], pred_buf.ptr, rng)
+    _, in_total = build_intra(tb, blocks, 0, rec.plane(0)[1], 0)
+    intra_buf = tb.DevBuf(in_total * ESZ + 64)
+    in_items, _ = build_intra(tb, blocks, rec.plane(0)[0], rec.plane(0)[1], intra_buf.ptr)
+    bi = build_blkinfo(tb, rng)
+    nfb = ((W + 63) // 64) * ((H + 63) // 64)
+    pri = rng.integers(0, 16, (2, nfb)).astype(np.int8); sec = rng.integers(0, 4, (2, nfb)).astype(np.int8)
+
+    d_me = tb.DevBuf.from_array(me_items); d_cand = tb.DevBuf.from_array(cands); d_me_out = tb.DevBuf(8 * len(me_items))
+    d_tx = tb.DevBuf.from_array(tx_items); d_tx_out = tb.DevBuf(16 * len(tx_items))
+    d_ip = tb.DevBuf.from_array(ip_items); d_in = tb.DevBuf.from_array(in_items)
+    d_bi = tb.DevBuf.from_array(bi)
+    d_pri = [tb.DevBuf.from_array(pri[k]) for k in range(2)]; d_sec = [tb.DevBuf.from_array(sec[k]) for k in range(2)]
+    d_dv = tb.DevBuf(nfb * 2 * 64 * 4); d_sums = tb.DevBuf(16 * (W // 8) * (H // 8))
+    resident_bytes = sum(b.nbytes for b in (d_me, d_cand, d_me_out, d_tx, d_tx_out, d_ip, d_in, pred_buf, intra_buf))
+
+    # pinned host staging for the end-to-end leg
+    def pinned(a):
+        p = L.tb_malloc_host(a.nbytes)
+        buf = (C.c_uint8 * a.nbytes).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        arr[...] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+        return p, a.nbytes
+    h_y, h_u, h_v = [pinned(p)[0] for p in fr[0]]
+    h_me, me_bytes = pinned(me_items); h_cand, cand_bytes = pinned(cands)
+    h_me_out = L.tb_malloc_host(8 * len(me_items)); h_tx_out = L.tb_malloc_host(16 * len(tx_items))
+    h_rec = [L.tb_malloc_host(W * H), L.tb_malloc_host(W * H // 4), L.tb_malloc_host(W * H // 4)]
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    me_ev = []
+
+    def step(e2e=False, time_me=False):
+        tb.check(L.tb_create_reference_frame(rec.h, pristine.h))  # the filters run in place: restore their input (device-side copy)
+        if e2e:
+            tb.check(L.tb_frame_upload(cur.h, h_y, W, h_u, h_v, W // 2))
+            tb.check(L.tb_memcpy_h2d(d_me.ptr, h_me, me_bytes)); tb.check(L.tb_memcpy_h2d(d_cand.ptr, h_cand, cand_bytes))
+        if time_me:
+            a, b = ev(), ev(); a.record(stream)
+        tb.check(L.tb_motion_estimate_batch(d_me.ptr, len(me_items), d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr))
+        if time_me:
+            b.record(stream); me_ev.append((a, b))
+        tb.check(L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1))
+        tb.check(L.tb_txfm_chain_batch(d_tx.ptr, len(tx_items), ESZ, BD, d_tx_out.ptr))
+        tb.check(L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD))
+        tb.check(L.tb_deblock_frame(rec.h, d_bi.ptr, QP, BD))
+        for plane in range(3):
+            tb.check(L.tb_cdef_frame(rec.h, scratch.h, d_bi.ptr, d_pri[int(plane > 0)].ptr, d_sec[int(plane > 0)].ptr, 5, 5, d_dv.ptr, BD, plane))
+        for plane in range(3):
+            tb.check(L.tb_clpf_detect_frame(rec.h, cur.h, d_bi.ptr, plane, BD, QP, d_sums.ptr))
+        for plane, (fbl, strength) in enumerate(((6, 2), (4, 1), (4, 2))):
+            tb.check(L.tb_clpf_frame(rec.h, scratch.h, d_bi.ptr, None, fbl, strength, BD, plane, QP))
+        tb.check(L.tb_create_reference_frame(newref.h, rec.h))
+        if e2e:
+            tb.check(L.tb_memcpy_d2h(h_me_out, d_me_out.ptr, 8 * len(me_items)))
+            tb.check(L.tb_memcpy_d2h(h_tx_out, d_tx_out.ptr, 16 * len(tx_items)))
+            tb.check(L.tb_frame_download(rec.h, h_rec[0], W, h_rec[1], h_rec[2], W // 2))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = L.tb_launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    t0, t1 = ev(), ev()
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(time_me=True)
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(L.tb_launch_count() - l0)
+    ms = t0.elapsed_time(t1)
+    me_ms = float(np.mean([a.elapsed_time(b) for a, b in me_ev]))
+    if args.breakdown:
+        names = ["restore", "motion_estimate", "interp", "txfm_chain", "intra", "deblock", "cdef x3", "clpf_detect x3", "clpf x3", "create_reference"]
+        calls = [lambda: L.tb_create_reference_frame(rec.h, pristine.h),
+                 lambda: L.tb_motion_estimate_batch(d_me.ptr, len(me_items), d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr),
+                 lambda: L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1),
+                 lambda: L.tb_txfm_chain_batch(d_tx.ptr, len(tx_items), ESZ, BD, d_tx_out.ptr),
+                 lambda: L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD),
+                 lambda: L.tb_deblock_frame(rec.h, d_bi.ptr, QP, BD),
+                 lambda: [L.tb_cdef_frame(rec.h, scratch.h, d_bi.ptr, d_pri[int(p > 0)].ptr, d_sec[int(p > 0)].ptr, 5, 5, d_dv.ptr, BD, p) for p in range(3)],
+                 lambda: [L.tb_clpf_detect_frame(rec.h, cur.h, d_bi.ptr, p, BD, QP, d_sums.ptr) for p in range(3)],
+                 lambda: [L.tb_clpf_frame(rec.h, scratch.h, d_bi.ptr, None, f_, s_, BD, p, QP) for p, (f_, s_) in enumerate(((6, 2), (4, 1), (4, 2)))],
+                 lambda: L.tb_create_reference_frame(newref.h, rec.h)]
+        bd_ms = {}
+        for nm, fn in zip(names, calls):
+            a, b = ev(), ev(); a.record(stream); fn(); b.record(stream); torch.cuda.synchronize()
+            bd_ms[nm] = round(a.elapsed_time(b), 3)
+        sys.stderr.write("breakdown_ms " + json.dumps(bd_ms) + "\n")
+    # end-to-end leg (host buffers in, host results out)
+    step(e2e=True); barrier()
+    e0, e1 = ev(), ev(); e0.record(stream)
+    for _ in range(args.steps):
+        step(e2e=True)
+    e1.record(stream); barrier()
+    ems = e0.elapsed_time(e1)
+    # work counters of the motion-search kernel (one extra untimed launch)
+    d_stats = tb.DevBuf.from_array(np.zeros(5, np.uint64))
+    L.tb_me_set_stats(d_stats.ptr)
+    tb.check(L.tb_motion_estimate_batch(d_me.ptr, len(me_items), d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr)); barrier()
+    L.tb_me_set_stats(None)
+    st = d_stats.download(np.uint64, 5)
+
+    if world > 1:
+        t = torch.tensor([ms, ems, me_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ems, me_ms = [float(v) for v in t.tolist()]
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = float(st[3] + st[4]) * ESZ  # w*h*s per integer candidate (+ one read of the original), ((w+5)(h+5)+w*h)*s per sub-pel probe
+    achieved = alg_bytes / (me_ms * 1e-3) / 1e9
+    value = world * args.steps * PIXELS / (ms * 1e-3) / 1e6
+    e2e_value = world * args.steps * PIXELS / (ems * 1e-3) / 1e6
+    h2d = 3 * W * H // 2 + me_bytes + cand_bytes
+    d2h = 8 * len(me_items) + 16 * len(tx_items) + 3 * W * H // 2
+    line = {
+        "metric": "encode hot-path Mpixels/s (1080p HDB_high_efficiency work mix, batched; host RD control flow excluded)",
+        "value": round(value, 3), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "1920x1080 8-bit 4:2:0, config_HDB_high_efficiency hot-path batch for ONE inter frame per step: %d motion searches "
+                               "(blocks 8..128 x 4 refs x 9 PBs, speed 0, bipred taps), %d candidate predictions, %d DCT/quant/recon chains, %d intra predictions, "
+                               "deblock+CDEF+CLPF(+detect)+reference pad; dependency-free batching (not a complete encode)" % (len(me_items), len(ip_items), len(tx_items), len(in_items)),
+                   "parallelism": "frame-per-GPU x%d, no collective" % world, "l2_policy": "per-step inputs+outputs %.0f MB > 126 MB L2" % (resident_bytes / 1e6)},
+        "e2e": {"value": round(e2e_value, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ems / args.steps, 3)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "me_batch_kernel<uint8_t> (a1/a2/a5/a7 fused motion search)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "ms_per_launch": round(me_ms, 3), "share_of_step": round(me_ms / (ms / args.steps), 3),
+                     "searches": int(st[0]), "int_block_sads": int(st[1]), "subpel_probes": int(st[2])},
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_arm(args, brief=True)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the same item lists through the reference's own kernels (oracle/_ref) on all host cores
+# ----------------------------------------------------------------------------------------------------------------------
+class _FakeTb:
+    pass
+
+
+def cpu_arm(args, brief=False):
+    import thor_b200  # item dtypes only (no GPU needed)
+    tb = _FakeTb()
+    for k in ("ME_ITEM", "TXFM_ITEM", "INTERP_ITEM", "INTRA_ITEM", "BLKINFO", "ME_RESULT", "TXFM_RESULT"):
+        setattr(tb, k, getattr(thor_b200, k))
+    refso = os.path.join(ROOT, "oracle", "_ref", "libcpubench_ref.so"); portso = os.path.join(ROOT, "oracle", "libcpubench_port.so")
+    if os.path.exists(refso):
+        C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libthorref.so"), mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(refso)
+    else:
+        if not os.path.exists(portso):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+        lib = C.CDLL(portso)
+    lib.cpu_bench_run.restype = C.c_double
+    lib.cpu_bench_run.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7
+    lib.cpu_bench_kind.restype = C.c_char_p
+    kind = lib.cpu_bench_kind().decode()
+    cores = len(os.sched_getaffinity(0))
+    sub = args.cpu_subsample  # every sub-th work item of each list
+    rng = np.random.default_rng(2026)
+    fr = synth_frames(rng, NREF + 1)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _refstructs import Frame as HFrame
+    from _libs import oracle, P
+    O = oracle()
+
+    def hframe(planes):
+        f = HFrame(W, H, BD, 0)
+        f.y[...] = planes[0]; f.u[...] = planes[1]; f.v[...] = planes[2]
+        for p, (pw, ph, pad) in enumerate(((W, H, 160), (W // 2, H // 2, 80), (W // 2, H // 2, 80))):
+            O.orc_pad_plane_lbd(P(f.full(p), f.origin(p)), f.stride(p), pw, ph, pad, pad)
+        return f
+    cur = hframe(fr[0]); refs = [hframe(fr[k + 1]) for k in range(NREF)]; rec = hframe(fr[1]); cand_rec = hframe(fr[1])
+    pl = lambda f, p: (f.full(p).ctypes.data + f.origin(p) * ESZ, f.stride(p))
+    blocks = block_grid()
+    me_items, cands = build_me(tb, blocks, pl(cur, 0)[0], pl(cur, 0)[1], [pl(r, 0)[0] for r in refs], pl(refs[0], 0)[1], rng, sub)
+    tx_items = build_txfm(tb, tu_list(blocks), [pl(cur, 0), pl(cur, 1)], [pl(refs[0], 0), pl(refs[0], 1)], [pl(cand_rec, 0), pl(cand_rec, 1)], rng, sub)
+    _, ip_total = build_interp(tb, blocks, [[pl(r, p) for p in range(3)] for r in refs], 0, np.random.default_rng(1), 1)
+    pred = np.zeros(ip_total + 64, np.uint8)
+    ip_items, _ = build_interp(tb, blocks, [[pl(r, p) for p in range(3)] for r in refs], pred.ctypes.data, rng, sub)
+    _, in_total = build_intra(tb, blocks, 0, pl(rec, 0)[1], 0)
+    ibuf = np.zeros(in_total + 64, np.uint8)
+    in_items, _ = build_intra(tb, blocks, pl(rec, 0)[0], pl(rec, 0)[1], ibuf.ctypes.data, sub)
+    me_out = np.zeros(len(me_items), tb.ME_RESULT); tx_out = np.zeros(len(tx_items), tb.TXFM_RESULT)
+    total = 0.0
+    steps = max(1, args.steps if args.impl == "reference" else 1)
+    t_wall = time.time()
+    for _ in range(steps):
+        total += lib.cpu_bench_run(0, me_items.ctypes.data, len(me_items), cands.ctypes.data, me_out.ctypes.data, 0, BD, 0, 1, W, H, cores)
+        total += lib.cpu_bench_run(3, ip_items.ctypes.data, len(ip_items), None, None, 0, BD, 0, 1, W, H, cores)
+        total += lib.cpu_bench_run(1, tx_items.ctypes.data, len(tx_items), None, tx_out.ctypes.data, 0, BD, 0, 1, W, H, cores)
+        total += lib.cpu_bench_run(2, in_items.ctypes.data, len(in_items), None, None, 0, BD, 0, 1, W, H, cores)
+    value = steps * PIXELS / sub / total / 1e6
+    sample = ("every %d-th work item of each list of one 1080p frame (%d motion searches, %d predictions, %d transform chains, %d intra predictions) "
+              "through the %s on %d threads; frame-level filters not included in the CPU sample" %
+              (sub, len(me_items), len(ip_items), len(tx_items), len(in_items), "reference's own kernels (oracle/_ref, SIMD path)" if kind == "reference" else "oracle port", cores))
+    res = {"value": round(value, 4), "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample, "seconds": round(total, 2)}
+    if brief:
+        return res
+    line = {"impl": "reference", "metric": "encode hot-path Mpixels/s (1080p HDB_high_efficiency work mix, batched; host RD control flow excluded)",
+            "value": res["value"], "unit": "Mpixel/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * total / steps * sub, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "same item lists as the GPU arm (1920x1080 8-bit, HDB_high_efficiency hot-path batch), 1/%d sample" % sub},
+            "cpu_baseline": res, "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-subsample", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) == 0:
+            cpu_arm(args)
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,11 @@ typedef struct { int16_t mvx, mvy; uint32_t cost; } tb_me_result_t;
 int tb_motion_estimate_batch(const tb_me_item_t *items_dev, int n, const int16_t *cand_dev, int sample_bytes, int bitdepth,
                              int encoder_speed, int enable_bipred, int fwidth, int fheight, tb_me_result_t *out_dev);
 
+/* optional work counters for the roofline: 5 uint64 in HBM {searches, integer-position block SADs, sub-pel probes,
+ * samples compared at integer positions (incl. one read of the original block), samples read+written by the sub-pel probes};
+ * NULL (default) disables counting */
+int tb_me_set_stats(uint64_t *stats_dev);
+
 /* ---- a7/a8: sub-pel interpolation, one prediction block per item (common/inter_prediction.c:65-183) */
 typedef struct {
   const void *ref; /* device ptr: block position in the padded reference plane */

@@ -77,6 +77,7 @@ lib.tb_frame_plane.restype = _vp
 lib.tb_frame_plane.argtypes = [_vp, _i, C.POINTER(_i)]
 lib.tb_sad_batch.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 lib.tb_motion_estimate_batch.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]
+lib.tb_me_set_stats.argtypes = [_vp]
 lib.tb_interp_batch.argtypes = [_vp, _i, _i, _i, _i]
 lib.tb_txfm_chain_batch.argtypes = [_vp, _i, _i, _i, _vp]
 lib.tb_intra_batch.argtypes = [_vp, _i, _i, _i]

@@ -24,6 +24,7 @@ struct Ctx {
   void *slot[NSLOT] = {nullptr};
   size_t cap[NSLOT] = {0};
   int sm_count = 148;
+  unsigned long long *me_stats = nullptr;
 };
 Ctx g;
 
@@ -345,9 +346,13 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
                              tb_me_result_t *out) {
   API_BEGIN();
   if (n <= 0) return TB_OK;
-  if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out);
-  else LAUNCH(me_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out);
+  if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
+  else LAUNCH(me_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
   API_END();
+}
+int tb_me_set_stats(uint64_t *stats_dev) {
+  g.me_stats = (unsigned long long *)stats_dev;
+  return TB_OK;
 }
 int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int bitdepth, int bipred) {
   API_BEGIN();

@@ -365,6 +365,8 @@ struct MeCtx {
   int size, width, height, sign, s, xpos, ypos, fw, fh, bitdepth, speed, bip;
   int mvpx, mvpy;
   double lambda;
+  // work counters for the roofline (not part of the result): integer-position block SADs and sub-pel probes
+  unsigned n_int, n_sub;
 };
 
 // first-minimum over lanes < n of key (cost); returns winning lane (or -1 if n == 0) and its cost
@@ -377,7 +379,7 @@ __device__ __forceinline__ int warp_first_min(uint32_t cost, int n, uint32_t &be
 }
 
 template <class S>
-__device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs, const MeCtx &c, int mvcx, int mvcy, const int16_t *cand,
+__device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs, MeCtx &c, int mvcx, int mvcy, const int16_t *cand,
                                      int ncand, int &out_mvx, int &out_mvy, uint32_t &out_cost) {
   const int lane = lane_id();
   const int s = c.s, shift = c.bitdepth - 8;
@@ -411,8 +413,10 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
         }
         sad = b;
         cx = (int)(int16_t)(cx + (s * bxo << 2));
+        c.n_int += 5 * n;
       } else {
         sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+        c.n_int += n;
       }
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       uint32_t best;
@@ -449,8 +453,10 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
       }
       sad = b;
       cx = (int)(int16_t)(cx + (s * bxo << 2));
+      c.n_int += 5 * n;
     } else {
       sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, pos, n);
+      c.n_int += n;
     }
     uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
     uint32_t best;
@@ -475,6 +481,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
       int cx = (int)(int16_t)(refx + diy[dir] * 4), cy = (int)(int16_t)(refy + dix[dir] * 4);
       clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
       uint32_t sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+      c.n_int += n;
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       uint32_t best;
       int w = warp_first_min(cost, n, best);
@@ -496,6 +503,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
 
   int ydh = 0, xdh = 0, ydq = 0, xdq = 0;
   uint32_t cmin = min_sad;
+  c.n_sub += c.speed == 0 ? 16 : 2;
   if (c.speed == 0) {
     // ---- true half-pel then quarter-pel probes (:625-663)
     const int8_t hm[9] = {0, 0, -2, 2, 0, -2, -2, 2, 2}, hn[9] = {0, -2, 0, 0, 2, -2, 2, -2, 2};
@@ -983,8 +991,6 @@ __device__ __forceinline__ int cdef_sample(const uint16_t *in, int ss, int pri_s
 template <class S> __device__ int warp_cdef_find_dir(const S *img, int stride, int coeff_shift, int &var_out) {
   // Each lane owns one or more line sums.  partial[d][n]: 8 directions x up to 15 lines = 120 sums -> 4 per lane.
   const int lane = lane_id();
-  __shared__ int dummy;  // (keeps the function usable from kernels without dynamic smem)
-  (void)dummy;
   // load the block into registers: lane l holds pixels (row l>>2, cols (l&3)*2, +1) -> 64 pixels over 32 lanes
   int r = lane >> 2, c0 = (lane & 3) * 2;
   int x0 = ((int)img[r * stride + c0] >> coeff_shift) - 128, x1 = ((int)img[r * stride + c0 + 1] >> coeff_shift) - 128;

@@ -61,18 +61,27 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 // ---- a5 --------------------------------------------------------------------------------------------------------
 template <class S>
 __global__ void __launch_bounds__(CTA_THREADS) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
-                                                               int fw, int fh, tb_me_result_t *out) {
+                                                               int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   for (int it = global_warp(); it < n; it += total_warps()) {
     tb_me_item_t q = items[it];
     MeCtx c;
     c.size = q.size; c.width = q.width; c.height = q.height; c.sign = q.sign; c.s = q.sign ? -1 : 1;
     c.xpos = q.xpos; c.ypos = q.ypos; c.fw = fw; c.fh = fh; c.bitdepth = bitdepth; c.speed = speed; c.bip = bip;
-    c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda;
+    c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda; c.n_int = 0; c.n_sub = 0;
     int mx, my;
     uint32_t cost;
     warp_motion_estimate<S>((const S *)q.orig, q.ostride, (const S *)q.ref, q.rstride, c, q.mvc_x, q.mvc_y, cand + 2 * (size_t)q.cand_ofs, q.ncand, mx, my,
                             cost);
-    if (lane_id() == 0) { out[it].mvx = (int16_t)mx; out[it].mvy = (int16_t)my; out[it].cost = cost; }
+    if (lane_id() == 0) {
+      out[it].mvx = (int16_t)mx; out[it].mvy = (int16_t)my; out[it].cost = cost;
+      if (stats) {  // roofline accounting: samples compared at integer positions, samples fetched for sub-pel probes
+        atomicAdd(&stats[0], 1ull);
+        atomicAdd(&stats[1], (unsigned long long)c.n_int);
+        atomicAdd(&stats[2], (unsigned long long)c.n_sub);
+        atomicAdd(&stats[3], (unsigned long long)(c.n_int + 1) * q.width * q.height);
+        atomicAdd(&stats[4], (unsigned long long)c.n_sub * ((q.width + 5) * (q.height + 5) + q.width * q.height));
+      }
+    }
   }
 }
 
