@@ -80,28 +80,32 @@ template <class S> __device__ __forceinline__ uint32_t warp_sad(const S *o, int 
 }
 
 // SADs of up to 32 reference positions of the same block: lane i supplies the sample offset `roff` of position i
-// (i < n); lane i receives SAD i.  Blocks of fewer than 32 words are evaluated 32/words positions at a time.
+// (i < n); lane i receives SAD i.  L = lanes cooperating on one position = words/16 (1 for blocks up to 8x8 u8: the
+// whole 5x5 telescope grid is then evaluated in ONE pass, one position per lane, no shuffles), 32 for >= 512 words.
 template <class S>
 __device__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
   constexpr int PW = Word<S>::PW;
   const int lane = lane_id();
   const int nwords = (w / PW) * h;
+  const int L = nwords >= 512 ? 32 : (nwords <= 16 ? 1 : nwords >> 4);  // power of two
   uint32_t out = 0;
-  if (nwords >= 32) {
+  if (L == 32) {
     for (int p = 0; p < n; p++) {
       int off = __shfl_sync(FULL, roff, p);
       uint32_t s = warp_sum(sad_partial<S>(o, os, r + off, rs, w, h, lane, 32));
       if (lane == p) out = s;
     }
+  } else if (L == 1) {
+    if (lane < n) out = sad_partial<S>(o, os, r + roff, rs, w, h, 0, 1);
   } else {
-    const int g = 32 / nwords;  // positions per pass; nwords is a power of two in {2,4,8,16}
-    const int sub = lane & (nwords - 1), grp = lane / nwords;
+    const int g = 32 / L;  // positions per pass
+    const int sub = lane & (L - 1), grp = lane / L;
     for (int base = 0; base < n; base += g) {
       int p = base + grp;
       int off = __shfl_sync(FULL, roff, p & 31);
-      uint32_t s = (p < n) ? sad_partial<S>(o, os, r + off, rs, w, h, sub, nwords) : 0u;
-      s = group_sum(s, nwords);
-      uint32_t got = __shfl_sync(FULL, s, ((lane - base) * nwords) & 31);
+      uint32_t s = (p < n) ? sad_partial<S>(o, os, r + off, rs, w, h, sub, L) : 0u;
+      s = group_sum(s, L);
+      uint32_t got = __shfl_sync(FULL, s, ((lane - base) * L) & 31);
       if (lane >= base && lane < base + g && lane < n) out = got;
     }
   }
@@ -238,23 +242,24 @@ __device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, 
   }
 }
 
-// SAD between the original block and the luma prediction at a fractional MV, without materialising the prediction
-// (the 8 half-pel + 8 quarter-pel probes of enc/encode_block.c:625-663).
+// SADs between the original block and the luma predictions at EIGHT fractional MVs (one half-pel or quarter-pel stage of
+// enc/encode_block.c:625-663) without materialising the predictions: probe t = lane / 4 uses MV (mvx0 + dx[t], mvy0 + dy[t]),
+// its four lanes share the block's samples.  Every lane of probe t returns SAD t.
 template <class S>
-__device__ uint32_t warp_sad_subpel(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w,
-                                    int pic_h, int xpos, int ypos, int bitdepth) {
+__device__ uint32_t subpel_stage_sads(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w, int pic_h,
+                                      int xpos, int ypos, int bitdepth) {
   int hi, vi, xf, yf;
   split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
   const S *ip = ref + vi * rs + hi;
-  const int maxv = (1 << bitdepth) - 1, lw = ilog2(w);
+  const int maxv = (1 << bitdepth) - 1, lw = ilog2(w), sub = lane_id() & 3;
   uint32_t acc = 0;
-  for (int p = lane_id(); p < (h << lw); p += 32) {
+  for (int p = sub; p < (h << lw); p += 4) {
     int row = p >> lw, col = p & (w - 1);
     const S *q = ip + row * rs + col;
     int v = (xf == 0 && yf == 0) ? (int)q[0] : luma_sample<S>(q, rs, xf, yf, bip, maxv);
     acc += (uint32_t)iabs((int)o[row * os + col] - v);
   }
-  return warp_sum(acc);
+  return group_sum(acc, 4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -361,6 +366,9 @@ __device__ uint32_t warp_sad_fastquarter(const S *o, int os, const S *r, int rs,
 // a5: motion_estimate.  enc/encode_block.c:517-711.  One warp runs one search; every stage evaluates its probes
 // in parallel across lanes and picks the winner with the reference's sequential tie rule (first strict minimum).
 // ---------------------------------------------------------------------------------------------------------------
+// sub-pel probe offsets in visiting order (enc/encode_block.c:627-628, 648-649)
+__constant__ int8_t c_hm[9] = {0, 0, -2, 2, 0, -2, -2, 2, 2}, c_hn[9] = {0, -2, 0, 0, 2, -2, 2, -2, 2};
+__constant__ int8_t c_qm[9] = {0, 0, -1, 1, 0, -1, -1, 1, 1}, c_qn[9] = {0, -1, 0, 0, 1, -1, 1, -1, 1};
 struct MeCtx {
   int size, width, height, sign, s, xpos, ypos, fw, fh, bitdepth, speed, bip;
   int mvpx, mvpy;
@@ -506,21 +514,30 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
   c.n_sub += c.speed == 0 ? 16 : 2;
   if (c.speed == 0) {
     // ---- true half-pel then quarter-pel probes (:625-663)
-    const int8_t hm[9] = {0, 0, -2, 2, 0, -2, -2, 2, 2}, hn[9] = {0, -2, 0, 0, 2, -2, 2, -2, 2};
-    const int8_t qm[9] = {0, 0, -1, 1, 0, -1, -1, 1, 1}, qn[9] = {0, -1, 0, 0, 1, -1, 1, -1, 1};
-    for (int i = 1; i <= 8; i++) {
-      int cy = (int)(int16_t)(refy + hm[i]), cx = (int)(int16_t)(refx + hn[i]);
-      uint32_t sad = warp_sad_subpel<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+    const int8_t *hm = c_hm, *hn = c_hn, *qm = c_qm, *qn = c_qn;
+    // each stage: the eight probes run concurrently on eight 4-lane groups; the winner is then chosen in the reference's
+    // sequential order (strict '<', i = 1..8)
+    {
+      const int t = (lane >> 2) + 1;
+      int cy = (int)(int16_t)(refy + hm[t]), cx = (int)(int16_t)(refx + hn[t]);
+      uint32_t sad = subpel_stage_sads<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
-      if (cost < cmin) { cmin = cost; ydh = hm[i]; xdh = hn[i]; }
+      for (int i = 1; i <= 8; i++) {
+        uint32_t ci = __shfl_sync(FULL, cost, (i - 1) * 4);
+        if (ci < cmin) { cmin = ci; ydh = hm[i]; xdh = hn[i]; }
+      }
     }
     optx = (int)(int16_t)(optx + xdh);
     opty = (int)(int16_t)(opty + ydh);
-    for (int i = 1; i <= 8; i++) {
-      int cy = (int)(int16_t)(opty + qm[i]), cx = (int)(int16_t)(optx + qn[i]);
-      uint32_t sad = warp_sad_subpel<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+    {
+      const int t = (lane >> 2) + 1;
+      int cy = (int)(int16_t)(opty + qm[t]), cx = (int)(int16_t)(optx + qn[t]);
+      uint32_t sad = subpel_stage_sads<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
-      if (cost < cmin) { cmin = cost; ydq = qm[i]; xdq = qn[i]; }
+      for (int i = 1; i <= 8; i++) {
+        uint32_t ci = __shfl_sync(FULL, cost, (i - 1) * 4);
+        if (ci < cmin) { cmin = ci; ydq = qm[i]; xdq = qn[i]; }
+      }
     }
   } else {
     // ---- bilinear approximations (:664-703)
@@ -558,9 +575,21 @@ __device__ __forceinline__ int dct_coef(int lN, int i, int j) {  // N = 1 << lN
   return m > 32 ? -(int)c_T[64 - m] : (int)c_T[m];
 }
 
+// The four matrices (N = 4, 8, 16, 32) as int16 tables for shared memory: lanes of a warp read DIFFERENT coefficients
+// in the transform loops, which constant memory would serialise.  Layout: N=4 @0, 8 @16, 16 @80, 32 @336 (1360 entries).
+constexpr int DCT_TAB_SIZE = 1360;
+__device__ __forceinline__ int dct_tab_ofs(int lN) { return lN == 2 ? 0 : (lN == 3 ? 16 : (lN == 4 ? 80 : 336)); }
+__device__ __forceinline__ void dct_tab_fill(int16_t *tab) {  // call with all threads of the CTA, then __syncthreads()
+  for (int t = threadIdx.x; t < DCT_TAB_SIZE; t += blockDim.x) {
+    int lN = t < 16 ? 2 : (t < 80 ? 3 : (t < 336 ? 4 : 5));
+    int e = t - dct_tab_ofs(lN);
+    tab[t] = (int16_t)dct_coef(lN, e >> lN, e & ((1 << lN) - 1));
+  }
+}
+
 // per-warp scratch: in[32*33] + tmp[16*33] int16 (padded pitch 33 -> conflict-free column access)
-struct TxScratch {
-  int16_t in[32 * 33];
+struct alignas(16) TxScratch {
+  alignas(16) int16_t in[32 * 33];
   int16_t tmp[16 * 33];
   int16_t cq[256];
   int16_t rc[256];
@@ -568,11 +597,12 @@ struct TxScratch {
 
 // Forward transform of `size` x `size` residual (row pitch = size, in global or shared memory) into sc.rc-style
 // compact qsize x qsize output `coef` (pitch qsize).  Returns nothing; all lanes participate.
-__device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, int fast, int bitdepth, TxScratch &sc, int16_t *coef) {
+__device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, int fast, int bitdepth, TxScratch &sc, int16_t *coef, const int16_t *tab) {
   const int lane = lane_id();
   int size1 = size, scale = 1;
   if (size > (32 >> fast)) { size1 = 32 >> fast; scale = size / size1; }
   const int l1 = ilog2(size1), qsize = min(size, 16);
+  const int16_t *M = tab + dct_tab_ofs(l1);
   // load (with box-sum down-scaling for large blocks, saturating like common/transform.c:261-278)
   for (int p = lane; p < size1 * size1; p += 32) {
     int i = p >> l1, j = p & (size1 - 1);
@@ -593,7 +623,7 @@ __device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, i
   for (int p = lane; p < qsize * size1; p += 32) {
     int i = p >> l1, j = p & (size1 - 1);
     int sum = 0;
-    for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.in[j * 33 + k];
+    for (int k = 0; k < size1; k++) sum += (int)M[(i << l1) + k] * (int)sc.in[j * 33 + k];
     sc.tmp[i * 33 + j] = (int16_t)((sum + add1) >> shift1);
   }
   __syncwarp();
@@ -602,7 +632,7 @@ __device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, i
   for (int p = lane; p < qsize * qsize; p += 32) {
     int i = p >> lq, j = p & (qsize - 1);
     int sum = 0;
-    for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.tmp[j * 33 + k];
+    for (int k = 0; k < size1; k++) sum += (int)M[(i << l1) + k] * (int)sc.tmp[j * 33 + k];
     coef[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
   }
   __syncwarp();
@@ -610,15 +640,16 @@ __device__ void warp_fwd_transform(const int16_t *block, int bpitch, int size, i
 
 // Inverse transform from compact qsize x qsize coefficients (pitch cpitch) to a size x size residual block
 // (pitch bpitch; size <= 32 core, 64/128 by sample replication, common/transform.c:467-494).
-__device__ void warp_inv_transform(const int16_t *coef, int cpitch, int size, int bitdepth, TxScratch &sc, int16_t *block, int bpitch) {
+__device__ void warp_inv_transform(const int16_t *coef, int cpitch, int size, int bitdepth, TxScratch &sc, int16_t *block, int bpitch, const int16_t *tab) {
   const int lane = lane_id();
   const int core = min(size, 32), rep = size / core, lc = ilog2(core), qsize = min(size, 16);
   const int shift2 = 20 - bitdepth, add2 = 1 << (shift2 - 1);
+  const int16_t *M = tab + dct_tab_ofs(lc);
   // 1st dimension: tmp[i][j] = clip16((sum_k M[k][j] * coef[k][i] + 64) >> 7), i < qsize, j < core
   for (int p = lane; p < qsize * core; p += 32) {
     int i = p >> lc, j = p & (core - 1);
     int sum = 0;
-    for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)coef[k * cpitch + i];
+    for (int k = 0; k < qsize; k++) sum += (int)M[(k << lc) + j] * (int)coef[k * cpitch + i];
     sc.tmp[i * 33 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
   }
   __syncwarp();
@@ -626,7 +657,7 @@ __device__ void warp_inv_transform(const int16_t *coef, int cpitch, int size, in
   for (int p = lane; p < core * core; p += 32) {
     int i = p >> lc, j = p & (core - 1);
     int sum = 0;
-    for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)sc.tmp[k * 33 + i];
+    for (int k = 0; k < qsize; k++) sum += (int)M[(k << lc) + j] * (int)sc.tmp[k * 33 + i];
     int v = iclip((sum + add2) >> shift2, -32768, 32767);
     if (rep == 1) block[i * bpitch + j] = (int16_t)v;
     else
@@ -723,6 +754,147 @@ __device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int si
   for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[zigzag_index(p >> lq, p & (qsize - 1), qsize)];
   __syncwarp();
   return __any_sync(FULL, cbp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 4x4 transform blocks (68 % of all transform blocks in the HDB mix): ONE THREAD runs the whole chain
+// residual -> 4-point DCT x2 -> quantize -> dequantize -> inverse DCT x2 -> reconstruct -> SSD in registers.
+// Same arithmetic as the generic routines (common/transform.c:281-307, 411-465 with the 4x4 matrix :63-68,
+// enc/encode_block.c:84-160, common/common_block.c:45-83); the butterflies are exact integer refactorings of the
+// matrix products.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dct4_fwd(int a0, int a1, int a2, int a3, int &y0, int &y1, int &y2, int &y3) {
+  int e0 = a0 + a3, e1 = a1 + a2, o0 = a0 - a3, o1 = a1 - a2;
+  y0 = 64 * (e0 + e1); y2 = 64 * (e0 - e1); y1 = 83 * o0 + 36 * o1; y3 = 36 * o0 - 83 * o1;
+}
+__device__ __forceinline__ void dct4_inv(int x0, int x1, int x2, int x3, int &y0, int &y1, int &y2, int &y3) {
+  int e0 = 64 * (x0 + x2), e1 = 64 * (x0 - x2), o0 = 83 * x1 + 36 * x3, o1 = 36 * x1 - 83 * x3;
+  y0 = e0 + o0; y1 = e1 + o1; y2 = e1 - o1; y3 = e0 - o0;
+}
+template <class S> __device__ __forceinline__ void load_row4(const S *p, int (&v)[4]) {
+  if (sizeof(S) == 1) {
+    uint32_t w = ldw_any(p);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = (int)((w >> (8 * i)) & 0xff);
+  } else {
+    uint32_t w0 = ldw_any(p), w1 = ldw_any(p + 2);
+    v[0] = (int)(w0 & 0xffff); v[1] = (int)(w0 >> 16); v[2] = (int)(w1 & 0xffff); v[3] = (int)(w1 >> 16);
+  }
+}
+template <class S> __device__ __forceinline__ void store_row4(S *p, const int (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) p[i] = (S)v[i];
+}
+
+// returns cbp; ssd out
+template <class S>
+__device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
+                            uint64_t &ssd_out) {
+  constexpr int ZZ[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};  // raster -> scan (common/common_tables.c:29-34)
+  const int maxv = (1 << bitdepth) - 1;
+  int o[16], p[16], t[16], c[16];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int a[4], b[4];
+    load_row4<S>(orig + r * os, a);
+    load_row4<S>(pred + r * ps, b);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { o[r * 4 + k] = a[k]; p[r * 4 + k] = b[k]; }
+  }
+  // forward, 1st dimension: t[i][j] = (sum_k M[i][k] * res[j][k] + add1) >> shift1 (int16)
+  const int shift1 = bitdepth - 6, add1 = 1 << (shift1 - 1);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int y0, y1, y2, y3;
+    dct4_fwd(o[j * 4] - p[j * 4], o[j * 4 + 1] - p[j * 4 + 1], o[j * 4 + 2] - p[j * 4 + 2], o[j * 4 + 3] - p[j * 4 + 3], y0, y1, y2, y3);
+    t[0 * 4 + j] = (int16_t)((y0 + add1) >> shift1); t[1 * 4 + j] = (int16_t)((y1 + add1) >> shift1);
+    t[2 * 4 + j] = (int16_t)((y2 + add1) >> shift1); t[3 * 4 + j] = (int16_t)((y3 + add1) >> shift1);
+  }
+  // 2nd dimension: coef[i][j] = (sum_k M[i][k] * t[j][k] + 64) >> 7, stored straight into scan order
+  int sc[16];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int y0, y1, y2, y3;
+    dct4_fwd(t[j * 4], t[j * 4 + 1], t[j * 4 + 2], t[j * 4 + 3], y0, y1, y2, y3);
+    sc[ZZ[0 * 4 + j]] = (int16_t)((y0 + 64) >> 7); sc[ZZ[1 * 4 + j]] = (int16_t)((y1 + 64) >> 7);
+    sc[ZZ[2 * 4 + j]] = (int16_t)((y2 + 64) >> 7); sc[ZZ[3 * 4 + j]] = (int16_t)((y3 + 64) >> 7);
+  }
+  // quantize (enc/encode_block.c:84-160), size 4: shift2 = 19 + qp/6; products fit 32 bits (|c| * 26214 + offset < 2^31)
+  const int intra = (coeff_type >> 1) & 1, scale = c_quant[qp % 6], shift2 = 19 + qp / 6;
+  const int off_last = (intra ? 38 : -26) * (1 << (shift2 - 8));
+  int last = -1;
+#pragma unroll
+  for (int pos = 0; pos < 16; pos++) {
+    int l = iabs(sc[pos]) * scale + off_last;
+    if ((iabs(l) >> shift2) != 0) last = pos;
+  }
+  const int off0 = (intra ? 102 : 51) << (shift2 - 8), off1 = (intra ? 115 : 90) << (shift2 - 8);
+  int mode = 1, cbp = 0, q[16];
+#pragma unroll
+  for (int pos = 0; pos < 16; pos++) {
+    int lev = 0;
+    if (pos <= last) {
+      int ac = scale * iabs(sc[pos]);
+      int level0 = ac >> shift2;
+      lev = (ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2;
+      cbp |= lev != 0;
+      if (mode) { if (lev == 0) mode = 0; }
+      else if (lev > 1) mode = 1;
+    }
+    q[pos] = sc[pos] < 0 ? -lev : lev;
+  }
+  if (coeffq_out) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) coeffq_out[r] = (int16_t)q[ZZ[r]];
+  }
+  uint64_t ssd = 0;
+  if (cbp) {
+    // dequantize (common/common_block.c:45-73), size 4: rshift = 1
+    const int lshift = qp / 6, dscale = c_dequant[qp % 6];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      int v = q[ZZ[r]] * dscale;
+      c[r] = lshift >= 1 ? (int)(int16_t)((unsigned)v << (lshift - 1)) : (int)(int16_t)((v + 1) >> 1);
+    }
+    // inverse, 1st dimension: t[i][j] = clip16((sum_k M[k][j] * c[k][i] + 64) >> 7)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int y0, y1, y2, y3;
+      dct4_inv(c[0 * 4 + i], c[1 * 4 + i], c[2 * 4 + i], c[3 * 4 + i], y0, y1, y2, y3);
+      t[i * 4 + 0] = iclip((y0 + 64) >> 7, -32768, 32767); t[i * 4 + 1] = iclip((y1 + 64) >> 7, -32768, 32767);
+      t[i * 4 + 2] = iclip((y2 + 64) >> 7, -32768, 32767); t[i * 4 + 3] = iclip((y3 + 64) >> 7, -32768, 32767);
+    }
+    // 2nd dimension + reconstruction: out[i][j] = clip16((sum_k M[k][j] * t[k][i] + add2) >> (20 - bitdepth))
+    const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int y[4];
+      dct4_inv(t[0 * 4 + i], t[1 * 4 + i], t[2 * 4 + i], t[3 * 4 + i], y[0], y[1], y[2], y[3]);
+      int v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int r = iclip((y[j] + addB) >> shiftB, -32768, 32767);
+        v[j] = sat_px(r + p[i * 4 + j], maxv);
+        int d = o[i * 4 + j] - v[j];
+        ssd += (uint32_t)(d * d);
+      }
+      if (rec) store_row4<S>(rec + i * rs, v);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        v[j] = p[i * 4 + j];
+        int d = o[i * 4 + j] - v[j];
+        ssd += (uint32_t)(d * d);
+      }
+      if (rec) store_row4<S>(rec + i * rs, v);
+    }
+  }
+  ssd_out = ssd;
+  return cbp;
 }
 
 // a13: dequantize.  common/common_block.c:45-73 (no weight matrix).  compact in, compact out (pitch qsize)

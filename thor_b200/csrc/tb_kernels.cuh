@@ -115,111 +115,138 @@ struct alignas(16) TxShared {
   TxScratch sc;
 };
 
-// residual on the fly -> forward -> quantise -> de-quantise -> inverse -> reconstruct + SSD
+// residual on the fly -> forward -> quantise -> de-quantise -> inverse -> reconstruct + SSD.
+// Each warp takes 32 consecutive items per iteration: its 4x4 items run one per LANE (thread_txfm4, all in registers);
+// larger blocks are then processed one at a time by the whole warp.
 template <class S>
 __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TxScratch &sc = ((TxScratch *)smem_raw)[threadIdx.x >> 5];
+  int16_t *tab = (int16_t *)smem_raw;
+  TxScratch &sc = ((TxScratch *)(smem_raw + ((DCT_TAB_SIZE * 2 + 15) & ~15)))[threadIdx.x >> 5];
+  dct_tab_fill(tab);
+  __syncthreads();
   const int lane = lane_id(), maxv = (1 << bitdepth) - 1;
-  for (int it = global_warp(); it < n; it += total_warps()) {
-    tb_txfm_item_t q = items[it];
-    const S *orig = (const S *)q.orig, *pred = (const S *)q.pred;
-    S *rec = (S *)q.rec;
-    const int size = q.size;
-    int size1 = size, scale = 1;
-    if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
-    const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
-    // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform
-    for (int p = lane; p < size1 * size1; p += 32) {
-      int i = p >> l1, j = p & (size1 - 1), v;
-      if (scale == 1) v = (int)orig[i * q.ostride + j] - (int)pred[i * q.pstride + j];
-      else {
-        int sum = 0;
-        for (int m = 0; m < scale; m++)
-          for (int nn = 0; nn < scale; nn++) {
-            int y = i * scale + m, x = j * scale + nn;
-            sum = iclip(sum + ((int)orig[y * q.ostride + x] - (int)pred[y * q.pstride + x]), -16384, 16383);
-          }
-        v = sum;
-      }
-      sc.in[i * 33 + j] = (int16_t)v;
+  for (int base = global_warp() * 32; base < n; base += total_warps() * 32) {
+    const int mine = base + lane;
+    int my_size = 0;
+    if (mine < n) my_size = items[mine].size;
+    if (my_size == 4) {
+      tb_txfm_item_t q = items[mine];
+      uint64_t ssd;
+      int cbp = thread_txfm4<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, ssd);
+      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
     }
-    __syncwarp();
-    {
-      const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
-      const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
-      for (int p = lane; p < qsize * size1; p += 32) {
-        int i = p >> l1, j = p & (size1 - 1), sum = 0;
-        for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.in[j * 33 + k];
-        sc.tmp[i * 33 + j] = (int16_t)((sum + add1) >> shift1);
+    unsigned big = __ballot_sync(FULL, my_size > 4);
+    while (big) {
+      const int it = base + __ffs(big) - 1;
+      big &= big - 1;
+      tb_txfm_item_t q = items[it];
+      const S *orig = (const S *)q.orig, *pred = (const S *)q.pred;
+      S *rec = (S *)q.rec;
+      const int size = q.size;
+      int size1 = size, scale = 1;
+      if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
+      const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
+      const int16_t *M1 = tab + dct_tab_ofs(l1);
+      // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform
+      for (int p = lane; p < size1 * size1; p += 32) {
+        int i = p >> l1, j = p & (size1 - 1), v;
+        if (scale == 1) v = (int)orig[i * q.ostride + j] - (int)pred[i * q.pstride + j];
+        else {
+          int sum = 0;
+          for (int m = 0; m < scale; m++)
+            for (int nn = 0; nn < scale; nn++) {
+              int y = i * scale + m, x = j * scale + nn;
+              sum = iclip(sum + ((int)orig[y * q.ostride + x] - (int)pred[y * q.pstride + x]), -16384, 16383);
+            }
+          v = sum;
+        }
+        sc.in[i * 33 + j] = (int16_t)v;
       }
       __syncwarp();
-      for (int p = lane; p < qsize * qsize; p += 32) {
-        int i = p >> lq, j = p & (qsize - 1), sum = 0;
-        for (int k = 0; k < size1; k++) sum += dct_coef(l1, i, k) * (int)sc.tmp[j * 33 + k];
-        sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
+      {
+        const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
+        const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
+        for (int p = lane; p < qsize * size1; p += 32) {
+          int i = p >> l1, j = p & (size1 - 1), sum = 0;
+          for (int k = 0; k < size1; k++) sum += (int)M1[(i << l1) + k] * (int)sc.in[j * 33 + k];
+          sc.tmp[i * 33 + j] = (int16_t)((sum + add1) >> shift1);
+        }
+        __syncwarp();
+        for (int p = lane; p < qsize * qsize; p += 32) {
+          int i = p >> lq, j = p & (qsize - 1), sum = 0;
+          for (int k = 0; k < size1; k++) sum += (int)M1[(i << l1) + k] * (int)sc.tmp[j * 33 + k];
+          sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
+        }
+        __syncwarp();
       }
+      int cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
+      if (q.coeffq)
+        for (int p = lane; p < qsize * qsize; p += 32) q.coeffq[p] = sc.cq[p];
+      uint64_t ssd = 0;
+      if (cbp) {
+        warp_dequantize(sc.cq, sc.rc, q.qp, size);
+        // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
+        const int core = min(size, 32), rep = size / core, lc = ilog2(core);
+        const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
+        const int16_t *M2 = tab + dct_tab_ofs(lc);
+        for (int p = lane; p < qsize * core; p += 32) {
+          int i = p >> lc, j = p & (core - 1), sum = 0;
+          for (int k = 0; k < qsize; k++) sum += (int)M2[(k << lc) + j] * (int)sc.rc[k * qsize + i];
+          sc.tmp[i * 33 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+        }
+        __syncwarp();
+        for (int p = lane; p < core * core; p += 32) {
+          int i = p >> lc, j = p & (core - 1), sum = 0;
+          for (int k = 0; k < qsize; k++) sum += (int)M2[(k << lc) + j] * (int)sc.tmp[k * 33 + i];
+          int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+          for (int m = 0; m < rep; m++)
+            for (int nn = 0; nn < rep; nn++) {
+              int y = i * rep + m, x = j * rep + nn;
+              int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
+              if (rec) rec[y * q.rstride + x] = (S)v;
+              int d = (int)orig[y * q.ostride + x] - v;
+              ssd += (uint64_t)(uint32_t)(d * d);
+            }
+        }
+        __syncwarp();
+      } else {
+        // cbp == 0: the reference copies the prediction (enc/encode_block.c:1145-1166 "memcpy pred -> rec")
+        const int ls = ilog2(size);
+        for (int p = lane; p < size * size; p += 32) {
+          int y = p >> ls, x = p & (size - 1);
+          int v = pred[y * q.pstride + x];
+          if (rec) rec[y * q.rstride + x] = (S)v;
+          int d = (int)orig[y * q.ostride + x] - v;
+          ssd += (uint64_t)(uint32_t)(d * d);
+        }
+      }
+      ssd = warp_sum64(ssd);
+      if (lane == 0) { out[it].ssd = ssd; out[it].cbp = cbp; out[it].pad = 0; }
       __syncwarp();
     }
-    int cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
-    if (q.coeffq)
-      for (int p = lane; p < qsize * qsize; p += 32) q.coeffq[p] = sc.cq[p];
-    uint64_t ssd = 0;
-    if (cbp) {
-      warp_dequantize(sc.cq, sc.rc, q.qp, size);
-      // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
-      const int core = min(size, 32), rep = size / core, lc = ilog2(core);
-      const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
-      for (int p = lane; p < qsize * core; p += 32) {
-        int i = p >> lc, j = p & (core - 1), sum = 0;
-        for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)sc.rc[k * qsize + i];
-        sc.tmp[i * 33 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
-      }
-      __syncwarp();
-      for (int p = lane; p < core * core; p += 32) {
-        int i = p >> lc, j = p & (core - 1), sum = 0;
-        for (int k = 0; k < qsize; k++) sum += dct_coef(lc, k, j) * (int)sc.tmp[k * 33 + i];
-        int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-        for (int m = 0; m < rep; m++)
-          for (int nn = 0; nn < rep; nn++) {
-            int y = i * rep + m, x = j * rep + nn;
-            int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
-            if (rec) rec[y * q.rstride + x] = (S)v;
-            int d = (int)orig[y * q.ostride + x] - v;
-            ssd += (uint64_t)(uint32_t)(d * d);
-          }
-      }
-      __syncwarp();
-    } else {
-      // cbp == 0: the reference copies the prediction (enc/encode_block.c:1145-1166 "memcpy pred -> rec")
-      const int ls = ilog2(size);
-      for (int p = lane; p < size * size; p += 32) {
-        int y = p >> ls, x = p & (size - 1);
-        int v = pred[y * q.pstride + x];
-        if (rec) rec[y * q.rstride + x] = (S)v;
-        int d = (int)orig[y * q.ostride + x] - v;
-        ssd += (uint64_t)(uint32_t)(d * d);
-      }
-    }
-    ssd = warp_sum64(ssd);
-    if (lane == 0) { out[it].ssd = ssd; out[it].cbp = cbp; out[it].pad = 0; }
-    __syncwarp();
   }
 }
 
 // drop-in single-shot kernels (one warp)
 __global__ void fwd_transform_kernel(const int16_t *block, int16_t *coeff, int size, int fast, int bitdepth) {
   __shared__ TxShared sh;
+  __shared__ int16_t tab[DCT_TAB_SIZE];
+  dct_tab_fill(tab);
+  __syncthreads();
   const int qsize = min(size, 16);
-  warp_fwd_transform(block, size, size, fast, bitdepth, sh.sc, sh.sc.rc);
+  warp_fwd_transform(block, size, size, fast, bitdepth, sh.sc, sh.sc.rc, tab);
   for (int p = lane_id(); p < qsize * qsize; p += 32) coeff[(p / qsize) * size + (p % qsize)] = sh.sc.rc[p];
 }
 __global__ void inv_transform_kernel(const int16_t *coeff, int16_t *block, int size, int bitdepth) {
   __shared__ TxShared sh;
+  __shared__ int16_t tab[DCT_TAB_SIZE];
+  dct_tab_fill(tab);
+  __syncthreads();
   const int qsize = min(size, 16);
   for (int p = lane_id(); p < qsize * qsize; p += 32) sh.sc.rc[p] = coeff[(p / qsize) * size + (p % qsize)];
   __syncwarp();
-  warp_inv_transform(sh.sc.rc, qsize, size, bitdepth, sh.sc, block, size);
+  warp_inv_transform(sh.sc.rc, qsize, size, bitdepth, sh.sc, block, size, tab);
 }
 __global__ void quant_kernel(const int16_t *coeff, int16_t *coeffq, int qp, int size, int type, int32_t *cbp) {
   __shared__ TxShared sh;
