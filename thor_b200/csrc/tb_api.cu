@@ -93,9 +93,9 @@ struct Win {
 };
 Win win(int s, const void *host, int esz, int stride, int x0, int y0, int x1, int y1, bool upload) {
   Win w;
-  // widen to 16-byte columns so that the logical origin keeps 16-byte alignment on the device
-  int per = 16 / esz;
-  int x0r = (x0 >= 0 ? x0 / per : -((-x0 + per - 1) / per)) * per;
+  // the window starts at device offset 0 of a 256-byte aligned slot: operands whose window starts at x0 = 0 (original
+  // blocks, transform buffers) keep their alignment; halo windows (x0 < 0) are only read with alignment-agnostic loads
+  const int x0r = x0;
   w.esz = esz; w.stride = stride; w.x0 = x0r; w.y0 = y0; w.x1 = x1; w.y1 = y1; w.host = (const char *)host;
   w.pitch = (((size_t)(x1 - x0r) * esz + 4) + 15) & ~(size_t)15;  // +4: ldw_any may touch the next word
   w.base = (char *)slot_buf(s, w.pitch * (size_t)(y1 - y0) + 64);
