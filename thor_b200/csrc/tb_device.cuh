@@ -987,6 +987,99 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
   return cbp;
 }
 
+// 8x8 transform blocks: also one THREAD per block.  The 64-entry work arrays live in local memory, which the hardware
+// interleaves per thread, so the lock-step (uniform-index) accesses of a warp coalesce into L1 lines; the DCT matrix is
+// read from the shared-memory table with a warp-uniform index (broadcast).  Same arithmetic as warp_fwd_transform /
+// warp_quantize / warp_dequantize / warp_inv_transform.
+template <class S>
+__device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
+                            const int16_t *tab, uint64_t &ssd_out) {
+  const int16_t *M = tab + dct_tab_ofs(3);
+  const int maxv = (1 << bitdepth) - 1;
+  int16_t a[64], b[64];  // a: residual -> coefficients (scan order) ; b: intermediate
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 8; c++) a[r * 8 + c] = (int16_t)((int)orig[r * os + c] - (int)pred[r * ps + c]);
+  const int shift1 = 3 + bitdepth - 8, add1 = 1 << (shift1 - 1);
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += (int)M[i * 8 + k] * (int)a[j * 8 + k];
+      b[i * 8 + j] = (int16_t)((sum + add1) >> shift1);
+    }
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += (int)M[i * 8 + k] * (int)b[j * 8 + k];
+      a[zigzag_index(i, j, 8)] = (int16_t)((sum + 128) >> 8);  // scan order
+    }
+  const int intra = (coeff_type >> 1) & 1, scale = c_quant[qp % 6], shift2 = 18 + qp / 6;
+  const int off_last = (intra ? 38 : -26) * (1 << (shift2 - 8));
+  int last = -1;
+  for (int pos = 0; pos < 64; pos++) {
+    int l = iabs((int)a[pos]) * scale + off_last;
+    if ((iabs(l) >> shift2) != 0) last = pos;
+  }
+  const int off0 = (intra ? 102 : 51) << (shift2 - 8), off1 = (intra ? 115 : 90) << (shift2 - 8);
+  int mode = 1, cbp = 0;
+  for (int pos = 0; pos < 64; pos++) {
+    int lev = 0, cc = a[pos];
+    if (pos <= last) {
+      int ac = scale * iabs(cc);
+      int level0 = ac >> shift2;
+      lev = (ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2;
+      cbp |= lev != 0;
+      if (mode) { if (lev == 0) mode = 0; }
+      else if (lev > 1) mode = 1;
+    }
+    b[pos] = (int16_t)(cc < 0 ? -lev : lev);  // quantised, scan order
+  }
+  if (coeffq_out)
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) coeffq_out[i * 8 + j] = b[zigzag_index(i, j, 8)];
+  uint64_t ssd = 0;
+  if (cbp) {
+    const int lshift = qp / 6, dscale = c_dequant[qp % 6];  // rshift = 2
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) {
+        int v = (int)b[zigzag_index(i, j, 8)] * dscale;
+        a[i * 8 + j] = lshift >= 2 ? (int16_t)((unsigned)v << (lshift - 2)) : (int16_t)((v + (1 << (1 - lshift))) >> (2 - lshift));
+      }
+    // inverse 1st dimension: b[i][j] = clip16((sum_k M[k][j] * a[k][i] + 64) >> 7)
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += (int)M[k * 8 + j] * (int)a[k * 8 + i];
+        b[i * 8 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+      }
+    const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += (int)M[k * 8 + j] * (int)b[k * 8 + i];
+        int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+        int pv = pred[i * ps + j];
+        int v = sat_px(r + pv, maxv);
+        if (rec) rec[i * rs + j] = (S)v;
+        int d = (int)orig[i * os + j] - v;
+        ssd += (uint32_t)(d * d);
+      }
+  } else {
+    for (int i = 0; i < 8; i++)
+      for (int j = 0; j < 8; j++) {
+        int v = pred[i * ps + j];
+        if (rec) rec[i * rs + j] = (S)v;
+        int d = (int)orig[i * os + j] - v;
+        ssd += (uint32_t)(d * d);
+      }
+  }
+  ssd_out = ssd;
+  return cbp;
+}
+
 // a13: dequantize.  common/common_block.c:45-73 (no weight matrix).  compact in, compact out (pitch qsize)
 __device__ void warp_dequantize(const int16_t *cq, int16_t *rc, int qp, int size) {
   const int lshift = qp / 6, qsize = min(size, 16), rshift = ilog2(size) - 1;

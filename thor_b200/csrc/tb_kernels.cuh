@@ -116,8 +116,8 @@ struct alignas(16) TxShared {
 };
 
 // residual on the fly -> forward -> quantise -> de-quantise -> inverse -> reconstruct + SSD.
-// Each warp takes 32 consecutive items per iteration: its 4x4 items run one per LANE (thread_txfm4, all in registers);
-// larger blocks are then processed one at a time by the whole warp.
+// Each warp takes 32 consecutive items per iteration: its 4x4 and 8x8 items run one per LANE (thread_txfm4 in registers,
+// thread_txfm8 in per-thread local arrays); larger blocks are then processed one at a time by the whole warp.
 template <class S>
 __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,8 +135,13 @@ __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_i
       uint64_t ssd;
       int cbp = thread_txfm4<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, ssd);
       out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
+    } else if (my_size == 8) {
+      tb_txfm_item_t q = items[mine];
+      uint64_t ssd;
+      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab, ssd);
+      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
     }
-    unsigned big = __ballot_sync(FULL, my_size > 4);
+    unsigned big = __ballot_sync(FULL, my_size > 8);
     while (big) {
       const int it = base + __ffs(big) - 1;
       big &= big - 1;
