@@ -62,37 +62,47 @@ template <class S> __device__ __forceinline__ int word_px(uint32_t w, int i) {
 // ---------------------------------------------------------------------------------------------------------------
 template <class S>
 __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, int rs, int w, int h, int sub, int nl) {
+  // Lane `sub` of `nl` takes the rows sub, sub+nl, ... (nl <= h).  Row pitches are multiples of 4 bytes, so the byte
+  // misalignment of the reference row is the same for every row: one aligned word stream per row, one funnel shift per word.
   constexpr int PW = Word<S>::PW;
-  const int lw = ilog2(w / PW);  // words per row = 1 << lw
-  const int nwords = h << lw;
+  const int ww = w / PW;  // words per row
+  const uintptr_t ra = (uintptr_t)r;
+  const unsigned sh = (unsigned)(ra & 3) * 8;
+  const uint32_t *rq = (const uint32_t *)(ra & ~(uintptr_t)3);
+  const uint32_t *oq = (const uint32_t *)o;
+  const int rsw = (rs * (int)sizeof(S)) >> 2, osw = (os * (int)sizeof(S)) >> 2;  // pitches in words
   uint32_t acc = 0;
-  for (int wi = sub; wi < nwords; wi += nl) {
-    int row = wi >> lw, col = (wi & ((1 << lw) - 1)) * PW;
-    uint32_t a = *(const uint32_t *)(o + row * os + col);
-    uint32_t b = ldw_any(r + row * rs + col);
-    acc += word_sad<S>(a, b);
+  for (int row = sub; row < h; row += nl) {
+    const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
+    uint32_t prev = q[0];
+    for (int c = 0; c < ww; c++) {
+      uint32_t nxt = q[c + 1];
+      acc += word_sad<S>(a[c], __funnelshift_r(prev, nxt, sh));
+      prev = nxt;
+    }
   }
   return acc;
 }
 // whole warp on one block
 template <class S> __device__ __forceinline__ uint32_t warp_sad(const S *o, int os, const S *r, int rs, int w, int h) {
-  return warp_sum(sad_partial<S>(o, os, r, rs, w, h, lane_id(), 32));
+  return warp_sum(lane_id() < h ? sad_partial<S>(o, os, r, rs, w, h, lane_id(), 32) : 0u);
 }
 
 // SADs of up to 32 reference positions of the same block: lane i supplies the sample offset `roff` of position i
 // (i < n); lane i receives SAD i.  L = lanes cooperating on one position = words/16 (1 for blocks up to 8x8 u8: the
 // whole 5x5 telescope grid is then evaluated in ONE pass, one position per lane, no shuffles), 32 for >= 512 words.
 template <class S>
-__device__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+__device__ __noinline__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
   constexpr int PW = Word<S>::PW;
   const int lane = lane_id();
   const int nwords = (w / PW) * h;
-  const int L = nwords >= 512 ? 32 : (nwords <= 16 ? 1 : nwords >> 4);  // power of two
+  int L = nwords >= 512 ? 32 : (nwords <= 16 ? 1 : nwords >> 4);  // power of two
+  if (L > h) L = h;  // rows are dealt to lanes
   uint32_t out = 0;
   if (L == 32) {
     for (int p = 0; p < n; p++) {
       int off = __shfl_sync(FULL, roff, p);
-      uint32_t s = warp_sum(sad_partial<S>(o, os, r + off, rs, w, h, lane, 32));
+      uint32_t s = warp_sum(lane < h ? sad_partial<S>(o, os, r + off, rs, w, h, lane, 32) : 0u);
       if (lane == p) out = s;
     }
   } else if (L == 1) {
@@ -327,7 +337,7 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
 // enc/encode_block.c:625-663) without materialising the predictions: probe t = lane / 4 uses MV (mvx0 + dx[t], mvy0 + dy[t]),
 // its four lanes share the block's samples.  Every lane of probe t returns SAD t.
 template <class S>
-__device__ uint32_t subpel_stage_sads(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w, int pic_h,
+__device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w, int pic_h,
                                       int xpos, int ypos, int bitdepth) {
   int hi, vi, xf, yf;
   split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
@@ -361,7 +371,7 @@ __device__ __forceinline__ int dn2(int a, int b) { return (a + b) >> 1; }
 
 // order: top, down, right, left, tl, tr, br, bl
 template <class S>
-__device__ uint32_t warp_sad_fasthalf(const S *a, int as, const S *b, int bs, int w, int h, int &bx, int &by) {
+__device__ __noinline__ uint32_t warp_sad_fasthalf(const S *a, int as, const S *b, int bs, int w, int h, int &bx, int &by) {
   uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int lw = ilog2(w);
   for (int p = lane_id(); p < (h << lw); p += 32) {
@@ -405,7 +415,7 @@ __device__ uint32_t warp_sad_fasthalf(const S *a, int as, const S *b, int bs, in
 
 // order: top, tl, tr, left, right, bl, down, br.  fx, fy: half-pel offset found so far (selects the formula set)
 template <class S>
-__device__ uint32_t warp_sad_fastquarter(const S *o, int os, const S *r, int rs, int w, int h, int fx, int fy, int &bx, int &by) {
+__device__ __noinline__ uint32_t warp_sad_fastquarter(const S *o, int os, const S *r, int rs, int w, int h, int fx, int fy, int &bx, int &by) {
   uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int lw = ilog2(w);
   for (int p = lane_id(); p < (h << lw); p += 32) {
@@ -677,10 +687,32 @@ __device__ __forceinline__ void dct_tab_fill(int16_t *tab) {  // call with all t
   }
 }
 
+// int8 forms (all coefficients are within +-90) for the DP2A inner loops: tab8[ofs + i*N + k] = M[i][k] and
+// tab8t[ofs + j*N + k] = M[k][j]; every row starts 4-byte aligned.
+__device__ __forceinline__ void dct_tab8_fill(int8_t *tab8, int8_t *tab8t) {
+  for (int t = threadIdx.x; t < DCT_TAB_SIZE; t += blockDim.x) {
+    int lN = t < 16 ? 2 : (t < 80 ? 3 : (t < 336 ? 4 : 5));
+    int e = t - dct_tab_ofs(lN), i = e >> lN, k = e & ((1 << lN) - 1);
+    tab8[t] = (int8_t)dct_coef(lN, i, k);
+    tab8t[t] = (int8_t)dct_coef(lN, k, i);
+  }
+}
+// sum += m[0..n) . v[0..n)  (m: int8 row, v: int16 row, both 4-byte aligned, n a multiple of 4): two DP2A per four terms
+__device__ __forceinline__ int dot_s8_s16(const int8_t *m, const int16_t *v, int n) {
+  int sum = 0;
+  const uint32_t *mw = (const uint32_t *)m, *vw = (const uint32_t *)v;
+  for (int k = 0; k < (n >> 2); k++) {
+    uint32_t mm = mw[k];
+    sum = __dp2a_lo((int)vw[2 * k], (int)mm, sum);
+    sum = __dp2a_hi((int)vw[2 * k + 1], (int)mm, sum);
+  }
+  return sum;
+}
+
 // per-warp scratch: in[32*33] + tmp[16*33] int16 (padded pitch 33 -> conflict-free column access)
 struct alignas(16) TxScratch {
-  alignas(16) int16_t in[32 * 33];
-  int16_t tmp[16 * 33];
+  alignas(16) int16_t in[48 * 34];   // forward input tile (<= 32 rows, pitch 34) / inverse: rcoeff^T (16 rows) + T^T (32 rows)
+  alignas(16) int16_t tmp[16 * 34];
   int16_t cq[256];
   int16_t rc[256];
 };
@@ -993,8 +1025,8 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
 // warp_quantize / warp_dequantize / warp_inv_transform.
 template <class S>
 __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
-                            const int16_t *tab, uint64_t &ssd_out) {
-  const int16_t *M = tab + dct_tab_ofs(3);
+                            const int8_t *tab8, uint64_t &ssd_out) {
+  const int8_t *M = tab8 + dct_tab_ofs(3);
   const int maxv = (1 << bitdepth) - 1;
   int16_t a[64], b[64];  // a: residual -> coefficients (scan order) ; b: intermediate
   for (int r = 0; r < 8; r++)

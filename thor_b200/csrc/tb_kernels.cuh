@@ -60,7 +60,7 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 
 // ---- a5 --------------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
+__global__ void __launch_bounds__(CTA_THREADS, 6) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
                                                                int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   for (int it = global_warp(); it < n; it += total_warps()) {
     tb_me_item_t q = items[it];
@@ -119,13 +119,14 @@ struct alignas(16) TxShared {
 // Each warp takes 32 consecutive items per iteration: its 4x4 and 8x8 items run one per LANE (thread_txfm4 in registers,
 // thread_txfm8 in per-thread local arrays); larger blocks are then processed one at a time by the whole warp.
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
+__global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int16_t *tab = (int16_t *)smem_raw;
+  int8_t *tab8 = (int8_t *)smem_raw, *tab8t = tab8 + DCT_TAB_SIZE;
   TxScratch &sc = ((TxScratch *)(smem_raw + ((DCT_TAB_SIZE * 2 + 15) & ~15)))[threadIdx.x >> 5];
-  dct_tab_fill(tab);
+  dct_tab8_fill(tab8, tab8t);
   __syncthreads();
   const int lane = lane_id(), maxv = (1 << bitdepth) - 1;
+  constexpr int PI = 34;  // int16 pitch of the scratch tiles: even (4-byte aligned pairs for DP2A), 17 words -> odd word pitch
   for (int base = global_warp() * 32; base < n; base += total_warps() * 32) {
     const int mine = base + lane;
     int my_size = 0;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_i
     } else if (my_size == 8) {
       tb_txfm_item_t q = items[mine];
       uint64_t ssd;
-      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab, ssd);
+      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, ssd);
       out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
     }
     unsigned big = __ballot_sync(FULL, my_size > 8);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_i
       int size1 = size, scale = 1;
       if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
       const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
-      const int16_t *M1 = tab + dct_tab_ofs(l1);
+      const int8_t *M1 = tab8 + dct_tab_ofs(l1);
       // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform
       for (int p = lane; p < size1 * size1; p += 32) {
         int i = p >> l1, j = p & (size1 - 1), v;
@@ -166,21 +167,23 @@ __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_i
             }
           v = sum;
         }
-        sc.in[i * 33 + j] = (int16_t)v;
+        sc.in[i * PI + j] = (int16_t)v;
       }
       __syncwarp();
       {
         const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
         const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
+        // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < qsize, j < size1)
         for (int p = lane; p < qsize * size1; p += 32) {
-          int i = p >> l1, j = p & (size1 - 1), sum = 0;
-          for (int k = 0; k < size1; k++) sum += (int)M1[(i << l1) + k] * (int)sc.in[j * 33 + k];
-          sc.tmp[i * 33 + j] = (int16_t)((sum + add1) >> shift1);
+          int i = p >> l1, j = p & (size1 - 1);
+          int sum = dot_s8_s16(M1 + (i << l1), sc.in + j * PI, size1);
+          sc.tmp[i * PI + j] = (int16_t)((sum + add1) >> shift1);
         }
         __syncwarp();
+        // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < qsize)
         for (int p = lane; p < qsize * qsize; p += 32) {
-          int i = p >> lq, j = p & (qsize - 1), sum = 0;
-          for (int k = 0; k < size1; k++) sum += (int)M1[(i << l1) + k] * (int)sc.tmp[j * 33 + k];
+          int i = p >> lq, j = p & (qsize - 1);
+          int sum = dot_s8_s16(M1 + (i << l1), sc.tmp + j * PI, size1);
           sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
         }
         __syncwarp();
@@ -190,20 +193,34 @@ __global__ void __launch_bounds__(CTA_THREADS) txfm_chain_kernel(const tb_txfm_i
         for (int p = lane; p < qsize * qsize; p += 32) q.coeffq[p] = sc.cq[p];
       uint64_t ssd = 0;
       if (cbp) {
-        warp_dequantize(sc.cq, sc.rc, q.qp, size);
+        // de-quantise (common/common_block.c:45-73) straight into the TRANSPOSED tile in[i][k] = rcoeff[k][i], so that the
+        // inverse transform's sums over k read contiguous int16 pairs
+        {
+          const int lshift = q.qp / 6, rshift = ilog2(size) - 1;
+          const int64_t dscale = c_dequant[q.qp % 6];
+          const int64_t dadd = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
+          for (int p = lane; p < qsize * qsize; p += 32) {
+            int k = p >> lq, i = p & (qsize - 1), c = sc.cq[p];
+            sc.in[i * PI + k] = lshift >= rshift ? (int16_t)((c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + dadd) >> (rshift - lshift));
+          }
+          __syncwarp();
+        }
         // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
         const int core = min(size, 32), rep = size / core, lc = ilog2(core);
         const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
-        const int16_t *M2 = tab + dct_tab_ofs(lc);
+        const int8_t *Mt = tab8t + dct_tab_ofs(lc);
+        // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < qsize, j < core)
+        int16_t *tmp2 = sc.in + 16 * PI;  // rows 16.. of the `in` tile are free here (rcoeff^T uses rows 0..15)
         for (int p = lane; p < qsize * core; p += 32) {
-          int i = p >> lc, j = p & (core - 1), sum = 0;
-          for (int k = 0; k < qsize; k++) sum += (int)M2[(k << lc) + j] * (int)sc.rc[k * qsize + i];
-          sc.tmp[i * 33 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+          int i = p >> lc, j = p & (core - 1);
+          int sum = dot_s8_s16(Mt + (j << lc), sc.in + i * PI, qsize);
+          tmp2[j * PI + i] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
         }
         __syncwarp();
+        // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core)
         for (int p = lane; p < core * core; p += 32) {
-          int i = p >> lc, j = p & (core - 1), sum = 0;
-          for (int k = 0; k < qsize; k++) sum += (int)M2[(k << lc) + j] * (int)sc.tmp[k * 33 + i];
+          int i = p >> lc, j = p & (core - 1);
+          int sum = dot_s8_s16(Mt + (j << lc), tmp2 + i * PI, qsize);
           int r = iclip((sum + addB) >> shiftB, -32768, 32767);
           for (int m = 0; m < rep; m++)
             for (int nn = 0; nn < rep; nn++) {
