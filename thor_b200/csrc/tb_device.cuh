@@ -74,10 +74,10 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   uint32_t acc = 0;
   for (int row = sub; row < h; row += nl) {
     const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
-    uint32_t prev = q[0];
+    uint32_t prev = __ldg(q);  // frames are read-only inside these kernels: LDG.CONSTANT instead of generic LD
     for (int c = 0; c < ww; c++) {
-      uint32_t nxt = q[c + 1];
-      acc += word_sad<S>(a[c], __funnelshift_r(prev, nxt, sh));
+      uint32_t nxt = __ldg(q + c + 1);
+      acc += word_sad<S>(__ldg(a + c), __funnelshift_r(prev, nxt, sh));
       prev = nxt;
     }
   }
@@ -273,7 +273,7 @@ __device__ __forceinline__ void hfilt4_u8(const uint8_t *p, uint32_t tlo, uint32
   uintptr_t a = (uintptr_t)(p - 2);
   const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
   const unsigned sh = (unsigned)(a & 3) * 8;
-  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
   const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -304,7 +304,7 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
         int v = (h1m[k] + h2a[k] + h2b[k] + h1p[k] + 8) >> 4;  // max 12*255+8 -> <= 191: already inside 0..255
         pk |= (uint32_t)v << (8 * k);
       }
-      acc += __vsadu4(*(const uint32_t *)(o + y * os + x0), pk);
+      acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
 #pragma unroll
       for (int k = 0; k < 4; k++) { h1m[k] = t1[k]; t1[k] = t2[k]; t2[k] = h1p[k]; h2a[k] = h2b[k]; h2b[k] = n2[k]; }
     }
@@ -328,7 +328,7 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
       int sum = v0 * H[0][k] + v1 * H[1][k] + v2 * H[2][k] + v3 * H[3][k] + v4 * H[4][k] + v5 * H[5][k];
       pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
     }
-    acc += __vsadu4(*(const uint32_t *)(o + y * os + x0), pk);
+    acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
   }
   return acc;
 }
