@@ -312,23 +312,33 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
   }
   const int8_t *fh = c_luma_taps[bip ? 1 : 0][xf], *fv = c_luma_taps[bip ? 1 : 0][yf];
   const uint32_t tlo = pack_s8x4(fh[0], fh[1], fh[2], fh[3]), thi = pack_s8x4(fh[4], fh[5], 0, 0);
-  const int v0 = fv[0], v1 = fv[1], v2 = fv[2], v3 = fv[3], v4 = fv[4], v5 = fv[5];
-  int H[6][4];  // filtered rows y-2 .. y+3
+  int fvr[6];
 #pragma unroll
-  for (int m = 0; m < 5; m++) hfilt4_u8(ip + (y0 - 2 + m) * rs + x0, tlo, thi, H[m + 1]);
-  for (int y = y0; y < y0 + nrows; y++) {
+  for (int m = 0; m < 6; m++) fvr[m] = fv[m];
+  // Ring of the six most recent filtered rows, addressed with compile-time indices: the row loop is unrolled by six so
+  // that no register moves are needed to slide the window.  H[(y - y0 + m) % 6] holds filtered row y - 2 + m.
+  int H[6][4];
 #pragma unroll
-    for (int m = 0; m < 5; m++)
+  for (int m = 0; m < 5; m++) hfilt4_u8(ip + (y0 - 2 + m) * rs + x0, tlo, thi, H[m]);
+  const uint8_t *nrow = ip + (y0 + 3) * rs + x0;
+  const uint8_t *orow = o + y0 * os + x0;
+  for (int yb = 0; yb < nrows; yb += 6) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) H[m][k] = H[m + 1][k];
-    hfilt4_u8(ip + (y + 3) * rs + x0, tlo, thi, H[5]);
-    uint32_t pk = 0;
+    for (int ph = 0; ph < 6; ph++) {
+      if (yb + ph < nrows) {
+        hfilt4_u8(nrow, tlo, thi, H[(ph + 5) % 6]);
+        nrow += rs;
+        uint32_t pk = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int sum = v0 * H[0][k] + v1 * H[1][k] + v2 * H[2][k] + v3 * H[3][k] + v4 * H[4][k] + v5 * H[5][k];
-      pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
+        for (int k = 0; k < 4; k++) {
+          int sum = fvr[0] * H[ph % 6][k] + fvr[1] * H[(ph + 1) % 6][k] + fvr[2] * H[(ph + 2) % 6][k] + fvr[3] * H[(ph + 3) % 6][k] +
+                    fvr[4] * H[(ph + 4) % 6][k] + fvr[5] * H[(ph + 5) % 6][k];
+          pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
+        }
+        acc += __vsadu4(__ldg((const uint32_t *)orow), pk);
+        orow += os;
+      }
     }
-    acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
   }
   return acc;
 }
@@ -346,7 +356,8 @@ __device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *
   uint32_t acc = 0;
   if (sizeof(S) == 1) {
     // units of 4 columns x RH rows, dealt round-robin to the probe's four lanes
-    const int RH = h >= 8 ? 8 : h, nseg = h / RH, units = (w >> 2) * nseg;
+    // segment height: tall enough to amortise the 5-row filter halo, short enough to give every lane of the probe work
+    const int RH = (w >> 2) * (h >> 4) >= 4 ? 16 : (h >= 8 && (w >> 2) * (h >> 3) >= 4 ? 8 : (h >= 8 ? 8 : h)), nseg = h / RH, units = (w >> 2) * nseg;
     for (int u = sub; u < units; u += 4) {
       int strip = u / nseg, seg = u - strip * nseg;
       acc += strip_sad_subpel_u8((const uint8_t *)o, os, (const uint8_t *)ip, rs, strip * 4, seg * RH, RH, xf, yf, bip);

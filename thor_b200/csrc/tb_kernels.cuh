@@ -60,7 +60,7 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 
 // ---- a5 --------------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, 6) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
+__global__ void __launch_bounds__(CTA_THREADS, 5) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
                                                                int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   for (int it = global_warp(); it < n; it += total_warps()) {
     tb_me_item_t q = items[it];
