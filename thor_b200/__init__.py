@@ -13,7 +13,7 @@ import numpy as np
 from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthor_b200.so")
+LIB_PATH = os.environ.get("THOR_B200_LIB") or os.path.join(_HERE, "libthor_b200.so")  # env override: A/B builds of the same sources
 
 TB_OK, TB_ERR_CUDA, TB_ERR_ARG = 0, -1, -2
 
@@ -23,7 +23,7 @@ class ThorB200Error(RuntimeError):
 
 
 def _load():
-    if _build.stale():
+    if _build.stale() and not os.environ.get("THOR_B200_LIB"):
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box: use the prebuilt library if there is one

@@ -26,21 +26,21 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    if not force and not stale() and out is None:
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc()] + flags + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
+    cmd = [nvcc()] + flags + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log" if out is None else os.path.basename(out) + ".log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if r.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libthor_b200.so")
     if verbose:
         print(log)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -364,7 +364,7 @@ int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int 
 int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, int bitdepth, tb_txfm_result_t *out) {
   API_BEGIN();
   if (n <= 0) return TB_OK;
-  size_t smem = ((DCT_TAB_SIZE * 2 + 15) & ~15) + sizeof(TxScratch) * WARPS_PER_CTA;
+  size_t smem = ((DCT_TAB8_SIZE * 2 + 15) & ~15) + sizeof(TxScratch) * WARPS_PER_CTA;
   const int warps = (n + 31) / 32;  // each warp iteration consumes 32 items
   if (sample_bytes == 1) LAUNCH(txfm_chain_kernel<uint8_t>, grid_for_warps(warps), CTA_THREADS, smem, items, n, bitdepth, out);
   else LAUNCH(txfm_chain_kernel<uint16_t>, grid_for_warps(warps), CTA_THREADS, smem, items, n, bitdepth, out);

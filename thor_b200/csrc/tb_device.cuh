@@ -12,6 +12,13 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef TB_SUBPEL_RING
+#define TB_SUBPEL_RING 0  // 1: ring-indexed filtered-row window unrolled by six (measured slower on B200: larger code)
+#endif
+#ifndef TB_SUBPEL_RH16
+#define TB_SUBPEL_RH16 0
+#endif
+
 namespace tb {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -60,26 +67,51 @@ template <class S> __device__ __forceinline__ int word_px(uint32_t w, int i) {
 // `o` must be 4-byte aligned with an even word pitch (original blocks always are); `r` arbitrary.
 // Lanes sub..sub+nl-1 of a group share the block; returns this lane's partial sum.
 // ---------------------------------------------------------------------------------------------------------------
+// SAD of an NR-row x NW-word tile: all 2*NR*NW + NR loads are issued before the first use (memory-level parallelism;
+// the per-word loop of the first version waited ~one L1 latency per word).
+template <class S, int NW, int NR>
+__device__ __forceinline__ uint32_t sad_tile(const uint32_t *q, int qstep, const uint32_t *a, int astep, unsigned sh) {
+  uint32_t qv[NR][NW + 1], av[NR][NW];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+#pragma unroll
+    for (int c = 0; c <= NW; c++) qv[r][c] = __ldg(q + r * qstep + c);  // frames are read-only here: LDG.CONSTANT
+#pragma unroll
+    for (int c = 0; c < NW; c++) av[r][c] = __ldg(a + r * astep + c);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+#pragma unroll
+    for (int c = 0; c < NW; c++) acc += word_sad<S>(av[r][c], __funnelshift_r(qv[r][c], qv[r][c + 1], sh));
+  return acc;
+}
+
 template <class S>
 __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, int rs, int w, int h, int sub, int nl) {
   // Lane `sub` of `nl` takes the rows sub, sub+nl, ... (nl <= h).  Row pitches are multiples of 4 bytes, so the byte
   // misalignment of the reference row is the same for every row: one aligned word stream per row, one funnel shift per word.
   constexpr int PW = Word<S>::PW;
-  const int ww = w / PW;  // words per row
+  const int ww = w / PW;  // words per row: 1, 2, 4, 8, 16, 32 (64 for 128-wide u16)
   const uintptr_t ra = (uintptr_t)r;
   const unsigned sh = (unsigned)(ra & 3) * 8;
   const uint32_t *rq = (const uint32_t *)(ra & ~(uintptr_t)3);
   const uint32_t *oq = (const uint32_t *)o;
   const int rsw = (rs * (int)sizeof(S)) >> 2, osw = (os * (int)sizeof(S)) >> 2;  // pitches in words
   uint32_t acc = 0;
-  for (int row = sub; row < h; row += nl) {
-    const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
-    uint32_t prev = __ldg(q);  // frames are read-only inside these kernels: LDG.CONSTANT instead of generic LD
-    for (int c = 0; c < ww; c++) {
-      uint32_t nxt = __ldg(q + c + 1);
-      acc += word_sad<S>(__ldg(a + c), __funnelshift_r(prev, nxt, sh));
-      prev = nxt;
-    }
+  int row = sub;
+  if (ww == 1) {
+    for (; row + 3 * nl < h; row += 4 * nl) acc += sad_tile<S, 1, 4>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
+    for (; row < h; row += nl) acc += sad_tile<S, 1, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
+  } else if (ww == 2) {
+    for (; row + 3 * nl < h; row += 4 * nl) acc += sad_tile<S, 2, 4>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
+    for (; row < h; row += nl) acc += sad_tile<S, 2, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
+  } else if (ww == 4) {
+    for (; row + nl < h; row += 2 * nl) acc += sad_tile<S, 4, 2>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
+    for (; row < h; row += nl) acc += sad_tile<S, 4, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
+  } else {
+    for (; row < h; row += nl)
+      for (int c = 0; c < ww; c += 8) acc += sad_tile<S, 8, 1>(rq + row * rsw + c, 0, oq + row * osw + c, 0, sh);
   }
   return acc;
 }
@@ -312,6 +344,28 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
   }
   const int8_t *fh = c_luma_taps[bip ? 1 : 0][xf], *fv = c_luma_taps[bip ? 1 : 0][yf];
   const uint32_t tlo = pack_s8x4(fh[0], fh[1], fh[2], fh[3]), thi = pack_s8x4(fh[4], fh[5], 0, 0);
+#if !TB_SUBPEL_RING
+  const int v0 = fv[0], v1 = fv[1], v2 = fv[2], v3 = fv[3], v4 = fv[4], v5 = fv[5];
+  int H[6][4];  // filtered rows y-2 .. y+3
+#pragma unroll
+  for (int m = 0; m < 5; m++) hfilt4_u8(ip + (y0 - 2 + m) * rs + x0, tlo, thi, H[m + 1]);
+  for (int y = y0; y < y0 + nrows; y++) {
+#pragma unroll
+    for (int m = 0; m < 5; m++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) H[m][k] = H[m + 1][k];
+    hfilt4_u8(ip + (y + 3) * rs + x0, tlo, thi, H[5]);
+    uint32_t pk = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int sum = v0 * H[0][k] + v1 * H[1][k] + v2 * H[2][k] + v3 * H[3][k] + v4 * H[4][k] + v5 * H[5][k];
+      pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
+    }
+    acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
+  }
+  return acc;
+}
+#else
   int fvr[6];
 #pragma unroll
   for (int m = 0; m < 6; m++) fvr[m] = fv[m];
@@ -342,6 +396,7 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
   }
   return acc;
 }
+#endif
 
 // SADs between the original block and the luma predictions at EIGHT fractional MVs (one half-pel or quarter-pel stage of
 // enc/encode_block.c:625-663) without materialising the predictions: probe t = lane / 4 uses MV (mvx0 + dx[t], mvy0 + dy[t]),
@@ -357,7 +412,11 @@ __device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *
   if (sizeof(S) == 1) {
     // units of 4 columns x RH rows, dealt round-robin to the probe's four lanes
     // segment height: tall enough to amortise the 5-row filter halo, short enough to give every lane of the probe work
-    const int RH = (w >> 2) * (h >> 4) >= 4 ? 16 : (h >= 8 && (w >> 2) * (h >> 3) >= 4 ? 8 : (h >= 8 ? 8 : h)), nseg = h / RH, units = (w >> 2) * nseg;
+#if TB_SUBPEL_RH16
+    const int RH = (w >> 2) * (h >> 4) >= 4 ? 16 : (h >= 8 ? 8 : h), nseg = h / RH, units = (w >> 2) * nseg;
+#else
+    const int RH = h >= 8 ? 8 : h, nseg = h / RH, units = (w >> 2) * nseg;
+#endif
     for (int u = sub; u < units; u += 4) {
       int strip = u / nseg, seg = u - strip * nseg;
       acc += strip_sad_subpel_u8((const uint8_t *)o, os, (const uint8_t *)ip, rs, strip * 4, seg * RH, RH, xf, yf, bip);
@@ -690,6 +749,11 @@ __device__ __forceinline__ int dct_coef(int lN, int i, int j) {  // N = 1 << lN
 // in the transform loops, which constant memory would serialise.  Layout: N=4 @0, 8 @16, 16 @80, 32 @336 (1360 entries).
 constexpr int DCT_TAB_SIZE = 1360;
 __device__ __forceinline__ int dct_tab_ofs(int lN) { return lN == 2 ? 0 : (lN == 3 ? 16 : (lN == 4 ? 80 : 336)); }
+// int8 tables use padded row pitches so that lanes reading DIFFERENT rows at the same column hit different banks:
+// N = 4: 4 B, 8: 8 B (<= 8 rows: no conflict), 16: 20 B, 32: 36 B.
+constexpr int DCT_TAB8_SIZE = 16 + 64 + 16 * 20 + 32 * 36;  // 1552
+__device__ __forceinline__ int dct_tab8_ofs(int lN) { return lN == 2 ? 0 : (lN == 3 ? 16 : (lN == 4 ? 80 : 400)); }
+__device__ __forceinline__ int dct_tab8_pitch(int lN) { return lN == 2 ? 4 : (lN == 3 ? 8 : (lN == 4 ? 20 : 36)); }
 __device__ __forceinline__ void dct_tab_fill(int16_t *tab) {  // call with all threads of the CTA, then __syncthreads()
   for (int t = threadIdx.x; t < DCT_TAB_SIZE; t += blockDim.x) {
     int lN = t < 16 ? 2 : (t < 80 ? 3 : (t < 336 ? 4 : 5));
@@ -704,8 +768,9 @@ __device__ __forceinline__ void dct_tab8_fill(int8_t *tab8, int8_t *tab8t) {
   for (int t = threadIdx.x; t < DCT_TAB_SIZE; t += blockDim.x) {
     int lN = t < 16 ? 2 : (t < 80 ? 3 : (t < 336 ? 4 : 5));
     int e = t - dct_tab_ofs(lN), i = e >> lN, k = e & ((1 << lN) - 1);
-    tab8[t] = (int8_t)dct_coef(lN, i, k);
-    tab8t[t] = (int8_t)dct_coef(lN, k, i);
+    int d = dct_tab8_ofs(lN) + i * dct_tab8_pitch(lN) + k;
+    tab8[d] = (int8_t)dct_coef(lN, i, k);
+    tab8t[d] = (int8_t)dct_coef(lN, k, i);
   }
 }
 // sum += m[0..n) . v[0..n)  (m: int8 row, v: int16 row, both 4-byte aligned, n a multiple of 4): two DP2A per four terms
@@ -915,8 +980,15 @@ template <class S> __device__ __forceinline__ void load_row4(const S *p, int (&v
   }
 }
 template <class S> __device__ __forceinline__ void store_row4(S *p, const int (&v)[4]) {
+  if (sizeof(S) == 1 && (((uintptr_t)p) & 3) == 0) {
+    *(uint32_t *)p = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+  } else if (sizeof(S) == 2 && (((uintptr_t)p) & 3) == 0) {
+    ((uint32_t *)p)[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+    ((uint32_t *)p)[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+  } else {
 #pragma unroll
-  for (int i = 0; i < 4; i++) p[i] = (S)v[i];
+    for (int i = 0; i < 4; i++) p[i] = (S)v[i];
+  }
 }
 
 // returns cbp; ssd out
@@ -1037,7 +1109,7 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
 template <class S>
 __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
                             const int8_t *tab8, uint64_t &ssd_out) {
-  const int8_t *M = tab8 + dct_tab_ofs(3);
+  const int8_t *M = tab8 + dct_tab8_ofs(3);  // pitch 8
   const int maxv = (1 << bitdepth) - 1;
   int16_t a[64], b[64];  // a: residual -> coefficients (scan order) ; b: intermediate
   for (int r = 0; r < 8; r++)

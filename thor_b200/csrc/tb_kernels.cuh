@@ -60,7 +60,7 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 
 // ---- a5 --------------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, 5) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
+__global__ void __launch_bounds__(CTA_THREADS, 4) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
                                                                int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   for (int it = global_warp(); it < n; it += total_warps()) {
     tb_me_item_t q = items[it];
@@ -121,8 +121,8 @@ struct alignas(16) TxShared {
 template <class S>
 __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int8_t *tab8 = (int8_t *)smem_raw, *tab8t = tab8 + DCT_TAB_SIZE;
-  TxScratch &sc = ((TxScratch *)(smem_raw + ((DCT_TAB_SIZE * 2 + 15) & ~15)))[threadIdx.x >> 5];
+  int8_t *tab8 = (int8_t *)smem_raw, *tab8t = tab8 + DCT_TAB8_SIZE;
+  TxScratch &sc = ((TxScratch *)(smem_raw + ((DCT_TAB8_SIZE * 2 + 15) & ~15)))[threadIdx.x >> 5];
   dct_tab8_fill(tab8, tab8t);
   __syncthreads();
   const int lane = lane_id(), maxv = (1 << bitdepth) - 1;
@@ -153,21 +153,28 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
       int size1 = size, scale = 1;
       if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
       const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
-      const int8_t *M1 = tab8 + dct_tab_ofs(l1);
+      const int8_t *M1 = tab8 + dct_tab8_ofs(l1);
+      const int mp1 = dct_tab8_pitch(l1);
       // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform
-      for (int p = lane; p < size1 * size1; p += 32) {
-        int i = p >> l1, j = p & (size1 - 1), v;
-        if (scale == 1) v = (int)orig[i * q.ostride + j] - (int)pred[i * q.pstride + j];
-        else {
-          int sum = 0;
+      if (scale == 1) {
+        for (int p = lane; p < (size1 * size1) >> 2; p += 32) {  // four samples per lane and step
+          int i = p >> (l1 - 2), j = (p & ((size1 >> 2) - 1)) << 2;
+          int a[4], b[4];
+          load_row4<S>(orig + i * q.ostride + j, a);
+          load_row4<S>(pred + i * q.pstride + j, b);
+#pragma unroll
+          for (int t = 0; t < 4; t++) sc.in[i * PI + j + t] = (int16_t)(a[t] - b[t]);
+        }
+      } else {
+        for (int p = lane; p < size1 * size1; p += 32) {
+          int i = p >> l1, j = p & (size1 - 1), sum = 0;
           for (int m = 0; m < scale; m++)
             for (int nn = 0; nn < scale; nn++) {
               int y = i * scale + m, x = j * scale + nn;
               sum = iclip(sum + ((int)orig[y * q.ostride + x] - (int)pred[y * q.pstride + x]), -16384, 16383);
             }
-          v = sum;
+          sc.in[i * PI + j] = (int16_t)sum;
         }
-        sc.in[i * PI + j] = (int16_t)v;
       }
       __syncwarp();
       {
@@ -176,14 +183,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
         // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < qsize, j < size1)
         for (int p = lane; p < qsize * size1; p += 32) {
           int i = p >> l1, j = p & (size1 - 1);
-          int sum = dot_s8_s16(M1 + (i << l1), sc.in + j * PI, size1);
+          int sum = dot_s8_s16(M1 + i * mp1, sc.in + j * PI, size1);
           sc.tmp[i * PI + j] = (int16_t)((sum + add1) >> shift1);
         }
         __syncwarp();
         // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < qsize)
         for (int p = lane; p < qsize * qsize; p += 32) {
           int i = p >> lq, j = p & (qsize - 1);
-          int sum = dot_s8_s16(M1 + (i << l1), sc.tmp + j * PI, size1);
+          int sum = dot_s8_s16(M1 + i * mp1, sc.tmp + j * PI, size1);
           sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
         }
         __syncwarp();
@@ -208,28 +215,47 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
         // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
         const int core = min(size, 32), rep = size / core, lc = ilog2(core);
         const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
-        const int8_t *Mt = tab8t + dct_tab_ofs(lc);
+        const int8_t *Mt = tab8t + dct_tab8_ofs(lc);
+        const int mpc = dct_tab8_pitch(lc);
         // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < qsize, j < core)
         int16_t *tmp2 = sc.in + 16 * PI;  // rows 16.. of the `in` tile are free here (rcoeff^T uses rows 0..15)
         for (int p = lane; p < qsize * core; p += 32) {
           int i = p >> lc, j = p & (core - 1);
-          int sum = dot_s8_s16(Mt + (j << lc), sc.in + i * PI, qsize);
+          int sum = dot_s8_s16(Mt + j * mpc, sc.in + i * PI, qsize);
           tmp2[j * PI + i] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
         }
         __syncwarp();
         // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core)
-        for (int p = lane; p < core * core; p += 32) {
-          int i = p >> lc, j = p & (core - 1);
-          int sum = dot_s8_s16(Mt + (j << lc), tmp2 + i * PI, qsize);
-          int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-          for (int m = 0; m < rep; m++)
-            for (int nn = 0; nn < rep; nn++) {
-              int y = i * rep + m, x = j * rep + nn;
-              int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
-              if (rec) rec[y * q.rstride + x] = (S)v;
-              int d = (int)orig[y * q.ostride + x] - v;
+        if (rep == 1) {
+          for (int p = lane; p < (core * core) >> 2; p += 32) {  // four samples per lane and step: word loads/stores
+            int i = p >> (lc - 2), j = (p & ((core >> 2) - 1)) << 2;
+            int pv[4], ov[4], v[4];
+            load_row4<S>(pred + i * q.pstride + j, pv);
+            load_row4<S>(orig + i * q.ostride + j, ov);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              int sum = dot_s8_s16(Mt + (j + t) * mpc, tmp2 + i * PI, qsize);
+              int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+              v[t] = sat_px(r + pv[t], maxv);
+              int d = ov[t] - v[t];
               ssd += (uint64_t)(uint32_t)(d * d);
             }
+            if (rec) store_row4<S>(rec + i * q.rstride + j, v);
+          }
+        } else {
+          for (int p = lane; p < core * core; p += 32) {
+            int i = p >> lc, j = p & (core - 1);
+            int sum = dot_s8_s16(Mt + j * mpc, tmp2 + i * PI, qsize);
+            int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+            for (int m = 0; m < rep; m++)
+              for (int nn = 0; nn < rep; nn++) {
+                int y = i * rep + m, x = j * rep + nn;
+                int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
+                if (rec) rec[y * q.rstride + x] = (S)v;
+                int d = (int)orig[y * q.ostride + x] - v;
+                ssd += (uint64_t)(uint32_t)(d * d);
+              }
+          }
         }
         __syncwarp();
       } else {
