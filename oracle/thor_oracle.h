@@ -82,6 +82,7 @@ void orc_cdef_prepare_input_##SFX(int sizex, int sizey, int xpos, int ypos, int 
 void orc_cdef_plane_##SFX(const S *src, S *dst, int stride, int width, int height, const orc_blkinfo_t *bi, int bi_stride, int sub, int plane, const int8_t *fb_pri, const int8_t *fb_sec, int pri_damping, int sec_damping, int *dirs, int *vars, int bitdepth); \
 void orc_pad_plane_##SFX(S *p, int stride, int w, int h, int pad_hor, int pad_ver); \
 void orc_scale_down2x2_##SFX(const S *in, int si, S *out, int so, int wo, int ho); \
+void orc_interpolate_frames_##SFX(S *outY, S *outU, S *outV, int so_y, int so_c, const S *r0Y, const S *r0U, const S *r0V, const S *r1Y, const S *r1U, const S *r1V, int sy, int sc, int width, int height, int pad, int ratio, int pos, int max_levels); \
 int  orc_motion_estimate_##SFX(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int encoder_speed, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred);
 
 ORC_DECL(uint8_t, lbd)

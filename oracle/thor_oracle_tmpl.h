@@ -770,3 +770,297 @@ int FN(orc_motion_estimate)(const S *orig, const S *ref, int size, int stride_r,
   *mv = opt;
   return (int)(cmin < min_sad ? cmin : min_sad);
 }
+
+/* ---- a21: temporal frame interpolation.  common/temporal_interp.c:36-992.
+ * Hierarchical (<= 4 levels, 2x2 down-scaled luma), raster-order bi-directional block matching on 16x16 blocks stored on
+ * an 8x8 grid, with skip test, neighbour/guide candidates, cross refinement and a neighbour-smoothness cost; then a merge
+ * pass per 8x8 block and integer-pel bi-directional averaging of all three planes.  MVs are in 1/8 sample units and are
+ * rounded to integers for every access ((mv + 4) >> 3).  mv[1] refers to the farther picture, mv[0] = scaled mv[1]. ---- */
+typedef struct {
+  orc_mv_t *mv[2];
+  int *bgmap;
+  int wt[2], reversed, bw, bh;
+  orc_mv_t skip_mv, scaled_skip_mv;
+} FN(orc_ti_mvd);
+
+typedef struct { const S *y; int stride, width, height, pad; } FN(orc_ti_pic);
+
+#ifndef ORC_TI_HELPERS
+#define ORC_TI_HELPERS
+static int orc_ti_scale_val(int v, int numer, int denom) {
+  if (denom == 0) return 0;
+  int prod = v * numer;
+  if (denom < 0) { denom = -denom; prod = -prod; }
+  return prod >= 0 ? (prod + denom / 2) / denom : -((-prod + denom / 2) / denom);
+}
+static orc_mv_t orc_ti_scale_mv(orc_mv_t mv, int numer, int denom) {
+  orc_mv_t o;
+  if (numer == denom) return mv;
+  if (numer == -denom) { o.x = (int16_t)-mv.x; o.y = (int16_t)-mv.y; return o; }
+  o.x = (int16_t)orc_ti_scale_val(mv.x, numer, denom);
+  o.y = (int16_t)orc_ti_scale_val(mv.y, numer, denom);
+  return o;
+}
+static int orc_ti_add_cand(orc_mv_t *list, int max, int len, orc_mv_t c) { /* temporal_interp.c:205-218 */
+  if (len < max) {
+    list[len] = c;
+    for (int i = 0; i < len; i++)
+      if (list[i].x == c.x && list[i].y == c.y) return len;
+    return len + 1;
+  }
+  return len;
+}
+static orc_mv_t orc_ti_absdist_filter(const orc_mv_t *l, int num) { /* :695-716, ties -> last */
+  int best = 0, best_cost = 0x3fffffff;
+  for (int j = 0; j < num; j++) {
+    int cost = 0;
+    for (int i = 0; i < num; i++) cost += abs(l[i].x - l[j].x) + abs(l[i].y - l[j].y);
+    if (cost <= best_cost) { best = j; best_cost = cost; }
+  }
+  return l[best];
+}
+#endif
+
+/* :375-456 (luma only): SAD between the two displaced size x size blocks; clipped per-sample form outside the padding */
+static uint32_t FN(orc_ti_sad_cost)(int xstart, int ystart, const FN(orc_ti_pic) *pic, const orc_mv_t *mv, int size, uint32_t cost_start) {
+  int xs[2], ys[2];
+  for (int t = 0; t < 2; t++) { xs[t] = xstart + ((mv[t].x + 4) >> 3); ys[t] = ystart + ((mv[t].y + 4) >> 3); }
+  const int pad = pic[0].pad, wP = pic[0].width + pad, hP = pic[0].height + pad;
+  const int s0 = pic[0].stride, s1 = pic[1].stride;
+  uint32_t c = cost_start;
+  if (xs[0] >= -pad && xs[0] + size <= wP && ys[0] >= -pad && ys[0] + size <= hP && xs[1] >= -pad && xs[1] + size <= wP && ys[1] >= -pad && ys[1] + size <= hP) {
+    c += FN(orc_sad)(pic[0].y + ys[0] * s0 + xs[0], pic[1].y + ys[1] * s1 + xs[1], s0, s1, size, size);
+  } else {
+    for (int i = 0; i < size; i++)
+      for (int j = 0; j < size; j++) {
+        int x0 = j + xs[0], x1 = j + xs[1], y0 = i + ys[0], y1 = i + ys[1];
+        x0 = x0 < -pad ? -pad : (x0 > wP - 1 ? wP - 1 : x0); x1 = x1 < -pad ? -pad : (x1 > wP - 1 ? wP - 1 : x1);
+        y0 = y0 < -pad ? -pad : (y0 > hP - 1 ? hP - 1 : y0); y1 = y1 < -pad ? -pad : (y1 > hP - 1 ? hP - 1 : y1);
+        c += (uint32_t)abs((int)pic[1].y[y1 * s1 + x1] - (int)pic[0].y[y0 * s0 + x0]);
+      }
+  }
+  return c;
+}
+
+static int FN(orc_ti_mv_cost)(orc_mv_t mv, const FN(orc_ti_mvd) *d, int xp, int yp, int st, int lambda) { /* :299-317, idx = 1 */
+  const orc_mv_t *a = d->mv[1];
+  int bw = d->bw, diff = 0;
+#define ORC_TI_D(p) (abs(mv.x - a[p].x) + abs(mv.y - a[p].y))
+  if (xp == 0 && yp == 0) diff = 0;
+  else if (yp > 0 && xp > 0 && xp < bw - st)
+    diff = ORC_TI_D((yp - st) * bw + xp + st) + ORC_TI_D((yp - st) * bw + xp) + ORC_TI_D((yp - st) * bw + xp - st) + ORC_TI_D(yp * bw + xp - st);
+  else if (yp == 0) diff = ORC_TI_D(xp - st);
+  else if (xp == 0) diff = ORC_TI_D((yp - st) * bw + xp + st) + ORC_TI_D((yp - st) * bw + xp);
+#undef ORC_TI_D
+  return (diff * lambda) >> 7;
+}
+
+/* :786-875 */
+static void FN(orc_ti_motion_estimate_bi)(FN(orc_ti_mvd) *d, const FN(orc_ti_mvd) *guide, const FN(orc_ti_pic) *in0, const FN(orc_ti_pic) *in1) {
+  const int bw = d->bw, bh = d->bh, st = 2, n = bw * bh;
+  if (!guide) { memset(d->mv[0], 0, sizeof(orc_mv_t) * (size_t)n); memset(d->mv[1], 0, sizeof(orc_mv_t) * (size_t)n); }
+  memset(d->bgmap, 0, sizeof(int) * (size_t)n);
+  FN(orc_ti_pic) pic[2];
+  pic[0] = d->reversed ? *in1 : *in0;
+  pic[1] = d->reversed ? *in0 : *in1;
+  const int pad = pic[0].pad, wP = pic[0].width + pad, hP = pic[0].height + pad;
+  orc_mv_t cand[20];
+  for (int i = 0; i < bh; i += st)
+    for (int j = 0; j < bw; j += st) {
+      const int pos = i * bw + j, xstart = j * 8, ystart = i * 8;
+      /* skip vector from the causal neighbours (:758-770) */
+      {
+        orc_mv_t vl[3];
+        int num = 0;
+        d->skip_mv.x = d->skip_mv.y = 0;
+        if (i > 0 && j < bw - st) vl[num++] = d->mv[1][(i - st) * bw + j + st];
+        if (j > 0) vl[num++] = d->mv[1][i * bw + j - st];
+        if (i > 0) vl[num++] = d->mv[1][(i - st) * bw + j];
+        if (num) d->skip_mv = orc_ti_absdist_filter(vl, num);
+        d->scaled_skip_mv = orc_ti_scale_mv(d->skip_mv, -d->wt[1], d->wt[0]);
+      }
+      /* skip test (:458-580): all four 8x8 quarters inside the padded area with SAD <= 8*64 */
+      {
+        orc_mv_t m1 = d->skip_mv, m0 = d->scaled_skip_mv;
+        int skip = 1;
+        for (int p = ystart; p < ystart + 16 && skip; p += 8)
+          for (int q = xstart; q < xstart + 16 && skip; q += 8) {
+            int x0 = q + ((m0.x + 4) >> 3), x1 = q + ((m1.x + 4) >> 3), y0 = p + ((m0.y + 4) >> 3), y1 = p + ((m1.y + 4) >> 3);
+            if (x0 >= -pad && x0 + 8 <= wP && y0 >= -pad && y0 + 8 <= hP && x1 >= -pad && x1 + 8 <= wP && y1 >= -pad && y1 + 8 <= hP) {
+              if ((int)FN(orc_sad)(pic[0].y + y0 * pic[0].stride + x0, pic[1].y + y1 * pic[1].stride + x1, pic[0].stride, pic[1].stride, 8, 8) > 8 * 64) skip = 0;
+            } else
+              skip = 0;
+          }
+        if (skip) { d->bgmap[pos] = 1; d->mv[1][pos] = d->skip_mv; d->mv[0][pos] = d->scaled_skip_mv; }
+      }
+      if (!d->bgmap[pos]) {
+        /* candidates (:230-283): zero, the guide's vector, up-right, left, up */
+        int len = 0;
+        orc_mv_t zero = {0, 0};
+        len = orc_ti_add_cand(cand, 20, len, zero);
+        if (guide) {
+          int numer = (d->reversed == guide->reversed) ? d->wt[0] : -d->wt[0];
+          len = orc_ti_add_cand(cand, 20, len, orc_ti_scale_mv(guide->mv[1][pos], numer, guide->wt[0]));
+        }
+        if (i > 0 && j < bw - st) len = orc_ti_add_cand(cand, 20, len, d->mv[1][(i - st) * bw + j + st]);
+        if (j > 0) len = orc_ti_add_cand(cand, 20, len, d->mv[1][i * bw + j - st]);
+        if (i > 0) len = orc_ti_add_cand(cand, 20, len, d->mv[1][(i - st) * bw + j]);
+        /* adaptive search (:584-668) */
+        const int guided = guide != NULL, lambda = guided ? 3000 / 4 : 3000;
+        orc_mv_t best_mv = cand[0], best_smv = orc_ti_scale_mv(cand[0], -d->wt[1], d->wt[0]);
+        uint32_t best_cost = 0x3fffffff;
+        for (int c = 0; c < len; c++) {
+          orc_mv_t mv[2], rl, rsl;
+          mv[1] = cand[c];
+          mv[0] = orc_ti_scale_mv(cand[c], -d->wt[1], d->wt[0]);
+          uint32_t cc = (uint32_t)FN(orc_ti_mv_cost)(cand[c], d, j, i, st, lambda);
+          cc = FN(orc_ti_sad_cost)(xstart, ystart, pic, mv, 16, cc);
+          rl = mv[1];
+          rsl = mv[0];
+          if (((4 + (uint32_t)c) * cc) / 8 < best_cost) {
+            int shift = guided ? 3 : 6, count = guided ? 8 : 64;
+            while (shift >= 3 && count > 0) {
+              int off = 1 << shift, better = 0;
+              orc_mv_t centre = rl;
+              for (int k = 0; k < 4; k++) {
+                orc_mv_t r = centre;
+                if (k == 0) r.x = (int16_t)(centre.x - off);
+                else if (k == 1) r.x = (int16_t)(centre.x + off);
+                else if (k == 2) r.y = (int16_t)(centre.y - off);
+                else r.y = (int16_t)(centre.y + off);
+                mv[1] = r;
+                mv[0] = orc_ti_scale_mv(r, -d->wt[1], d->wt[0]);
+                uint32_t bc = (uint32_t)FN(orc_ti_mv_cost)(r, d, j, i, st, lambda);
+                bc = FN(orc_ti_sad_cost)(xstart, ystart, pic, mv, 16, bc);
+                if (bc < cc) { cc = bc; rl = r; rsl = mv[0]; better = 1; }
+              }
+              if (!better) shift--;
+              count -= 4;
+            }
+          }
+          if (cc < best_cost) { best_mv = rl; best_smv = rsl; best_cost = cc; }
+        }
+        d->mv[1][pos] = best_mv;
+        d->mv[0][pos] = best_smv;
+      }
+      for (int q = 0; q < st; q++)
+        for (int p = 0; p < st; p++) { d->mv[0][pos + q * bw + p] = d->mv[0][pos]; d->mv[1][pos + q * bw + p] = d->mv[1][pos]; d->bgmap[pos + q * bw + p] = d->bgmap[pos]; }
+    }
+  /* merge pass on the 8x8 grid (:219-229, 670-693, 853-872) */
+  orc_mv_t *m0 = (orc_mv_t *)malloc(sizeof(orc_mv_t) * (size_t)n), *m1 = (orc_mv_t *)malloc(sizeof(orc_mv_t) * (size_t)n);
+  for (int i = 0; i < bh; i++)
+    for (int j = 0; j < bw; j++) {
+      int len = 0, off = (i & 1) ? 2 : 1;
+      len = orc_ti_add_cand(cand, 20, len, d->mv[1][i * bw + j]);
+      if (i - off >= 0) len = orc_ti_add_cand(cand, 20, len, d->mv[1][(i - off) * bw + j]);
+      if (i + off < bh) len = orc_ti_add_cand(cand, 20, len, d->mv[1][(i + off) * bw + j]);
+      if (j - off >= 0) len = orc_ti_add_cand(cand, 20, len, d->mv[1][i * bw + j - off]);
+      if (j + off < bw) len = orc_ti_add_cand(cand, 20, len, d->mv[1][i * bw + j + off]);
+      if (len > 1) {
+        uint32_t best = 0x3fffffff;
+        orc_mv_t bm = {0, 0}, bs = {0, 0};
+        for (int c = 0; c < len; c++) {
+          orc_mv_t mv[2];
+          mv[1] = cand[c];
+          mv[0] = orc_ti_scale_mv(cand[c], -d->wt[1], d->wt[0]);
+          uint32_t bc = FN(orc_ti_sad_cost)(j * 8, i * 8, pic, mv, 8, 0);
+          if (bc < best) { best = bc; bm = cand[c]; bs = mv[0]; }
+        }
+        m1[i * bw + j] = bm;
+        m0[i * bw + j] = bs;
+      } else {
+        m0[i * bw + j] = d->mv[0][i * bw + j];
+        m1[i * bw + j] = d->mv[1][i * bw + j];
+      }
+    }
+  memcpy(d->mv[0], m0, sizeof(orc_mv_t) * (size_t)n);
+  memcpy(d->mv[1], m1, sizeof(orc_mv_t) * (size_t)n);
+  free(m0);
+  free(m1);
+}
+
+/* :319-373, 877-935: integer-pel bi-directional average of one plane */
+static void FN(orc_ti_interp_plane)(const FN(orc_ti_mvd) *d, const S *p0, int s0, const S *p1, int s1, S *out, int so, int wP, int hP, int pad, int chroma) {
+  const int bs = chroma ? 4 : 8;
+  for (int yp = 0; yp < d->bh; yp++)
+    for (int xp = 0; xp < d->bw; xp++) {
+      orc_mv_t mv0 = d->mv[0][yp * d->bw + xp], mv1 = d->mv[1][yp * d->bw + xp];
+      if (chroma) { mv1.x >>= 1; mv1.y >>= 1; mv0 = orc_ti_scale_mv(mv1, -d->wt[1], d->wt[0]); }
+      const int xstart = xp * bs, ystart = yp * bs;
+      int xs[2] = {xstart + ((mv0.x + 4) >> 3), xstart + ((mv1.x + 4) >> 3)}, ys[2] = {ystart + ((mv0.y + 4) >> 3), ystart + ((mv1.y + 4) >> 3)};
+      int in0 = xs[0] >= -pad && xs[0] + bs <= wP && ys[0] >= -pad && ys[0] + bs <= hP, in1 = xs[1] >= -pad && xs[1] + bs <= wP && ys[1] >= -pad && ys[1] + bs <= hP;
+      S *p = out + ystart * so + xstart;
+      for (int i = 0; i < bs; i++)
+        for (int j = 0; j < bs; j++) {
+          if (in0 && in1) p[i * so + j] = (S)(((int)p0[(ys[0] + i) * s0 + xs[0] + j] + (int)p1[(ys[1] + i) * s1 + xs[1] + j] + 1) >> 1);
+          else if (in1) p[i * so + j] = p1[(ys[1] + i) * s1 + xs[1] + j];
+          else if (in0) p[i * so + j] = p0[(ys[0] + i) * s1 + xs[0] + j]; /* sic: row pitch s1 (temporal_interp.c:353) */
+          else {
+            int x0 = j + xs[0], x1 = j + xs[1], y0 = i + ys[0], y1 = i + ys[1];
+            x0 = x0 < -pad ? -pad : (x0 > wP - 1 ? wP - 1 : x0); x1 = x1 < -pad ? -pad : (x1 > wP - 1 ? wP - 1 : x1);
+            y0 = y0 < -pad ? -pad : (y0 > hP - 1 ? hP - 1 : y0); y1 = y1 < -pad ? -pad : (y1 > hP - 1 ? hP - 1 : y1);
+            p[i * so + j] = (S)(((int)p0[y0 * s0 + x0] + (int)p1[y1 * s1 + x1] + 1) / 2);
+          }
+        }
+    }
+}
+
+static void FN(orc_ti_alloc)(FN(orc_ti_mvd) *d, int w, int h, int ratio, int k) { /* :84-129, interpolate = 1 */
+  d->bw = 2 * ((w + 15) / 16);
+  d->bh = 2 * ((h + 15) / 16);
+  size_t n = (size_t)d->bw * d->bh;
+  d->mv[0] = (orc_mv_t *)calloc(n, sizeof(orc_mv_t));
+  d->mv[1] = (orc_mv_t *)calloc(n, sizeof(orc_mv_t));
+  d->bgmap = (int *)calloc(n, sizeof(int));
+  d->reversed = k > ratio / 2;
+  d->wt[0] = d->reversed ? k : ratio - k;
+  d->wt[1] = ratio - d->wt[0];
+}
+
+/* outY/U/V: planes of the new frame at sample (0,0) (needs >= 8 samples of writable border right/below); r0x, r1x: the two
+ * references with `pad` samples of replicated border (luma; pad/2 chroma).  max_levels is computed by the caller exactly as
+ * the reference does (:914, double log10).  Level l > 0 pictures are 2x2 down-scaled luma with 32 samples of border. */
+void FN(orc_interpolate_frames)(S *outY, S *outU, S *outV, int so_y, int so_c, const S *r0Y, const S *r0U, const S *r0V, const S *r1Y, const S *r1U,
+                                const S *r1V, int sy, int sc, int width, int height, int pad, int ratio, int pos, int max_levels) {
+  FN(orc_ti_mvd) mvd[4], spat[4];
+  S *buf[4][2] = {{0}};
+  FN(orc_ti_pic) in[4][2];
+  in[0][0].y = r0Y; in[0][1].y = r1Y;
+  for (int t = 0; t < 2; t++) { in[0][t].stride = sy; in[0][t].width = width; in[0][t].height = height; in[0][t].pad = pad; }
+  for (int l = 0; l < max_levels; l++) { FN(orc_ti_alloc)(&mvd[l], width >> l, height >> l, ratio, pos); FN(orc_ti_alloc)(&spat[l], width >> l, height >> l, ratio, pos); }
+  for (int l = 1; l < max_levels; l++) {
+    int w = width >> l, h = height >> l, st = (w + 64 + 15) & ~15;
+    for (int t = 0; t < 2; t++) {
+      buf[l][t] = (S *)calloc((size_t)st * (h + 64) + 64, sizeof(S));
+      S *o = buf[l][t] + 32 * st + 32;
+      FN(orc_scale_down2x2)(in[l - 1][t].y, in[l - 1][t].stride, o, st, w, h);
+      FN(orc_pad_plane)(o, st, w, h, 32, 32);
+      in[l][t].y = o; in[l][t].stride = st; in[l][t].width = w; in[l][t].height = h; in[l][t].pad = 32;
+    }
+  }
+  for (int l = max_levels - 1; l >= 0; l--) {
+    FN(orc_ti_motion_estimate_bi)(&mvd[l], l != max_levels - 1 ? &spat[l] : NULL, &in[l][0], &in[l][1]);
+    if (l > 0) { /* upscale_mv_data_2x2 :176-203 */
+      FN(orc_ti_mvd) *o = &spat[l - 1];
+      for (int i = 0; i < o->bh; i++)
+        for (int j = 0; j < o->bw; j++) {
+          orc_mv_t m = mvd[l].mv[1][(i / 2) * mvd[l].bw + j / 2];
+          m.x = (int16_t)(m.x << 1);
+          m.y = (int16_t)(m.y << 1);
+          o->mv[1][i * o->bw + j] = m;
+          o->mv[0][i * o->bw + j] = orc_ti_scale_mv(m, -o->wt[1], o->wt[0]);
+        }
+    }
+  }
+  {
+    const FN(orc_ti_mvd) *d = &mvd[0];
+    const int rev = d->reversed, wP = width + 4, hP = height + 4;
+    FN(orc_ti_interp_plane)(d, rev ? r1Y : r0Y, sy, rev ? r0Y : r1Y, sy, outY, so_y, wP, hP, 4, 0);
+    FN(orc_ti_interp_plane)(d, rev ? r1U : r0U, sc, rev ? r0U : r1U, sc, outU, so_c, wP >> 1, hP >> 1, 2, 1);
+    FN(orc_ti_interp_plane)(d, rev ? r1V : r0V, sc, rev ? r0V : r1V, sc, outV, so_c, wP >> 1, hP >> 1, 2, 1);
+  }
+  for (int l = 0; l < max_levels; l++) {
+    free(mvd[l].mv[0]); free(mvd[l].mv[1]); free(mvd[l].bgmap); free(spat[l].mv[0]); free(spat[l].mv[1]); free(spat[l].bgmap);
+    if (l) { free(buf[l][0]); free(buf[l][1]); }
+  }
+}

@@ -499,3 +499,41 @@ def test_motion_estimate(hbd, bd):
         a = getattr(O, "orc_motion_estimate_" + s)(P(org), refp, size, f.sy, width, height, m0, mvc, mvp, C.c_double(lam), speed, bd, sign, fw, fh, xpos, ypos, cands, nc, bip)
         b = getattr(E, "ref_motion_estimate_" + s)(P(org), refp, size, f.sy, width, height, m1, mvc, mvp, C.c_double(lam), speed, bd, sign, fw, fh, xpos, ypos, cands, nc, bip)
         assert (a, m0[0], m0[1]) == (b, m1[0], m1[1]), (trial, size, width, height, speed, sign, bip)
+
+
+def _ti_pair(rng, w, h, bd, hbd, hard):
+    """two padded frames: the second is the first shifted by (1,-2) + noise, with one displaced patch; hard=True adds enough
+    noise that the skip test fails almost everywhere and the candidate/cross search runs"""
+    a = Frame(w, h, bd, hbd)
+    a.randomize(rng)
+    b = Frame(w, h, bd, hbd)
+    amp = 14 if hard else 3
+    for p in range(3):
+        sh = (1, -2) if p == 0 else (0, -1)
+        b.plane(p)[...] = np.clip(np.roll(a.plane(p).astype(int), sh, axis=(0, 1)) + rng.integers(-amp, amp + 1, a.plane(p).shape), 0, (1 << bd) - 1)
+    b.y[h // 4:h // 4 + 40, w // 3:w // 3 + 56] = np.clip(a.y[h // 4 + 6:h // 4 + 46, w // 3 - 9:w // 3 + 47].astype(int) + 20, 0, (1 << bd) - 1)
+    return a, b
+
+
+def ti_levels(w, h):
+    import math
+    return min(4, int(math.log10(min(w, h)) / math.log10(2.0) - 4.0))  # common/temporal_interp.c:914
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_interpolate_frames(hbd, bd):
+    rng = np.random.default_rng(15)
+    s = sfx(hbd)
+    for (w, h) in [(128, 72), (192, 136), (320, 192)]:
+        for hard in (False, True):
+            for ratio, pos in [(2, 1), (4, 1), (4, 3), (8, 5)]:
+                a, b = _ti_pair(rng, w, h, bd, hbd, hard)
+                getattr(R, "pad_yuv_frame_" + s)(C.byref(a.s)); getattr(R, "pad_yuv_frame_" + s)(C.byref(b.s))
+                o1 = Frame(w, h, bd, hbd); o2 = Frame(w, h, bd, hbd)
+                getattr(R, "interpolate_frames_" + s)(C.byref(o1.s), C.byref(a.s), C.byref(b.s), ratio, pos)
+                getattr(O, "orc_interpolate_frames_" + s)(P(o2.Y, o2.origin(0)), P(o2.U, o2.origin(1)), P(o2.V, o2.origin(1)), o2.sy, o2.sc,
+                                                         P(a.Y, a.origin(0)), P(a.U, a.origin(1)), P(a.V, a.origin(1)), P(b.Y, b.origin(0)), P(b.U, b.origin(1)),
+                                                         P(b.V, b.origin(1)), a.sy, a.sc, w, h, 160, ratio, pos, ti_levels(w, h))
+                for p in range(3):
+                    assert (o1.plane(p) == o2.plane(p)).all(), (w, h, hard, ratio, pos, p)
+                assert (o1.y != a.y).any()
