@@ -197,6 +197,11 @@ int tb_pad_frame(tb_frame_t *f);                                         /* comm
 int tb_create_reference_frame(tb_frame_t *ref, const tb_frame_t *rec);   /* common_frame.c:745 */
 int tb_scale_down2x2(const tb_frame_t *in, tb_frame_t *out);             /* temporal_interp.c:143 (luma + pad) */
 
+/* ---- a21: temporal frame interpolation, interpolate_frames() common/temporal_interp.c:909 (encoder enc/mainenc.c:353,409 and decoder
+ * dec/decode_frame.c:110): writes the visible area of `out` (>= 16 samples of border required); the caller pads it (tb_pad_frame)
+ * as the reference does.  ref0/ref1 must carry their replicated borders. */
+int tb_interpolate_frames(tb_frame_t *out, const tb_frame_t *ref0, const tb_frame_t *ref1, int ratio, int pos);
+
 /* ---- single-block, HOST-buffer forms of host-object functions on the path (staged per call like the drop-in symbols) */
 int tb_quantize(const int16_t *coeff, int16_t *coeffq, int qp, int size, int coeff_block_type); /* quantize(), enc/encode_block.c:84; returns cbp */
 void tb_dequantize(const int16_t *coeffq, int16_t *rcoeff, int qp, int size);                   /* dequantize(), common/common_block.c:45 */

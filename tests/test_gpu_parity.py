@@ -603,3 +603,52 @@ def test_me_1080p_properties(tb):
     tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, cands.ptr, esz, bd, 0, 1, w, h, d_out.ptr))
     r2 = d_out.download(tb.ME_RESULT, n)
     assert (r2 == r1[perm]).all()
+
+
+def _ti_case(tb, rng, w, h, bd, hbd, hard, ratio, pos):
+    import math
+    s = sfx(hbd)
+    esz = 2 if hbd else 1
+    a = HFrame(w, h, bd, hbd); a.randomize(rng)
+    b = HFrame(w, h, bd, hbd)
+    amp = 14 if hard else 3
+    for p in range(3):
+        sh = (1, -2) if p == 0 else (0, -1)
+        b.plane(p)[...] = np.clip(np.roll(a.plane(p).astype(int), sh, axis=(0, 1)) + rng.integers(-amp, amp + 1, a.plane(p).shape), 0, (1 << bd) - 1)
+    b.y[h // 4:h // 4 + 40, w // 3:w // 3 + 56] = np.clip(a.y[h // 4 + 6:h // 4 + 46, w // 3 - 9:w // 3 + 47].astype(int) + 20, 0, (1 << bd) - 1)
+    dev = []
+    for f in (a, b):
+        t = tb.Frame(w, h, esz); t.upload(f.y, f.u, f.v)
+        r = tb.Frame(w, h, esz)
+        tb.check(tb.lib.tb_create_reference_frame(r.h, t.h))
+        dev.append(r)
+        for p, (pw, ph, pad) in enumerate(((w, h, 160), (w // 2, h // 2, 80), (w // 2, h // 2, 80))):
+            getattr(O, "orc_pad_plane_" + s)(P(f.full(p), f.origin(p)), f.stride(p), pw, ph, pad, pad)
+    out = tb.Frame(w, h, esz)
+    tb.check(tb.lib.tb_interpolate_frames(out.h, dev[0].h, dev[1].h, ratio, pos))
+    got = out.download()
+    o2 = HFrame(w, h, bd, hbd)
+    levels = min(4, int(math.log10(min(w, h)) / math.log10(2.0) - 4.0))
+    getattr(O, "orc_interpolate_frames_" + s)(P(o2.Y, o2.origin(0)), P(o2.U, o2.origin(1)), P(o2.V, o2.origin(1)), o2.sy, o2.sc, P(a.Y, a.origin(0)), P(a.U, a.origin(1)),
+                                             P(a.V, a.origin(1)), P(b.Y, b.origin(0)), P(b.U, b.origin(1)), P(b.V, b.origin(1)), a.sy, a.sc, w, h, 160, ratio, pos, levels)
+    return got, [o2.plane(p).copy() for p in range(3)], a
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_interpolate_frames(tb, hbd, bd):
+    rng = np.random.default_rng(115)
+    for (w, h) in [(128, 72), (192, 136), (320, 192)]:
+        for hard in (False, True):
+            for ratio, pos in [(2, 1), (4, 3), (8, 5)]:
+                got, want, a = _ti_case(tb, rng, w, h, bd, hbd, hard, ratio, pos)
+                for p in range(3):
+                    assert (got[p] == want[p]).all(), (w, h, hard, ratio, pos, p, int((got[p] != want[p]).sum()))
+                assert (got[0] != a.y).any()
+
+
+def test_interpolate_frames_1080p(tb):
+    rng = np.random.default_rng(116)
+    for hard in (False, True):
+        got, want, _ = _ti_case(tb, rng, 1920, 1080, 8, 0, hard, 2, 1)
+        for p in range(3):
+            assert (got[p] == want[p]).all(), (hard, p, int((got[p] != want[p]).sum()))

@@ -88,6 +88,7 @@ lib.tb_cdef_frame.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]
 lib.tb_pad_frame.argtypes = [_vp]
 lib.tb_create_reference_frame.argtypes = [_vp, _vp]
 lib.tb_scale_down2x2.argtypes = [_vp, _vp]
+lib.tb_interpolate_frames.argtypes = [_vp, _vp, _vp, _i, _i]
 lib.tb_quantize.argtypes = [_vp, _vp, _i, _i, _i]
 lib.tb_dequantize.argtypes = [_vp, _vp, _i, _i]
 lib.tb_improve_uv_prediction.argtypes = [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <cstring>
 #include "tb_kernels.cuh"
+#include "tb_tinterp.cuh"
+#include <cmath>
 
 using namespace tb;
 
@@ -447,6 +449,98 @@ int tb_scale_down2x2(const tb_frame_t *in, tb_frame_t *out) {
   else
     LAUNCH(scale_down_kernel<uint16_t>, grd, blk, 0, (const uint16_t *)in->origin[0], in->stride[0], (uint16_t *)out->origin[0], out->stride[0], out->width,
            out->height);
+  API_END();
+}
+
+}  // extern "C"
+
+// ---- a21: temporal interpolation (common/temporal_interp.c:909-992) on resident frames
+struct TiWork {
+  int w = 0, h = 0, esz = 0, levels = 0;
+  tb_frame *pyr[4][2] = {{nullptr}};
+  short2 *mv0[4] = {nullptr}, *mv1[4] = {nullptr}, *sp0[4] = {nullptr}, *sp1[4] = {nullptr}, *m0[4] = {nullptr}, *m1[4] = {nullptr};
+  int *progress = nullptr;
+  int bw[4], bh[4];
+};
+static TiWork g_ti;
+
+template <class S> static void ti_run(tb_frame *out, const tb_frame *r0, const tb_frame *r1, int ratio, int pos) {
+  TiWork &W = g_ti;
+  const int w = r0->width, h = r0->height, levels = W.levels;
+  const int reversed = pos > ratio / 2, wt0 = reversed ? pos : ratio - pos, wt1 = ratio - wt0;
+  const tb_frame *lv[4][2];
+  lv[0][0] = r0; lv[0][1] = r1;
+  for (int l = 1; l < levels; l++)
+    for (int t = 0; t < 2; t++) {
+      tb_frame *d = W.pyr[l][t];
+      const tb_frame *s = lv[l - 1][t];
+      dim3 blk(32, 8), grd((d->width + 31) / 32, (d->height + 7) / 8);
+      LAUNCH(scale_down_kernel<S>, grd, blk, 0, (const S *)s->origin[0], s->stride[0], (S *)d->origin[0], d->stride[0], d->width, d->height);
+      dim3 grd2((d->width + 2 * d->padh[0] + 31) / 32, (d->height + 2 * d->padv[0] + 7) / 8);
+      LAUNCH(pad_copy_kernel<S>, grd2, blk, 0, (S *)d->origin[0], d->stride[0], (const S *)d->origin[0], d->stride[0], d->width, d->height, d->padh[0], d->padv[0], 1);
+      lv[l][t] = d;
+    }
+  for (int l = levels - 1; l >= 0; l--) {
+    TiLevel L;
+    for (int t = 0; t < 2; t++) {
+      const tb_frame *f = lv[l][reversed ? 1 - t : t];
+      L.pic[t].y = f->origin[0]; L.pic[t].stride = f->stride[0]; L.pic[t].width = f->width; L.pic[t].height = f->height; L.pic[t].pad = f->padh[0];
+    }
+    L.mv0 = W.mv0[l]; L.mv1 = W.mv1[l]; L.bw = W.bw[l]; L.bh = W.bh[l]; L.wt0 = wt0; L.wt1 = wt1; L.reversed = reversed;
+    L.guide = l != levels - 1 ? W.sp1[l] : nullptr; L.guide_reversed = reversed; L.guide_wt0 = wt0; L.progress = W.progress;
+    const int nrows = L.bh / 2, n = L.bw * L.bh;
+    ck(cudaMemsetAsync(W.progress, 0, sizeof(int) * (size_t)nrows, g.stream), "memset");
+    if (!L.guide) {
+      ck(cudaMemsetAsync(L.mv0, 0, sizeof(short2) * (size_t)n, g.stream), "memset");
+      ck(cudaMemsetAsync(L.mv1, 0, sizeof(short2) * (size_t)n, g.stream), "memset");
+    }
+    LAUNCH(ti_me_kernel<S>, (nrows + 3) / 4, 128, 0, L);
+    LAUNCH(ti_merge_kernel<S>, grid_for_warps(n), CTA_THREADS, 0, L, W.m0[l], W.m1[l]);
+    if (l > 0)
+      LAUNCH(ti_upscale_kernel, (W.bw[l - 1] * W.bh[l - 1] + 127) / 128, 128, 0, W.m1[l], W.bw[l], W.sp0[l - 1], W.sp1[l - 1], W.bw[l - 1], W.bh[l - 1], wt0, wt1);
+  }
+  const tb_frame *p0 = reversed ? r1 : r0, *p1 = reversed ? r0 : r1;
+  for (int p = 0; p < 3; p++) {
+    const int c = p ? 1 : 0, bs = c ? 4 : 8;
+    dim3 blk(32, 8), grd((W.bw[0] * bs + 31) / 32, (W.bh[0] * bs + 7) / 8);
+    LAUNCH(ti_interp_kernel<S>, grd, blk, 0, (const S *)p0->origin[p], p0->stride[p], (const S *)p1->origin[p], p1->stride[p], (S *)out->origin[p], out->stride[p], W.m0[0],
+           W.m1[0], W.bw[0], W.bh[0], (w + 4) >> c, (h + 4) >> c, 4 >> c, c, wt0, wt1);
+  }
+}
+
+extern "C" {
+
+int tb_interpolate_frames(tb_frame_t *out, const tb_frame_t *ref0, const tb_frame_t *ref1, int ratio, int pos) {
+  API_BEGIN();
+  if (!same_geometry(ref0, ref1) || out->width != ref0->width || out->height != ref0->height || out->esz != ref0->esz || out->pad < 16) return TB_ERR_ARG;
+  TiWork &W = g_ti;
+  const int w = ref0->width, h = ref0->height;
+  if (W.w != w || W.h != h || W.esz != ref0->esz) {  // (re)build the cached pyramid + vector fields for this geometry
+    for (int l = 0; l < 4; l++) {
+      for (int t = 0; t < 2; t++) if (W.pyr[l][t]) { tb_frame_destroy(W.pyr[l][t]); W.pyr[l][t] = nullptr; }
+      short2 **arrs[6] = {&W.mv0[l], &W.mv1[l], &W.sp0[l], &W.sp1[l], &W.m0[l], &W.m1[l]};
+      for (auto a : arrs) if (*a) { cudaFree(*a); *a = nullptr; }
+    }
+    if (W.progress) { cudaFree(W.progress); W.progress = nullptr; }
+    // the reference derives the level count in double precision (common/temporal_interp.c:914)
+    int levels = (int)(std::log10((double)(w < h ? w : h)) / std::log10(2.0) - 4.0);
+    W.levels = levels < 4 ? levels : 4;
+    if (W.levels < 1) return TB_ERR_ARG;
+    for (int l = 0; l < W.levels; l++) {
+      const int wl = w >> l, hl = h >> l;
+      W.bw[l] = 2 * ((wl + 15) / 16); W.bh[l] = 2 * ((hl + 15) / 16);
+      const size_t n = (size_t)W.bw[l] * W.bh[l] * sizeof(short2);
+      short2 **arrs[6] = {&W.mv0[l], &W.mv1[l], &W.sp0[l], &W.sp1[l], &W.m0[l], &W.m1[l]};
+      for (auto a : arrs) { if (cudaMalloc((void **)a, n) != cudaSuccess) return TB_ERR_CUDA; cudaMemsetAsync(*a, 0, n, g.stream); }
+      if (l > 0)
+        for (int t = 0; t < 2; t++)
+          if (!(W.pyr[l][t] = tb_frame_create(wl & ~1 ? wl : 2, hl & ~1 ? hl : 2, 32, ref0->esz))) return TB_ERR_CUDA;
+    }
+    if (cudaMalloc((void **)&W.progress, sizeof(int) * (size_t)(W.bh[0] / 2 + 1)) != cudaSuccess) return TB_ERR_CUDA;
+    W.w = w; W.h = h; W.esz = ref0->esz;
+  }
+  if (ref0->esz == 1) ti_run<uint8_t>(out, ref0, ref1, ratio, pos);
+  else ti_run<uint16_t>(out, ref0, ref1, ratio, pos);
   API_END();
 }
 
