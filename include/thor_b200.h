@@ -135,6 +135,30 @@ typedef struct { int16_t mvx, mvy; uint32_t cost; } tb_me_result_t;
 int tb_motion_estimate_batch(const tb_me_item_t *items_dev, int n, const int16_t *cand_dev, int sample_bytes, int bitdepth,
                              int encoder_speed, int enable_bipred, int fwidth, int fheight, tb_me_result_t *out_dev);
 
+/* ---- a5: simultaneous bi-directional search (mv0 = -mv1) of motion_estimate_bi(), enc/encode_block.c:798-914 (B frames, speed 0).
+ * cand: up to four list entries used AS quarter-pel vectors (sic), like frame_info->mvcand at that call site. */
+typedef struct {
+  const void *orig, *ref0, *ref1; /* device ptrs at the coding block's position */
+  int32_t ostride, rstride;
+  int16_t xpos, ypos;
+  uint8_t size, sign, pad0, pad1;
+  int16_t mvc_x, mvc_y, mvp_x, mvp_y;
+  int32_t cand_ofs, ncand;
+  double lambda;
+} tb_me_bi_item_t;
+int tb_motion_estimate_bi_batch(const tb_me_bi_item_t *items_dev, int n, const int16_t *cand_dev, int sample_bytes, int bitdepth, int enable_bipred,
+                                int fwidth, int fheight, tb_me_result_t *out_dev);
+
+/* ---- a9 / a5 element-wise block combinations: op 0 average_blocks_all (a+b)>>1 (common/inter_prediction.c:228), op 1 the bipred search
+ * target sat(2a - b) (enc/encode_block.c:1780), op 2 block_avg (a+b+1)>>1 (common/common_kernels.c:38) */
+typedef struct {
+  const void *a, *b;
+  void *dst;
+  int32_t astride, bstride, dstride;
+  uint16_t width, height;
+} tb_combine_item_t;
+int tb_block_combine_batch(const tb_combine_item_t *items_dev, int n, int sample_bytes, int op, int bitdepth);
+
 /* optional work counters for the roofline: 5 uint64 in HBM {searches, integer-position block SADs, sub-pel probes,
  * samples compared at integer positions (incl. one read of the original block), samples read+written by the sub-pel probes};
  * NULL (default) disables counting */

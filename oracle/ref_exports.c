@@ -32,4 +32,15 @@ int X(motion_estimate)(SAMPLE *orig, SAMPLE *ref, int size, int stride_r, int wi
   int n = mvcand_num;
   return motion_estimate(orig, ref, size, stride_r, width, height, mv, mvc, mvp, lambda, &p, sign, fwidth, fheight, xpos, ypos, mvcand, &n, enable_bipred);
 }
+int X(motion_estimate_bi)(SAMPLE *orig, SAMPLE *ref0, SAMPLE *ref1, int size, int stride_r, int width, int height, mv_t *mv, mv_t *mvc, mv_t *mvp, double lambda,
+                          int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, mv_t *mvcand, int mvcand_num, int enable_bipred) {
+  enc_params p;
+  memset(&p, 0, sizeof(p));
+  p.bitdepth = bitdepth;
+  mv_t list[8];  /* the reference scribbles on entries 0..5 of the list */
+  memset(list, 0, sizeof(list));
+  for (int i = 0; i < mvcand_num && i < 8; i++) list[i] = mvcand[i];
+  int n = mvcand_num;
+  return motion_estimate_bi(orig, ref0, ref1, size, stride_r, width, height, mv, mvc, mvp, lambda, &p, sign, fwidth, fheight, xpos, ypos, list, &n, enable_bipred);
+}
 void X(set_use_simd)(int v) { use_simd = v; }

@@ -83,6 +83,8 @@ void orc_cdef_plane_##SFX(const S *src, S *dst, int stride, int width, int heigh
 void orc_pad_plane_##SFX(S *p, int stride, int w, int h, int pad_hor, int pad_ver); \
 void orc_scale_down2x2_##SFX(const S *in, int si, S *out, int so, int wo, int ho); \
 void orc_interpolate_frames_##SFX(S *outY, S *outU, S *outV, int so_y, int so_c, const S *r0Y, const S *r0U, const S *r0V, const S *r1Y, const S *r1U, const S *r1V, int sy, int sc, int width, int height, int pad, int ratio, int pos, int max_levels); \
+int  orc_motion_estimate_bi_##SFX(const S *orig, const S *ref0, const S *ref1, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred); \
+void orc_block_combine_##SFX(S *dst, int ds, const S *a, int as, const S *b, int bs, int w, int h, int op, int bitdepth); \
 int  orc_motion_estimate_##SFX(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int encoder_speed, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred);
 
 ORC_DECL(uint8_t, lbd)

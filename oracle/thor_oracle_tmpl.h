@@ -1064,3 +1064,70 @@ void FN(orc_interpolate_frames)(S *outY, S *outU, S *outV, int so_y, int so_c, c
     if (l) { free(buf[l][0]); free(buf[l][1]); }
   }
 }
+
+/* ---- a5: simultaneous bi-directional search with mv0 = -mv1.  enc/encode_block.c:798-914.  3x3 telescope at steps
+ * 32..1 quarter-pels (the last step visits only the legal quarter/half positions), then six candidates (four list entries
+ * used AS quarter-pel vectors, the predictor, zero).  Each probe averages the two true interpolations, (a+b)>>1.
+ * Note the second clip_mv runs on the already clipped vector and its result is the one kept. ---- */
+int FN(orc_motion_estimate_bi)(const S *orig, const S *ref0, const S *ref1, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc,
+                               const orc_mv_t *mvp, double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand,
+                               int mvcand_num, int enable_bipred) {
+  static S rf0[128 * 128], rf1[128 * 128];
+  uint32_t min_sad = 1u << 31, sad;
+  orc_mv_t cand, opt = {0, 0}, mref;
+  mref.y = (int16_t)(((mvc->y + 2) >> 2) << 2);
+  mref.x = (int16_t)(((mvc->x + 2) >> 2) << 2);
+  for (int pass = 0; pass < 2; pass++) {
+    int nsteps = pass == 0 ? 6 : 1;
+    for (int si = 0; si < nsteps; si++) {
+      int step = pass == 0 ? (32 >> si) : 0;
+      int kmax = pass == 0 ? 3 : 6;  /* 3x3 grid rows, or the six candidates */
+      for (int kk = 0; kk < kmax; kk++)
+        for (int ll = 0; ll < (pass == 0 ? 3 : 1); ll++) {
+          if (pass == 0) {
+            int k = (kk - 1) * step, l = (ll - 1) * step;
+            if (step < 32 && k == 0 && l == 0) continue;
+            if (step == 1) {
+              int vf = mref.y & 3, hf = mref.x & 3, skip;
+              if (vf == 0 && hf == 0) skip = abs(k) != abs(l);
+              else if (vf == 2 && hf == 2) skip = 1;
+              else skip = abs(k) == abs(l);
+              if (skip) continue;
+            }
+            cand.y = (int16_t)(mref.y + k);
+            cand.x = (int16_t)(mref.x + l);
+          } else {
+            orc_mv_t z = {0, 0};
+            cand = kk < 4 ? (kk < mvcand_num ? mvcand[kk] : z) : (kk == 4 ? *mvp : z);
+          }
+          orc_clip_mv(&cand, ypos, xpos, fwidth, fheight, size, size, sign);
+          FN(orc_get_inter_prediction_luma)(rf0, ref0, width, height, stride_r, width, &cand, sign, enable_bipred, fwidth, fheight, xpos, ypos, bitdepth);
+          orc_clip_mv(&cand, ypos, xpos, fwidth, fheight, size, size, 1 - sign);
+          FN(orc_get_inter_prediction_luma)(rf1, ref1, width, height, stride_r, width, &cand, 1 - sign, enable_bipred, fwidth, fheight, xpos, ypos, bitdepth);
+          sad = 0;
+          for (int i = 0; i < height; i++)
+            for (int j = 0; j < width; j++) sad += (unsigned)abs((int)orig[i * size + j] - (((int)rf0[i * size + j] + (int)rf1[i * size + j]) >> 1));
+          sad >>= bitdepth - 8;
+          sad += (unsigned)(lambda * (double)orc_quote_mv_bits((int16_t)(cand.y - mvp->y), (int16_t)(cand.x - mvp->x)) + 0.5);
+          if (sad < min_sad) { min_sad = sad; opt = cand; }
+        }
+      if (pass == 0) mref = opt;
+    }
+  }
+  *mv = opt;
+  return (int)min_sad;
+}
+
+/* ---- a9/a5 element-wise block combinations: op 0 average_blocks_all (a+b)>>1 (common/inter_prediction.c:228-247),
+ * op 1 bipred search target sat(2a - b) (enc/encode_block.c:1780-1782), op 2 block_avg (a+b+1)>>1 ---- */
+void FN(orc_block_combine)(S *dst, int ds, const S *a, int as, const S *b, int bs, int w, int h, int op, int bitdepth) {
+  int maxv = (1 << bitdepth) - 1;
+  for (int i = 0; i < h; i++)
+    for (int j = 0; j < w; j++) {
+      int x = a[i * as + j], y = b[i * bs + j], v;
+      if (op == 0) v = (x + y) >> 1;
+      else if (op == 1) v = orc_sat(2 * (int16_t)x - (int16_t)y, maxv);
+      else v = (x + y + 1) >> 1;
+      dst[i * ds + j] = (S)v;
+    }
+}

@@ -82,12 +82,12 @@ def test_struct_layouts_match_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "thor_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",sizeof(tb_sad_item_t),'
                    'sizeof(tb_me_item_t),sizeof(tb_me_result_t),sizeof(tb_interp_item_t),sizeof(tb_txfm_item_t),sizeof(tb_txfm_result_t),'
-                   'sizeof(tb_intra_item_t),sizeof(tb_blkinfo_t));return 0;}\n')
+                   'sizeof(tb_intra_item_t),sizeof(tb_blkinfo_t));printf("%zu %zu\\n",sizeof(tb_me_bi_item_t),sizeof(tb_combine_item_t));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [t.SAD_ITEM.itemsize, t.ME_ITEM.itemsize, t.ME_RESULT.itemsize, t.INTERP_ITEM.itemsize, t.TXFM_ITEM.itemsize,
-                     t.TXFM_RESULT.itemsize, t.INTRA_ITEM.itemsize, t.BLKINFO.itemsize]
+                     t.TXFM_RESULT.itemsize, t.INTRA_ITEM.itemsize, t.BLKINFO.itemsize, t.ME_BI_ITEM.itemsize, t.COMBINE_ITEM.itemsize]
 
 
 def test_no_cpu_fallback():

@@ -652,3 +652,56 @@ def test_interpolate_frames_1080p(tb):
         got, want, _ = _ti_case(tb, rng, 1920, 1080, 8, 0, hard, 2, 1)
         for p in range(3):
             assert (got[p] == want[p]).all(), (hard, p, int((got[p] != want[p]).sum()))
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_batch_motion_estimate_bi_and_combine(tb, hbd, bd):
+    rng = np.random.default_rng(117)
+    s = sfx(hbd)
+    esz = 2 if hbd else 1
+    w, h = 192, 128
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    href2, _, dref2, _, _ = make_frames(tb, rng, w, h, bd, hbd, shift=(-1, 2))
+    r0, rst = dref.plane(0); r1, _ = dref2.plane(0); optr, ost = dcur.plane(0)
+    n = 60
+    items = np.zeros(n, tb.ME_BI_ITEM)
+    cands = rng.integers(-20, 20, (n, 4, 2)).astype(np.int16)
+    meta = []
+    for i in range(n):
+        size = int(rng.choice([8, 16, 32, 64]))
+        xpos = int(rng.integers(0, w // size)) * size; ypos = int(rng.integers(0, h // size)) * size
+        sign = int(rng.integers(0, 2)); nc = int(rng.integers(0, 5)); lam = float(rng.uniform(2.0, 40.0))
+        mvc = rng.integers(-30, 30, 2); mvp = rng.integers(-30, 30, 2)
+        items[i] = (optr + (ypos * ost + xpos) * esz, r0 + (ypos * rst + xpos) * esz, r1 + (ypos * rst + xpos) * esz, ost, rst, xpos, ypos, size, sign, 0, 0,
+                    mvc[0], mvc[1], mvp[0], mvp[1], 4 * i, nc, lam)
+        meta.append((size, xpos, ypos, sign, nc, lam, mvc, mvp))
+    d_items = tb.DevBuf.from_array(items); d_c = tb.DevBuf.from_array(cands); d_out = tb.DevBuf(8 * n)
+    tb.check(tb.lib.tb_motion_estimate_bi_batch(d_items.ptr, n, d_c.ptr, esz, bd, 1, w, h, d_out.ptr))
+    got = d_out.download(tb.ME_RESULT, n)
+    for i, (size, xpos, ypos, sign, nc, lam, mvc, mvp) in enumerate(meta):
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur.y[ypos:ypos + size, xpos:xpos + size]
+        m0 = (C.c_int16 * 2)(0, 0)
+        cc = (C.c_int16 * 8)(*[int(v) for v in cands[i].reshape(-1)])
+        cost = getattr(O, "orc_motion_estimate_bi_" + s)(P(org), P(href.Y, href.origin(0) + ypos * href.sy + xpos), P(href2.Y, href2.origin(0) + ypos * href2.sy + xpos), size,
+                                                          href.sy, size, size, m0, (C.c_int16 * 2)(int(mvc[0]), int(mvc[1])), (C.c_int16 * 2)(int(mvp[0]), int(mvp[1])),
+                                                          C.c_double(lam), bd, sign, w, h, xpos, ypos, cc, nc, 1)
+        assert (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])) == (cost, m0[0], m0[1]), (i, size, sign, nc)
+    # element-wise combinations on resident frames
+    m = 90
+    citems = np.zeros(m, tb.COMBINE_ITEM)
+    out = tb.DevBuf(m * 64 * 64 * esz)
+    cm = []
+    for i in range(m):
+        bw, bh = int(rng.choice([4, 8, 16, 32, 64])), int(rng.choice([4, 8, 16, 32, 64]))
+        x, y = int(rng.integers(0, w - bw)), int(rng.integers(0, h - bh))
+        citems[i] = (optr + (y * ost + x) * esz, r0 + (y * rst + x) * esz, out.ptr + i * 64 * 64 * esz, ost, rst, bw, bw, bh)
+        cm.append((bw, bh, x, y))
+    d_ci = tb.DevBuf.from_array(citems)
+    for op in (0, 1, 2):
+        tb.check(tb.lib.tb_block_combine_batch(d_ci.ptr, m, esz, op, bd))
+        res = out.download(sdt(hbd), (m, 64 * 64))
+        for i, (bw, bh, x, y) in enumerate(cm):
+            want = aligned((bh, bw), sdt(hbd))
+            getattr(O, "orc_block_combine_" + s)(P(want), bw, P(cur.Y, cur.origin(0) + y * cur.sy + x), cur.sy, P(href.Y, href.origin(0) + y * href.sy + x), href.sy, bw, bh, op, bd)
+            assert (res[i, :bw * bh].reshape(bh, bw) == want).all(), (op, i)

@@ -537,3 +537,50 @@ def test_interpolate_frames(hbd, bd):
                 for p in range(3):
                     assert (o1.plane(p) == o2.plane(p)).all(), (w, h, hard, ratio, pos, p)
                 assert (o1.y != a.y).any()
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_motion_estimate_bi_and_combine(hbd, bd):
+    rng = np.random.default_rng(16)
+    s = sfx(hbd)
+    E = ref_enc(hbd)
+    fw, fh = 192, 128
+    f0 = Frame(fw, fh, bd, hbd); f0.randomize(rng)
+    f1 = Frame(fw, fh, bd, hbd)
+    f1.y[...] = np.clip(np.roll(f0.y.astype(int), (2, 3), axis=(0, 1)) + rng.integers(-4, 5, f0.y.shape), 0, (1 << bd) - 1)
+    for f in (f0, f1):
+        getattr(R, "pad_yuv_frame_" + s)(C.byref(f.s))
+    cur = np.clip((f0.y.astype(int) + np.roll(f0.y.astype(int), (1, 1), axis=(0, 1))) // 2 + rng.integers(-3, 4, f0.y.shape), 0, (1 << bd) - 1)
+    for trial in range(40):
+        size = int(rng.choice([8, 16, 32, 64]))
+        xpos, ypos = int(rng.integers(0, fw // size)) * size, int(rng.integers(0, fh // size)) * size
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur[ypos:ypos + size, xpos:xpos + size]
+        sign = int(rng.integers(0, 2)); lam = float(rng.uniform(2.0, 40.0))
+        mvc = (C.c_int16 * 2)(int(rng.integers(-30, 30)), int(rng.integers(-30, 30)))
+        mvp = (C.c_int16 * 2)(int(rng.integers(-30, 30)), int(rng.integers(-30, 30)))
+        nc = int(rng.integers(0, 7))
+        cands = (C.c_int16 * 16)(*[int(v) for v in rng.integers(-20, 20, 16)])
+        m0 = (C.c_int16 * 2)(0, 0); m1 = (C.c_int16 * 2)(0, 0)
+        p0 = P(f0.Y, f0.origin(0) + ypos * f0.sy + xpos); p1 = P(f1.Y, f1.origin(0) + ypos * f1.sy + xpos)
+        a = getattr(O, "orc_motion_estimate_bi_" + s)(P(org), p0, p1, size, f0.sy, size, size, m0, mvc, mvp, C.c_double(lam), bd, sign, fw, fh, xpos, ypos, cands, nc, 1)
+        b = getattr(E, "ref_motion_estimate_bi_" + s)(P(org), p0, p1, size, f0.sy, size, size, m1, mvc, mvp, C.c_double(lam), bd, sign, fw, fh, xpos, ypos, cands, nc, 1)
+        assert (a, m0[0], m0[1]) == (b, m1[0], m1[1]), (trial, size, sign, nc)
+    # element-wise combinations: op 0 against average_blocks_all, op 2 against block_avg_simd, op 1 against its definition
+    from _refstructs import Mv
+    class BlockPos(C.Structure):
+        _fields_ = [("ypos", C.c_uint16), ("xpos", C.c_uint16), ("size", C.c_uint8), ("bwidth", C.c_uint8), ("bheight", C.c_uint8), ("sb_size", C.c_uint8)]
+    for size in (8, 16, 64):
+        a = rand_plane(rng, size, size, bd, hbd); b = rand_plane(rng, size, size, bd, hbd)
+        ac = rand_plane(rng, size // 2, size // 2, bd, hbd); bc = rand_plane(rng, size // 2, size // 2, bd, hbd)
+        o0 = aligned((size, size), sdt(hbd), fill=0); o1 = aligned((size, size), sdt(hbd), fill=0)
+        u1 = aligned((size // 2, size // 2), sdt(hbd), fill=0); v1 = aligned((size // 2, size // 2), sdt(hbd), fill=0)
+        bp = BlockPos(0, 0, size, size, size, 128)
+        getattr(R, "average_blocks_all_" + s)(P(o1), P(u1), P(v1), P(a), P(ac), P(ac), P(b), P(bc), P(bc), C.byref(bp), 1)
+        getattr(O, "orc_block_combine_" + s)(P(o0), size, P(a), size, P(b), size, size, size, 0, bd)
+        assert (o0 == o1).all()
+        getattr(O, "orc_block_combine_" + s)(P(o0), size, P(a), size, P(b), size, size, size, 1, bd)
+        assert (o0 == np.clip(2 * a.astype(int) - b.astype(int), 0, (1 << bd) - 1)).all()
+        getattr(O, "orc_block_combine_" + s)(P(o0), size, P(a), size, P(b), size, size, size, 2, bd)
+        getattr(R, "block_avg_simd_" + s)(P(o1), P(a), P(b), size, size, size, size, size)
+        assert (o0 == o1).all()

@@ -41,6 +41,11 @@ SAD_ITEM = np.dtype([("a", "u8"), ("b", "u8"), ("astride", "i4"), ("bstride", "i
 ME_ITEM = np.dtype([("orig", "u8"), ("ref", "u8"), ("ostride", "i4"), ("rstride", "i4"), ("xpos", "i2"), ("ypos", "i2"), ("size", "u1"),
                     ("width", "u1"), ("height", "u1"), ("sign", "u1"), ("mvc_x", "i2"), ("mvc_y", "i2"), ("mvp_x", "i2"), ("mvp_y", "i2"),
                     ("cand_ofs", "i4"), ("ncand", "i4"), ("lambda", "f8")], align=True)
+ME_BI_ITEM = np.dtype([("orig", "u8"), ("ref0", "u8"), ("ref1", "u8"), ("ostride", "i4"), ("rstride", "i4"), ("xpos", "i2"), ("ypos", "i2"), ("size", "u1"),
+                       ("sign", "u1"), ("pad0", "u1"), ("pad1", "u1"), ("mvc_x", "i2"), ("mvc_y", "i2"), ("mvp_x", "i2"), ("mvp_y", "i2"), ("cand_ofs", "i4"),
+                       ("ncand", "i4"), ("lambda", "f8")], align=True)
+COMBINE_ITEM = np.dtype([("a", "u8"), ("b", "u8"), ("dst", "u8"), ("astride", "i4"), ("bstride", "i4"), ("dstride", "i4"), ("width", "u2"), ("height", "u2")],
+                        align=True)
 ME_RESULT = np.dtype([("mvx", "i2"), ("mvy", "i2"), ("cost", "u4")], align=True)
 INTERP_ITEM = np.dtype([("ref", "u8"), ("dst", "u8"), ("rstride", "i4"), ("dstride", "i4"), ("xpos", "i2"), ("ypos", "i2"), ("mvx", "i2"),
                         ("mvy", "i2"), ("width", "u1"), ("height", "u1"), ("sign", "u1"), ("chroma", "u1"), ("pic_w", "i2"), ("pic_h", "i2"),
@@ -78,6 +83,8 @@ lib.tb_frame_plane.argtypes = [_vp, _i, C.POINTER(_i)]
 lib.tb_sad_batch.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 lib.tb_motion_estimate_batch.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]
 lib.tb_me_set_stats.argtypes = [_vp]
+lib.tb_motion_estimate_bi_batch.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
+lib.tb_block_combine_batch.argtypes = [_vp, _i, _i, _i, _i]
 lib.tb_interp_batch.argtypes = [_vp, _i, _i, _i, _i]
 lib.tb_txfm_chain_batch.argtypes = [_vp, _i, _i, _i, _vp]
 lib.tb_intra_batch.argtypes = [_vp, _i, _i, _i]

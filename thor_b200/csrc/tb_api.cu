@@ -352,6 +352,21 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
   else LAUNCH(me_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
   API_END();
 }
+int tb_motion_estimate_bi_batch(const tb_me_bi_item_t *items, int n, const int16_t *cand, int sample_bytes, int bitdepth, int bip, int fw, int fh, tb_me_result_t *out) {
+  API_BEGIN();
+  if (n <= 0) return TB_OK;
+  if (sample_bytes == 1) LAUNCH(me_bi_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, bip, fw, fh, out);
+  else LAUNCH(me_bi_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, bip, fw, fh, out);
+  API_END();
+}
+int tb_block_combine_batch(const tb_combine_item_t *items, int n, int sample_bytes, int op, int bitdepth) {
+  API_BEGIN();
+  if (n <= 0) return TB_OK;
+  if (op < 0 || op > 2) return TB_ERR_ARG;
+  if (sample_bytes == 1) LAUNCH(combine_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, op, bitdepth);
+  else LAUNCH(combine_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, op, bitdepth);
+  API_END();
+}
 int tb_me_set_stats(uint64_t *stats_dev) {
   g.me_stats = (unsigned long long *)stats_dev;
   return TB_OK;

@@ -18,6 +18,12 @@
 #ifndef TB_SUBPEL_RH16
 #define TB_SUBPEL_RH16 0
 #endif
+#ifndef TB_SAD_TILE
+#define TB_SAD_TILE 1  // 1: issue all loads of a row tile before use; 0: one word at a time
+#endif
+#ifndef TB_ME_MINBLOCKS
+#define TB_ME_MINBLOCKS 6  // __launch_bounds__(128, N) of the motion-search kernel: registers/thread <= 65536 / (128 N)
+#endif
 
 namespace tb {
 
@@ -99,6 +105,7 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   const uint32_t *oq = (const uint32_t *)o;
   const int rsw = (rs * (int)sizeof(S)) >> 2, osw = (os * (int)sizeof(S)) >> 2;  // pitches in words
   uint32_t acc = 0;
+#if TB_SAD_TILE
   int row = sub;
   if (ww == 1) {
     for (; row + 3 * nl < h; row += 4 * nl) acc += sad_tile<S, 1, 4>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
@@ -113,6 +120,17 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
     for (; row < h; row += nl)
       for (int c = 0; c < ww; c += 8) acc += sad_tile<S, 8, 1>(rq + row * rsw + c, 0, oq + row * osw + c, 0, sh);
   }
+#else
+  for (int row = sub; row < h; row += nl) {
+    const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
+    uint32_t prev = __ldg(q);
+    for (int c = 0; c < ww; c++) {
+      uint32_t nxt = __ldg(q + c + 1);
+      acc += word_sad<S>(__ldg(a + c), __funnelshift_r(prev, nxt, sh));
+      prev = nxt;
+    }
+  }
+#endif
   return acc;
 }
 // whole warp on one block
@@ -730,6 +748,83 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
   out_mvx = (int)(int16_t)(optx + xdq);
   out_mvy = (int)(int16_t)(opty + ydq);
   out_cost = cmin < min_sad ? cmin : min_sad;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a5: motion_estimate_bi, simultaneous bi-directional search with mv0 = -mv1.  enc/encode_block.c:798-914.
+// Each probe is SAD(orig, (P0 + P1) >> 1) with both predictions truly interpolated; up to eight probes of a step run
+// concurrently on 4-lane groups, the winner is then taken in the reference's visiting order.
+// ---------------------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __noinline__ uint32_t bi_probe_sad(const S *o, int os, const S *ref0, const S *ref1, int rs, int size, int mvx0, int mvy0, int mvx1, int mvy1, int sign, int bip,
+                                              int fw, int fh, int xpos, int ypos, int bitdepth) {
+  int hi0, vi0, xf0, yf0, hi1, vi1, xf1, yf1;
+  split_mv(mvx0, mvy0, sign, 2, fw, fh, xpos, ypos, size, size, hi0, vi0, xf0, yf0);
+  split_mv(mvx1, mvy1, 1 - sign, 2, fw, fh, xpos, ypos, size, size, hi1, vi1, xf1, yf1);
+  const S *ip0 = ref0 + vi0 * rs + hi0, *ip1 = ref1 + vi1 * rs + hi1;
+  const int maxv = (1 << bitdepth) - 1, ls = ilog2(size), sub = lane_id() & 3;
+  uint32_t acc = 0;
+  for (int p = sub; p < size * size; p += 4) {
+    int row = p >> ls, col = p & (size - 1);
+    const S *q0 = ip0 + row * rs + col, *q1 = ip1 + row * rs + col;
+    int v0 = (xf0 == 0 && yf0 == 0) ? (int)q0[0] : luma_sample<S>(q0, rs, xf0, yf0, bip, maxv);
+    int v1 = (xf1 == 0 && yf1 == 0) ? (int)q1[0] : luma_sample<S>(q1, rs, xf1, yf1, bip, maxv);
+    acc += (uint32_t)iabs((int)o[row * os + col] - ((v0 + v1) >> 1));
+  }
+  return group_sum(acc, 4);
+}
+
+template <class S>
+__device__ void warp_motion_estimate_bi(const S *orig, int os, const S *ref0, const S *ref1, int rs, int size, int sign, int xpos, int ypos, int fw, int fh, int bitdepth, int bip,
+                                        double lambda, int mvcx, int mvcy, int mvpx, int mvpy, const int16_t *cand, int ncand, int &out_mvx, int &out_mvy,
+                                        uint32_t &out_cost) {
+  const int lane = lane_id(), shift = bitdepth - 8, grp = lane >> 2;
+  uint32_t min_sad = 1u << 31;
+  int optx = 0, opty = 0;
+  int refx = (int)(int16_t)(((mvcx + 2) >> 2) << 2), refy = (int)(int16_t)(((mvcy + 2) >> 2) << 2);
+  // six telescope steps (3x3 grids) followed by one pass over the six candidates
+  for (int stage = 0; stage < 7; stage++) {
+    const int step = stage < 6 ? (32 >> stage) : 0;
+    const int nslots = stage < 6 ? 9 : 6;
+    for (int base = 0; base < nslots; base += 8) {
+      // slot handled by this lane group
+      const int slot = base + grp;
+      bool valid = slot < nslots;
+      int cx = 0, cy = 0;
+      if (valid) {
+        if (stage < 6) {
+          int k = (slot / 3 - 1) * step, l = (slot % 3 - 1) * step;
+          if (step < 32 && k == 0 && l == 0) valid = false;
+          if (step == 1) {
+            int vf = refy & 3, hf = refx & 3;
+            bool ex = (vf == 0 && hf == 0) ? (iabs(k) != iabs(l)) : ((vf == 2 && hf == 2) ? true : (iabs(k) == iabs(l)));
+            if (ex) valid = false;
+          }
+          cy = (int)(int16_t)(refy + k);
+          cx = (int)(int16_t)(refx + l);
+        } else {
+          if (slot < 4) { if (slot < ncand) { cx = cand[2 * slot]; cy = cand[2 * slot + 1]; } }
+          else if (slot == 4) { cx = mvpx; cy = mvpy; }
+        }
+      }
+      int c0x = cx, c0y = cy;
+      clip_mv(c0x, c0y, ypos, xpos, fw, fh, size, size, sign);
+      int c1x = c0x, c1y = c0y;  // the second clip runs on the already clipped vector; its result is the one kept
+      clip_mv(c1x, c1y, ypos, xpos, fw, fh, size, size, 1 - sign);
+      uint32_t sad = bi_probe_sad<S>(orig, os, ref0, ref1, rs, size, c0x, c0y, c1x, c1y, sign, bip, fw, fh, xpos, ypos, bitdepth);
+      uint32_t cost = (sad >> shift) + mv_cost(lambda, quote_mv_bits((int)(int16_t)(c1y - mvpy), (int)(int16_t)(c1x - mvpx)));
+      for (int t = 0; t < 8; t++) {
+        bool v = __shfl_sync(FULL, (int)valid, t * 4) != 0;
+        uint32_t ct = __shfl_sync(FULL, cost, t * 4);
+        int tx = __shfl_sync(FULL, c1x, t * 4), ty = __shfl_sync(FULL, c1y, t * 4);
+        if (v && ct < min_sad) { min_sad = ct; optx = tx; opty = ty; }
+      }
+    }
+    if (stage < 6) { refx = optx; refy = opty; }
+  }
+  out_mvx = optx;
+  out_mvy = opty;
+  out_cost = min_sad;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 
 // ---- a5 --------------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, 4) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
+__global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
                                                                int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   for (int it = global_warp(); it < n; it += total_warps()) {
     tb_me_item_t q = items[it];
@@ -81,6 +81,34 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) me_batch_kernel(const tb_me_it
         atomicAdd(&stats[3], (unsigned long long)(c.n_int + 1) * q.width * q.height);
         atomicAdd(&stats[4], (unsigned long long)c.n_sub * ((q.width + 5) * (q.height + 5) + q.width * q.height));
       }
+    }
+  }
+}
+
+template <class S>
+__global__ void __launch_bounds__(CTA_THREADS) me_bi_batch_kernel(const tb_me_bi_item_t *items, int n, const int16_t *cand, int bitdepth, int bip, int fw, int fh,
+                                                                  tb_me_result_t *out) {
+  for (int it = global_warp(); it < n; it += total_warps()) {
+    tb_me_bi_item_t q = items[it];
+    int mx, my;
+    uint32_t cost;
+    warp_motion_estimate_bi<S>((const S *)q.orig, q.ostride, (const S *)q.ref0, (const S *)q.ref1, q.rstride, q.size, q.sign, q.xpos, q.ypos, fw, fh, bitdepth, bip, q.lambda,
+                               q.mvc_x, q.mvc_y, q.mvp_x, q.mvp_y, cand + 2 * (size_t)q.cand_ofs, q.ncand, mx, my, cost);
+    if (lane_id() == 0) { out[it].mvx = (int16_t)mx; out[it].mvy = (int16_t)my; out[it].cost = cost; }
+  }
+}
+// a9 / a5 element-wise block combinations, one warp per item (op 0: (a+b)>>1, 1: sat(2a-b), 2: (a+b+1)>>1)
+template <class S> __global__ void __launch_bounds__(CTA_THREADS) combine_batch_kernel(const tb_combine_item_t *items, int n, int op, int bitdepth) {
+  const int maxv = (1 << bitdepth) - 1;
+  for (int it = global_warp(); it < n; it += total_warps()) {
+    tb_combine_item_t q = items[it];
+    const S *a = (const S *)q.a, *b = (const S *)q.b;
+    S *d = (S *)q.dst;
+    for (int p = lane_id(); p < q.width * q.height; p += 32) {
+      int row = p / q.width, col = p - row * q.width;
+      int x = a[row * q.astride + col], y = b[row * q.bstride + col];
+      int v = op == 0 ? (x + y) >> 1 : (op == 1 ? sat_px(2 * x - y, maxv) : (x + y + 1) >> 1);
+      d[row * q.dstride + col] = (S)v;
     }
   }
 }
