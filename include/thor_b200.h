@@ -217,6 +217,11 @@ int tb_clpf_detect_frame(const tb_frame_t *rec, const tb_frame_t *org, const tb_
  * dirvar_dev: 2*64 ints per filter block (dir, var), produced by the luma pass and consumed by the chroma passes */
 int tb_cdef_frame(tb_frame_t *rec, tb_frame_t *scratch, const tb_blkinfo_t *blkinfo_dev, const int8_t *fb_pri_dev, const int8_t *fb_sec_dev,
                   int pri_damping, int sec_damping, int32_t *dirvar_dev, int bitdepth, int plane); /* common_frame.c:826 */
+/* a19 (encoder): the pixel work of cdef_search (enc/encode_frame.c:285-376) — per 64x64 filter block fb (raster), plane class c (0 luma,
+ * 1 = U+V) and strength index gi < {64,32,16}[speed]: mse[(c * nfb + fb) * 64 + gi] (dist_8x8 for full luma 8x8 blocks, SSE otherwise),
+ * plus allskip[fb] and the dir/var table (layout of tb_cdef_frame).  The greedy preset selection (:58-192, 378-470) stays on the host. */
+int tb_cdef_search_mse(const tb_frame_t *rec, const tb_frame_t *org, const tb_blkinfo_t *blkinfo_dev, int speed, int pri_damping, int bitdepth, int32_t *dirvar_dev,
+                       uint8_t *allskip_dev, uint64_t *mse_dev);
 int tb_pad_frame(tb_frame_t *f);                                         /* common_frame.c:657 */
 int tb_create_reference_frame(tb_frame_t *ref, const tb_frame_t *rec);   /* common_frame.c:745 */
 int tb_scale_down2x2(const tb_frame_t *in, tb_frame_t *out);             /* temporal_interp.c:143 (luma + pad) */

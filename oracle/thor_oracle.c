@@ -1,6 +1,7 @@
 /* thor_oracle.c — TEST INFRASTRUCTURE ONLY (see thor_oracle.h).  Bit-depth independent half of the plain-C
  * restatement of the Thor hot path, plus the two instantiations of thor_oracle_tmpl.h. */
 #include "thor_oracle.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -286,6 +287,78 @@ void orc_cdef_filter_block(uint8_t *dst8, uint16_t *dst16, int dstride, const ui
       if (dst8) dst8[i * dstride + j] = (uint8_t)y;
       else dst16[i * dstride + j] = (uint16_t)y;
     }
+}
+
+/* ---- a19 (encoder): preset selection of cdef_search.  enc/encode_frame.c:58-192 (greedy joint search, dual = luma + chroma)
+ * and :378-470 (sort, de-duplicate, per-block assignment).  mse0/mse1: [sb_count][64] for the non-all-skip filter blocks.
+ * Outputs: strengths[8], uv_strengths[8] (already mapped through priconv), selected[sb_count]; returns nb_strength_bits. */
+static uint64_t orc_search_one_dual(int *lev0, int *lev1, int nb, const uint64_t *m0, const uint64_t *m1, int sb_count, int total) {
+  static uint64_t tot[64][64];
+  memset(tot, 0, sizeof(tot));
+  for (int i = 0; i < sb_count; i++) {
+    uint64_t best = (uint64_t)1 << 63;
+    for (int g = 0; g < nb; g++) {
+      uint64_t c = m0[i * 64 + lev0[g]] + m1[i * 64 + lev1[g]];
+      if (c < best) best = c;
+    }
+    for (int j = 0; j < total; j++)
+      for (int k = 0; k < total; k++) {
+        uint64_t c = m0[i * 64 + j] + m1[i * 64 + k];
+        tot[j][k] += c < best ? c : best;
+      }
+  }
+  uint64_t bt = (uint64_t)1 << 63;
+  int b0 = 0, b1 = 0;
+  for (int j = 0; j < total; j++)
+    for (int k = 0; k < total; k++)
+      if (tot[j][k] < bt) { bt = tot[j][k]; b0 = j; b1 = k; }
+  lev0[nb] = b0;
+  lev1[nb] = b1;
+  return bt;
+}
+static int orc_u32_cmp(const void *a, const void *b) { return *(const uint32_t *)a < *(const uint32_t *)b ? -1 : *(const uint32_t *)a > *(const uint32_t *)b; }
+int orc_cdef_select(const uint64_t *mse0, const uint64_t *mse1, int sb_count, int speed, int cdef_bits, double lambda, int *strengths, int *uv_strengths, int *selected) {
+  static const int priconv[3][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {0, 1, 2, 3, 5, 7, 10, 13}, {0, 1, 3, 6}};
+  static const int pristrengths[3] = {64, 32, 16};
+  const int total = pristrengths[speed], nb = 1 << cdef_bits;
+  int lev0[16], lev1[16] = {0};
+  uint64_t tot = 0;
+  for (int i = 0; i < nb; i++) tot = orc_search_one_dual(lev0, lev1, i, mse0, mse1, sb_count, total);
+  for (int i = 0; i < 4 * nb; i++) {
+    for (int j = 0; j < nb - 1; j++) { lev0[j] = lev0[j + 1]; lev1[j] = lev1[j + 1]; }
+    tot = orc_search_one_dual(lev0, lev1, nb - 1, mse0, mse1, sb_count, total);
+  }
+  tot += (uint64_t)(sb_count * lambda * cdef_bits);
+  tot += (uint64_t)(nb * lambda * 6);
+  (void)tot;  /* a single bit budget is tried (encode_frame.c:385), so the total only mirrors the reference */
+  for (int j = 0; j < nb; j++) { strengths[j] = lev0[j]; uv_strengths[j] = lev1[j]; }
+  int gi_trans[8];
+  uint32_t list[8];
+  for (int i = 0; i < nb; i++) list[i] = ((uint32_t)strengths[i] << 16) + ((uint32_t)uv_strengths[i] << 8) + (uint32_t)i;
+  qsort(list, (size_t)nb, sizeof(*list), orc_u32_cmp);
+  int j = 0;
+  for (int i = 0; i < nb; i++) {
+    gi_trans[list[i] & 255] = j;
+    if (!i || (list[i] & ~255u) != (list[i - 1] & ~255u)) {
+      strengths[j] = (int)(list[i] >> 16);
+      uv_strengths[j++] = (int)((list[i] >> 8) & 255);
+    }
+  }
+  const int bits = orc_log2i(j), nstr = 1 << bits;
+  for (int i = 0; i < sb_count; i++) {
+    uint64_t best = (uint64_t)1 << 63;
+    int bg = 0;
+    for (int g = 0; g < (1 << bits); g++) {
+      uint64_t c = mse0[i * 64 + strengths[gi_trans[g]]] + mse1[i * 64 + uv_strengths[gi_trans[g]]];
+      if (c < best) { bg = gi_trans[g] < nstr - 1 ? gi_trans[g] : nstr - 1; best = c; }
+    }
+    selected[i] = bg;
+  }
+  for (int q = 0; q < nstr; q++) {
+    strengths[q] = priconv[speed][strengths[q] / 4] * 4 + strengths[q] % 4;
+    uv_strengths[q] = priconv[speed][uv_strengths[q] / 4] * 4 + uv_strengths[q] % 4;
+  }
+  return bits;
 }
 
 #define S uint8_t

@@ -54,6 +54,7 @@ void orc_cdef_filter_block(uint8_t *dst8, uint16_t *dst16, int dstride, const ui
                            int pri_strength, int sec_strength, int dir, int pri_damping, int sec_damping,
                            int bsize, int coeff_shift);
 int  orc_adjust_strength(int strength, int32_t var);
+int  orc_cdef_select(const uint64_t *mse0, const uint64_t *mse1, int sb_count, int speed, int cdef_bits, double lambda, int *strengths, int *uv_strengths, int *selected);
 
 #define ORC_DECL(S, SFX) \
 unsigned orc_sad_##SFX(const S *a, const S *b, int astride, int bstride, int width, int height); \
@@ -83,6 +84,8 @@ void orc_cdef_plane_##SFX(const S *src, S *dst, int stride, int width, int heigh
 void orc_pad_plane_##SFX(S *p, int stride, int w, int h, int pad_hor, int pad_ver); \
 void orc_scale_down2x2_##SFX(const S *in, int si, S *out, int so, int wo, int ho); \
 void orc_interpolate_frames_##SFX(S *outY, S *outU, S *outV, int so_y, int so_c, const S *r0Y, const S *r0U, const S *r0V, const S *r1Y, const S *r1U, const S *r1V, int sy, int sc, int width, int height, int pad, int ratio, int pos, int max_levels); \
+uint64_t orc_dist_8x8_##SFX(const S *dst, int dstride, const S *src, int sstride, int coeff_shift); \
+void orc_cdef_search_mse_##SFX(const S *recY, const S *recU, const S *recV, const S *orgY, const S *orgU, const S *orgV, int sy, int sc, int width, int height, const orc_blkinfo_t *bi, int speed, int pri_damping, int bitdepth, uint64_t *mse, int *dirs, int *vars, uint8_t *allskip_out); \
 int  orc_motion_estimate_bi_##SFX(const S *orig, const S *ref0, const S *ref1, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred); \
 void orc_block_combine_##SFX(S *dst, int ds, const S *a, int as, const S *b, int bs, int w, int h, int op, int bitdepth); \
 int  orc_motion_estimate_##SFX(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int encoder_speed, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred);

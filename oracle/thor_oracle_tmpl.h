@@ -1131,3 +1131,79 @@ void FN(orc_block_combine)(S *dst, int ds, const S *a, int as, const S *b, int b
       dst[i * ds + j] = (S)v;
     }
 }
+
+/* enc/encode_frame.c:194-221: perceptual 8x8 distortion; src = original, dst = filtered.  ISO-C double arithmetic
+ * (no contraction): ((A * .5) * B) / sqrt(C + svar * dvar), floor(.5 + ...). */
+uint64_t FN(orc_dist_8x8)(const S *dst, int dstride, const S *src, int sstride, int coeff_shift) {
+  uint64_t sum_s = 0, sum_d = 0, sum_s2 = 0, sum_d2 = 0, sum_sd = 0;
+  for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+      uint64_t s = src[i * sstride + j], d = dst[i * dstride + j];
+      sum_s += s; sum_d += d; sum_s2 += s * s; sum_d2 += d * d; sum_sd += s * d;
+    }
+  uint64_t svar = sum_s2 - ((sum_s * sum_s + 32) >> 6), dvar = sum_d2 - ((sum_d * sum_d + 32) >> 6);
+  return (uint64_t)floor(.5 + (sum_d2 + sum_s2 - 2 * sum_sd) * .5 * (svar + dvar + (400 << 2 * coeff_shift)) / (sqrt((20000 << 4 * coeff_shift) + svar * (double)dvar)));
+}
+
+/* ---- a19 (encoder): the pixel work of cdef_search.  enc/encode_frame.c:228-376.
+ * For every 64x64 filter block that is not all-skip, every plane and every strength index gi < total (= pristrengths[speed]),
+ * the distortion of the CDEF-filtered blocks against the original: dist_8x8 (double arithmetic, :194-221) for full 8x8 luma
+ * blocks, plain SSE otherwise (U and V accumulate into the same slot).  Reference quirks reproduced: the search filters chroma
+ * in 8x8 blocks taken from the top-left 32x32 of the filter block's block-info/direction grid, and passes sec_strength
+ * unadjusted (0..3) whereas cdef_frame applies 4 for 3.
+ *   mse[(plane != 0) * nfb * 64 + fb * 64 + gi], dirs/vars[fb * 64 + m*8+n], allskip[fb]; fb = raster index of the filter block */
+void FN(orc_cdef_search_mse)(const S *recY, const S *recU, const S *recV, const S *orgY, const S *orgU, const S *orgV, int sy, int sc, int width, int height,
+                             const orc_blkinfo_t *bi, int speed, int pri_damping, int bitdepth, uint64_t *mse, int *dirs, int *vars, uint8_t *allskip_out) {
+  static const int priconv[3][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {0, 1, 2, 3, 5, 7, 10, 13}, {0, 1, 3, 6}};
+  static const int pristrengths[3] = {64, 32, 16};
+  const int total = pristrengths[speed], nh = (width + 63) >> 6, nv = (height + 63) >> 6, nfb = nh * nv, cs = bitdepth - 8;
+  static uint16_t tile[(64 + 4) * 80];
+  S dst[64];
+  for (int k = 0, ci = 0; k < nv; k++)
+    for (int l = 0; l < nh; l++, ci++) {
+      const int xoff = l << 6, yoff = k << 6;
+      int allskip = 1;
+      for (int m = 0; allskip && m < 8; m++)
+        for (int n = 0; allskip && n < 8; n++) {
+          int xp = xoff + n * 8, yp = yoff + m * 8;
+          if (xp < width && yp < height) allskip &= bi[(yp / 4) * (width / 4) + xp / 4].mode == 0;
+        }
+      allskip_out[ci] = (uint8_t)allskip;
+      for (int gi = 0; gi < 64; gi++) mse[ci * 64 + gi] = mse[(size_t)nfb * 64 + ci * 64 + gi] = 0;
+      if (allskip) continue;
+      int h = (height < ((k + 1) << 6) ? height : ((k + 1) << 6)) & 63, w = (width < ((l + 1) << 6) ? width : ((l + 1) << 6)) & 63;
+      h += !h << 6;
+      w += !w << 6;
+      for (int plane = 0; plane < 3; plane++) {
+        const int sub = plane != 0, sstride = plane ? sc : sy;
+        const S *src = plane ? (plane == 1 ? recU : recV) : recY, *org = plane ? (plane == 1 ? orgU : orgV) : orgY;
+        int fsx = (width - xoff < 64 ? width - xoff : 64) >> sub, fsy = (height - yoff < 64 ? height - yoff : 64) >> sub;
+        int fx = xoff >> sub, fy = yoff >> sub;
+        int bt = (fx == 0 ? 1 : 0) | (fy == 0 ? 4 : 0) | (fx == (width >> sub) - fsx ? 2 : 0) | (fy == (height >> sub) - fsy ? 8 : 0);
+        FN(orc_cdef_prepare_input)(fsx, fsy, fx, fy, bt, 2, tile + 2 * 80 + 2, 80, src, sstride);
+        for (int gi = 0; gi < total; gi++) {
+          const int pri = priconv[speed][gi / 4], sec = gi % 4;
+          for (int m = 0; m < ((h + 7) >> (3 + sub)); m++)
+            for (int n = 0; n < ((w + 7) >> (3 + sub)); n++) {
+              int xpos = fx + n * 8, ypos = fy + m * 8;
+              int sizex = (width >> sub) - xpos < 8 ? (width >> sub) - xpos : 8, sizey = (height >> sub) - ypos < 8 ? (height >> sub) - ypos : 8;
+              int index = ((yoff + m * 8) / 4) * (width / 4) + (xoff + n * 8) / 4;
+              if (plane == 0 && gi == 0) dirs[ci * 64 + m * 8 + n] = FN(orc_cdef_find_dir)(src + ypos * sstride + xpos, sstride, &vars[ci * 64 + m * 8 + n], cs);
+              if (bi[index].mode == 0) continue;
+              int adj = plane ? pri : orc_adjust_strength(pri, vars[ci * 64 + m * 8 + n]);
+              int pd = pri_damping - !!plane, sd = pri_damping - !!plane;
+              if (adj && orc_log2i(adj) > pd) pd = orc_log2i(adj);
+              orc_cdef_filter_block(sizeof(S) == 1 ? (uint8_t *)dst : NULL, sizeof(S) == 1 ? NULL : (uint16_t *)dst, sizex, tile + 2 * 80 + 2 + n * 8 + m * 8 * 80, 80,
+                                    adj << cs, sec << cs, pri ? dirs[ci * 64 + m * 8 + n] : 0, pd + cs, sd + cs, sizex, cs);
+              const S *ob = org + ypos * sstride + xpos;
+              uint64_t *acc = &mse[(size_t)(plane != 0) * nfb * 64 + ci * 64 + gi];
+              if (plane || sizex != 8 || sizey != 8) {
+                for (int i = 0; i < sizey; i++)
+                  for (int j = 0; j < sizex; j++) { int d = (int)dst[i * sizex + j] - (int)ob[i * sstride + j]; *acc += (uint64_t)(int64_t)(d * d); }
+              } else
+                *acc += FN(orc_dist_8x8)(dst, sizex, ob, sstride, cs);
+            }
+        }
+      }
+    }
+}

@@ -21,7 +21,7 @@ def oracle():
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
             subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
         lib = C.CDLL(so)
-        for n in ("orc_ssd_lbd", "orc_ssd_hbd"):
+        for n in ("orc_ssd_lbd", "orc_ssd_hbd", "orc_dist_8x8_lbd", "orc_dist_8x8_hbd"):
             getattr(lib, n).restype = C.c_uint64
         for n in ("orc_dct_matrix", "orc_zigzag"):
             getattr(lib, n).restype = C.c_void_p
@@ -91,3 +91,16 @@ def rand_plane(rng, h, w, bitdepth, hbd, smooth=False):
     else:
         a[...] = rng.integers(0, maxv + 1, (h, w)).astype(a.dtype)
     return a
+
+
+def ref_frame(hbd):
+    """oracle/_ref/libthorref_frame_{lbd,hbd}.so: cdef_search + dist_8x8 trampolines (enc/encode_frame.c included in place)"""
+    k = "rf%d" % hbd
+    if k not in _cache:
+        so = os.path.join(ORACLE_DIR, "_ref", "libthorref_frame_%s.so" % ("hbd" if hbd else "lbd"))
+        lib = None
+        if os.path.exists(so) and ref() is not None:
+            lib = C.CDLL(so)
+            getattr(lib, "ref_dist_8x8_" + ("hbd" if hbd else "lbd")).restype = C.c_uint64
+        _cache[k] = lib
+    return _cache[k]

@@ -705,3 +705,30 @@ def test_batch_motion_estimate_bi_and_combine(tb, hbd, bd):
             want = aligned((bh, bw), sdt(hbd))
             getattr(O, "orc_block_combine_" + s)(P(want), bw, P(cur.Y, cur.origin(0) + y * cur.sy + x), cur.sy, P(href.Y, href.origin(0) + y * href.sy + x), href.sy, bw, bh, op, bd)
             assert (res[i, :bw * bh].reshape(bh, bw) == want).all(), (op, i)
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_cdef_search_mse(tb, hbd, bd):
+    """encoder-side CDEF strength search: the device distortion table must equal the oracle's (which is pinned against the reference's
+    cdef_search through the greedy selection, tests/test_oracle_vs_ref.py::test_cdef_search)"""
+    rng = np.random.default_rng(118)
+    s = sfx(hbd)
+    esz = 2 if hbd else 1
+    for (w, h), speed in [((192, 136), 1), ((320, 192), 0), ((200, 136), 2)]:
+        f = HFrame(w, h, bd, hbd, 32, 32); f.randomize(rng)
+        org = f.copy()
+        for p in range(3):
+            org.plane(p)[...] = np.clip(f.plane(p).astype(int) + rng.integers(-7, 8, f.plane(p).shape), 0, (1 << bd) - 1)
+        bi, _ = random_blkinfo(rng, w, h, p_skip=0.25)
+        nfb = ((w + 63) // 64) * ((h + 63) // 64)
+        drec = tb.Frame(w, h, esz, 32); dorg = tb.Frame(w, h, esz, 32)
+        drec.upload(f.y, f.u, f.v); dorg.upload(org.y, org.u, org.v)
+        dbi = tb.DevBuf.from_array(bi); ddv = tb.DevBuf(nfb * 2 * 64 * 4); dsk = tb.DevBuf(max(nfb, 16)); dmse = tb.DevBuf(2 * nfb * 64 * 8)
+        tb.check(tb.lib.tb_cdef_search_mse(drec.h, dorg.h, dbi.ptr, speed, 5, bd, ddv.ptr, dsk.ptr, dmse.ptr))
+        got = dmse.download(np.uint64, (2, nfb, 64)); gsk = dsk.download(np.uint8, (max(nfb, 16),))[:nfb]
+        mse = np.zeros((2, nfb, 64), np.uint64); od = np.zeros((nfb, 64), np.int32); ov = np.zeros((nfb, 64), np.int32); ask = np.zeros(nfb, np.uint8)
+        getattr(O, "orc_cdef_search_mse_" + s)(P(f.Y, f.origin(0)), P(f.U, f.origin(1)), P(f.V, f.origin(1)), P(org.Y, org.origin(0)), P(org.U, org.origin(1)),
+                                                P(org.V, org.origin(1)), f.sy, f.sc, w, h, P(bi), speed, 5, bd, P(mse), P(od), P(ov), P(ask))
+        assert (gsk == ask).all()
+        assert (got == mse).all(), (w, h, speed, int((got != mse).sum()))
+        assert mse.any()

@@ -584,3 +584,48 @@ def test_motion_estimate_bi_and_combine(hbd, bd):
         getattr(O, "orc_block_combine_" + s)(P(o0), size, P(a), size, P(b), size, size, size, 2, bd)
         getattr(R, "block_avg_simd_" + s)(P(o1), P(a), P(b), size, size, size, size, size)
         assert (o0 == o1).all()
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
+def test_cdef_search(hbd, bd):
+    """encoder-side CDEF strength search: oracle distortion table + greedy selection against the reference's cdef_search()"""
+    from _libs import ref_frame
+    F = ref_frame(hbd)
+    rng = np.random.default_rng(17)
+    s = sfx(hbd)
+    # dist_8x8 (double arithmetic)
+    for _ in range(300):
+        a = rand_plane(rng, 8, 24, bd, hbd, smooth=bool(rng.integers(0, 2))); b = aligned((8, 8), sdt(hbd))
+        b[...] = np.clip(a[:, :8].astype(int) + rng.integers(-9, 10, (8, 8)), 0, (1 << bd) - 1)
+        assert getattr(O, "orc_dist_8x8_" + s)(P(b), 8, P(a), 24, bd - 8) == getattr(F, "ref_dist_8x8_" + s)(P(b), 8, P(a), 24, bd - 8)
+    for (w, h), speed, cbits, qp in [((192, 136), 1, 3, 30), ((320, 192), 1, 1, 40), ((200, 136), 0, 2, 34), ((192, 128), 2, 3, 36)]:
+        f = Frame(w, h, bd, hbd, 32, 32)
+        f.randomize(rng)
+        org = f.copy()
+        for p in range(3):
+            org.plane(p)[...] = np.clip(f.plane(p).astype(int) + rng.integers(-7, 8, f.plane(p).shape), 0, (1 << bd) - 1)
+        bi, dd = random_blkinfo(rng, w, h, p_skip=0.25)
+        nfb = ((w + 63) // 64) * ((h + 63) // 64)
+        lam = 60.0
+        st = (C.c_int * 8)(*[127] * 8); ust = (C.c_int * 8)(*[127] * 8)
+        level = (C.c_int * (2 * nfb))(); sec = (C.c_int * (2 * nfb))(); dirs = (C.c_int * (64 * nfb))(); vars_ = (C.c_int * (64 * nfb))(); sbits = C.c_int(0)
+        bits = getattr(F, "ref_cdef_search_" + s)(C.byref(f.s), C.byref(org.s), dd, w, h, bd, qp, C.c_double(lam), cbits, speed, st, ust, level, sec, dirs, vars_, C.byref(sbits))
+        # oracle: distortion table, then selection
+        mse = np.zeros((2, nfb, 64), np.uint64); od = np.zeros((nfb, 64), np.int32); ov = np.zeros((nfb, 64), np.int32); ask = np.zeros(nfb, np.uint8)
+        getattr(O, "orc_cdef_search_mse_" + s)(P(f.Y, f.origin(0)), P(f.U, f.origin(1)), P(f.V, f.origin(1)), P(org.Y, org.origin(0)), P(org.U, org.origin(1)),
+                                                P(org.V, org.origin(1)), f.sy, f.sc, w, h, P(bi), speed, 5, bd, P(mse), P(od), P(ov), P(ask))
+        live = np.flatnonzero(ask == 0)
+        m0 = np.ascontiguousarray(mse[0][live]); m1 = np.ascontiguousarray(mse[1][live])
+        ost = (C.c_int * 16)(); oust = (C.c_int * 16)(); sel = (C.c_int * max(1, len(live)))()
+        obits = O.orc_cdef_select(P(m0), P(m1), len(live), speed, cbits, C.c_double(lam), ost, oust, sel)
+        assert obits == bits
+        assert list(ost)[:1 << bits] == list(st)[:1 << bits] and list(oust)[:1 << bits] == list(ust)[:1 << bits]
+        for k, fb in enumerate(live):
+            assert level[2 * fb] == ost[sel[k]] >> 2 and sec[2 * fb] == ost[sel[k]] & 3, (fb, k)
+            assert level[2 * fb + 1] == oust[sel[k]] >> 2 and sec[2 * fb + 1] == oust[sel[k]] & 3
+            # directions / variances of the blocks inside the frame
+            for m in range(8):
+                for n in range(8):
+                    if (fb % ((w + 63) // 64)) * 64 + n * 8 < w and (fb // ((w + 63) // 64)) * 64 + m * 8 < h:
+                        assert od[fb, m * 8 + n] == dirs[fb * 64 + m * 8 + n] and ov[fb, m * 8 + n] == vars_[fb * 64 + m * 8 + n]
+        assert sbits.value == bits * len(live)

@@ -92,6 +92,7 @@ lib.tb_deblock_frame.argtypes = [_vp, _vp, _i, _i]
 lib.tb_clpf_frame.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]
 lib.tb_clpf_detect_frame.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp]
 lib.tb_cdef_frame.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i]
+lib.tb_cdef_search_mse.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]
 lib.tb_pad_frame.argtypes = [_vp]
 lib.tb_create_reference_frame.argtypes = [_vp, _vp]
 lib.tb_scale_down2x2.argtypes = [_vp, _vp]

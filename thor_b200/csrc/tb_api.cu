@@ -215,6 +215,19 @@ static void cdef_t(tb_frame *rec, tb_frame *scr, const tb_blkinfo_t *bi, const i
          sec, pd, sd, dirvar, cs);
   swap_plane(rec, scr, plane);
 }
+template <class S>
+static void cdef_search_t(const tb_frame *rec, const tb_frame *org, const tb_blkinfo_t *bi, int speed, int pri_damping, int bitdepth, int32_t *dirvar, uint8_t *allskip,
+                          uint64_t *mse) {
+  static const int pristrengths[3] = {64, 32, 16};
+  const int w = rec->width, h = rec->height, nfb = ((w + 63) >> 6) * ((h + 63) >> 6), cs = bitdepth - 8, total = pristrengths[speed];
+  LAUNCH(cdef_allskip_kernel, (nfb + 127) / 128, 128, 0, bi, w, h, allskip);
+  const int nb = ((w + 7) >> 3) * ((h + 7) >> 3);
+  LAUNCH(cdef_dir_kernel<S>, grid_for_warps(nb), CTA_THREADS, 0, (const S *)rec->origin[0], rec->stride[0], w, h, allskip, cs, dirvar);
+  ck(cudaMemsetAsync(mse, 0, sizeof(uint64_t) * 2 * (size_t)nfb * 64, g.stream), "memset");
+  LAUNCH(cdef_search_kernel<S>, grid_for_warps(nfb * 2 * total), CTA_THREADS, 0, (const S *)rec->origin[0], (const S *)rec->origin[1], (const S *)rec->origin[2],
+         (const S *)org->origin[0], (const S *)org->origin[1], (const S *)org->origin[2], rec->stride[0], rec->stride[1], w, h, bi, allskip, dirvar, speed, total,
+         pri_damping, cs, (unsigned long long *)mse);
+}
 template <class S> static void pad_t(tb_frame *dst, const tb_frame *src, int border_only) {
   for (int p = 0; p < 3; p++) {
     dim3 blk(32, 8), grd((dst->pw[p] + 2 * dst->padh[p] + 31) / 32, (dst->ph[p] + 2 * dst->padv[p] + 7) / 8);
@@ -441,6 +454,14 @@ int tb_cdef_frame(tb_frame_t *rec, tb_frame_t *scratch, const tb_blkinfo_t *bi, 
   API_END();
 }
 
+int tb_cdef_search_mse(const tb_frame_t *rec, const tb_frame_t *org, const tb_blkinfo_t *blkinfo_dev, int speed, int pri_damping, int bitdepth, int32_t *dirvar_dev,
+                       uint8_t *allskip_dev, uint64_t *mse_dev) {
+  API_BEGIN();
+  if (!same_geometry(rec, org) || speed < 0 || speed > 2) return TB_ERR_ARG;
+  if (rec->esz == 1) cdef_search_t<uint8_t>(rec, org, blkinfo_dev, speed, pri_damping, bitdepth, dirvar_dev, allskip_dev, mse_dev);
+  else cdef_search_t<uint16_t>(rec, org, blkinfo_dev, speed, pri_damping, bitdepth, dirvar_dev, allskip_dev, mse_dev);
+  API_END();
+}
 int tb_pad_frame(tb_frame_t *f) {
   API_BEGIN();
   if (f->esz == 1) pad_t<uint8_t>(f, f, 1);

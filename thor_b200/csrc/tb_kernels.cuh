@@ -672,6 +672,92 @@ __global__ void cdef_plane_kernel(const S *src, S *dst, int stride, int width, i
   }
   dst[y * stride + x] = (S)out;
 }
+// a19 (encoder): distortion table of cdef_search (enc/encode_frame.c:285-376).  One warp per (filter block, plane class,
+// strength index): it filters every non-skip 8x8 block of the filter block with that strength and accumulates dist_8x8
+// (double, round-to-nearest ops: no contraction) for full luma blocks or the plain SSE otherwise.  Reference quirks kept:
+// chroma is filtered in 8x8 blocks whose skip flag / direction come from the top-left 4x4 entries of the block grid, and the
+// secondary strength is used unadjusted (0..3).
+__constant__ int8_t c_priconv[3][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {0, 1, 2, 3, 5, 7, 10, 13, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 3, 6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+template <class S>
+__global__ void __launch_bounds__(CTA_THREADS) cdef_search_kernel(const S *recY, const S *recU, const S *recV, const S *orgY, const S *orgU, const S *orgV, int sy, int sc,
+                                                                  int width, int height, const tb_blkinfo_t *bi, const uint8_t *allskip, const int32_t *dirvar, int speed,
+                                                                  int total, int pri_damping, int coeff_shift, unsigned long long *mse) {
+  const int nh = (width + 63) >> 6, nv = (height + 63) >> 6, nfb = nh * nv, lane = lane_id();
+  const int units = nfb * 2 * total;
+  for (int u = global_warp(); u < units; u += total_warps()) {
+    const int gi = u % total, cls = (u / total) & 1, fb = u / (2 * total);
+    if (allskip[fb]) {
+      if (lane == 0) mse[(size_t)cls * nfb * 64 + fb * 64 + gi] = 0;
+      continue;
+    }
+    const int l = fb % nh, k = fb / nh, xoff = l << 6, yoff = k << 6;
+    int h = min(height, (k + 1) << 6) & 63, w = min(width, (l + 1) << 6) & 63;
+    h += !h << 6;
+    w += !w << 6;
+    const int pri = c_priconv[speed][gi >> 2], sec = gi & 3;
+    unsigned long long acc = 0;
+    for (int plane = cls ? 1 : 0; plane <= (cls ? 2 : 0); plane++) {
+      const int sub = plane != 0, st = plane ? sc : sy, pw = width >> sub, ph = height >> sub;
+      const S *src = plane ? (plane == 1 ? recU : recV) : recY, *org = plane ? (plane == 1 ? orgU : orgV) : orgY;
+      const int nbm = (h + 7) >> (3 + sub), nbn = (w + 7) >> (3 + sub);
+      for (int b = 0; b < nbm * nbn; b++) {
+        const int m = b / nbn, n = b - m * nbn;
+        const int xpos = (xoff >> sub) + n * 8, ypos = (yoff >> sub) + m * 8;
+        const int sizex = min(pw - xpos, 8), sizey = min(ph - ypos, 8);
+        if (bi[(((yoff + m * 8) >> 2)) * (width >> 2) + ((xoff + n * 8) >> 2)].mode == 0) continue;
+        const int dir = dirvar[(fb * 2 + 0) * 64 + m * 8 + n], var = dirvar[(fb * 2 + 1) * 64 + m * 8 + n];
+        const int adj = plane ? pri : adjust_strength(pri, var);
+        int pd = pri_damping - (plane ? 1 : 0), sd = pri_damping - (plane ? 1 : 0);
+        if (adj) pd = max(ilog2(adj), pd);
+        const int ps = adj << coeff_shift, ss = sec << coeff_shift, d = pri ? dir : 0;
+        pd += coeff_shift;
+        sd += coeff_shift;
+        const int sel = (ps >> coeff_shift) & 1;
+        const int pt[2] = {sel ? 3 : 4, sel ? 3 : 2}, stp[2] = {2, 1};
+        unsigned long long s_s = 0, s_d = 0, s_s2 = 0, s_d2 = 0, s_sd = 0, sse = 0;
+        for (int p = lane; p < sizex * sizey; p += 32) {
+          const int i = p / sizex, j = p - i * sizex, x = xpos + j, y = ypos + i;
+          const int X = src[y * st + x];
+          int mx = X, mn = X, sum = 0;
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            const int dirs3[3] = {d, (d + 2) & 7, (d + 6) & 7};
+#pragma unroll
+            for (int g = 0; g < 3; g++) {
+              const int dy = c_cdef_dy[dirs3[g]][t], dx = c_cdef_dx[dirs3[g]][t];
+#pragma unroll
+              for (int sgn = 0; sgn < 2; sgn++) {
+                int yy = y + (sgn ? -dy : dy), xx = x + (sgn ? -dx : dx);
+                int v = (yy < 0 || yy >= ph || xx < 0 || xx >= pw) ? 30000 : (int)src[yy * st + xx];
+                sum += (g == 0 ? pt[t] : stp[t]) * constrain(v - X, g == 0 ? ps : ss, (unsigned)(g == 0 ? pd : sd));
+                if (v != 30000) mx = max(mx, v);
+                mn = min(mn, v);
+              }
+            }
+          }
+          sum = (int)(int16_t)sum;
+          const int F = iclip(X + ((8 + sum - (sum < 0)) >> 4), mn, mx);
+          const int Oo = org[y * st + x];
+          s_s += (unsigned)Oo; s_d += (unsigned)F; s_s2 += (unsigned)(Oo * Oo); s_d2 += (unsigned)(F * F); s_sd += (unsigned)(Oo * F);
+          sse += (unsigned)((F - Oo) * (F - Oo));
+        }
+        if (plane || sizex != 8 || sizey != 8) {
+          acc += warp_sum64(sse);
+        } else {
+          s_s = warp_sum64(s_s); s_d = warp_sum64(s_d); s_s2 = warp_sum64(s_s2); s_d2 = warp_sum64(s_d2); s_sd = warp_sum64(s_sd);
+          // dist_8x8 (enc/encode_frame.c:194-221), ISO-C evaluation order with explicitly rounded double operations
+          const unsigned long long svar = s_s2 - ((s_s * s_s + 32) >> 6), dvar = s_d2 - ((s_d * s_d + 32) >> 6);
+          const double a = __dmul_rn(__ull2double_rn(s_d2 + s_s2 - 2 * s_sd), 0.5);
+          const double bb = __dmul_rn(a, __ull2double_rn(svar + dvar + (unsigned long long)(400 << 2 * coeff_shift)));
+          const double den = __dsqrt_rn(__dadd_rn((double)(20000 << 4 * coeff_shift), __dmul_rn(__ull2double_rn(svar), __ull2double_rn(dvar))));
+          acc += (unsigned long long)floor(__dadd_rn(0.5, __ddiv_rn(bb, den)));
+        }
+      }
+    }
+    if (lane == 0) mse[(size_t)cls * nfb * 64 + fb * 64 + gi] = acc;
+  }
+}
+
 // drop-in cdef_filter_block_simd on a staged uint16 tile
 __global__ void cdef_block_kernel(uint8_t *dst8, uint16_t *dst16, int dstride, const uint16_t *in, int sstride, int pri, int sec, int dir, int pd, int sd, int bsize,
                                   int coeff_shift) {
