@@ -328,19 +328,7 @@ def run_gpu(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     me_ev = []
 
-    def step(e2e=False, time_me=False):
-        tb.check(L.tb_create_reference_frame(rec.h, pristine.h))  # the filters run in place: restore their input (device-side copy)
-        if e2e:
-            tb.check(L.tb_frame_upload(cur.h, h_y, W, h_u, h_v, W // 2))
-            tb.check(L.tb_memcpy_h2d(d_me.ptr, h_me, me_bytes)); tb.check(L.tb_memcpy_h2d(d_cand.ptr, h_cand, cand_bytes))
-        if time_me:
-            a, b = ev(), ev(); a.record(stream)
-        tb.check(L.tb_motion_estimate_batch(d_me.ptr, len(me_items), d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr))
-        if time_me:
-            b.record(stream); me_ev.append((a, b))
-        tb.check(L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1))
-        tb.check(L.tb_txfm_chain_batch(d_tx.ptr, len(tx_items), ESZ, BD, d_tx_out.ptr))
-        tb.check(L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD))
+    def filters_and_ref():
         tb.check(L.tb_deblock_frame(rec.h, d_bi.ptr, QP, BD))
         for plane in range(3):
             tb.check(L.tb_cdef_frame(rec.h, scratch.h, d_bi.ptr, d_pri[int(plane > 0)].ptr, d_sec[int(plane > 0)].ptr, 5, 5, d_dv.ptr, BD, plane))
@@ -349,10 +337,66 @@ def run_gpu(args):
         for plane, (fbl, strength) in enumerate(((6, 2), (4, 1), (4, 2))):
             tb.check(L.tb_clpf_frame(rec.h, scratch.h, d_bi.ptr, None, fbl, strength, BD, plane, QP))
         tb.check(L.tb_create_reference_frame(newref.h, rec.h))
-        if e2e:
-            tb.check(L.tb_memcpy_d2h(h_me_out, d_me_out.ptr, 8 * len(me_items)))
-            tb.check(L.tb_memcpy_d2h(h_tx_out, d_tx_out.ptr, 16 * len(tx_items)))
-            tb.check(L.tb_frame_download(rec.h, h_rec[0], W, h_rec[1], h_rec[2], W // 2))
+
+    def step(time_me=False):
+        tb.check(L.tb_create_reference_frame(rec.h, pristine.h))  # the filters run in place: restore their input (device-side copy)
+        if time_me:
+            a, b = ev(), ev(); a.record(stream)
+        tb.check(L.tb_motion_estimate_batch(d_me.ptr, len(me_items), d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr))
+        if time_me:
+            b.record(stream); me_ev.append((a, b))
+        tb.check(L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1))
+        tb.check(L.tb_txfm_chain_batch(d_tx.ptr, len(tx_items), ESZ, BD, d_tx_out.ptr))
+        tb.check(L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD))
+        filters_and_ref()
+
+    # End-to-end step: the same work fed from pinned host memory and drained to pinned host memory INSIDE the step.  Three
+    # streams: uploads (source frame, candidate lists, search items in NCH chunks), compute, downloads (search results,
+    # transform results per chunk, filtered frame); chunk i of a kernel waits only for chunk i of its upload and chunk i of a
+    # download waits only for chunk i of its kernel, so PCIe traffic hides behind the kernels.  Nothing is carried over from
+    # one step to the next: the step ends when the last download has landed.
+    NCH = 4
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    use = lambda st: tb.check(L.tb_set_stream(C.c_void_p(st.cuda_stream)))
+    bounds = lambda n: [n * k // NCH for k in range(NCH + 1)]
+    mb, xb = bounds(len(me_items)), bounds(len(tx_items))
+    ME_SZ, TX_SZ = me_items.dtype.itemsize, tx_items.dtype.itemsize
+
+    def step_e2e():
+        start = torch.cuda.Event(); start.record(stream)
+        up.wait_event(start); down.wait_event(start)
+        use(up)
+        tb.check(L.tb_frame_upload(cur.h, h_y, W, h_u, h_v, W // 2))
+        tb.check(L.tb_memcpy_h2d(d_cand.ptr, h_cand, cand_bytes))
+        up_done = []
+        for k in range(NCH):
+            tb.check(L.tb_memcpy_h2d(d_me.ptr + mb[k] * ME_SZ, h_me + mb[k] * ME_SZ, (mb[k + 1] - mb[k]) * ME_SZ))
+            e = torch.cuda.Event(); e.record(up); up_done.append(e)
+        use(stream)
+        tb.check(L.tb_create_reference_frame(rec.h, pristine.h))
+        for k in range(NCH):
+            stream.wait_event(up_done[k])
+            tb.check(L.tb_motion_estimate_batch(d_me.ptr + mb[k] * ME_SZ, mb[k + 1] - mb[k], d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr + 8 * mb[k]))
+        me_done = torch.cuda.Event(); me_done.record(stream)
+        tb.check(L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1))
+        tx_done = []
+        for k in range(NCH):
+            tb.check(L.tb_txfm_chain_batch(d_tx.ptr + xb[k] * TX_SZ, xb[k + 1] - xb[k], ESZ, BD, d_tx_out.ptr + 16 * xb[k]))
+            e = torch.cuda.Event(); e.record(stream); tx_done.append(e)
+        tb.check(L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD))
+        filters_and_ref()
+        all_done = torch.cuda.Event(); all_done.record(stream)
+        use(down)
+        down.wait_event(me_done)
+        tb.check(L.tb_memcpy_d2h_async(h_me_out, d_me_out.ptr, 8 * len(me_items)))
+        for k in range(NCH):
+            down.wait_event(tx_done[k])
+            tb.check(L.tb_memcpy_d2h_async(h_tx_out + 16 * xb[k], d_tx_out.ptr + 16 * xb[k], 16 * (xb[k + 1] - xb[k])))
+        down.wait_event(all_done)
+        tb.check(L.tb_frame_download_async(rec.h, h_rec[0], W, h_rec[1], h_rec[2], W // 2))
+        landed = torch.cuda.Event(); landed.record(down)
+        use(stream)
+        stream.wait_event(landed)
 
     def barrier():
         if world > 1:
@@ -392,10 +436,12 @@ def run_gpu(args):
             bd_ms[nm] = round(a.elapsed_time(b), 3)
         sys.stderr.write("breakdown_ms " + json.dumps(bd_ms) + "\n")
     # end-to-end leg (host buffers in, host results out)
-    step(e2e=True); barrier()
+    for _ in range(2):
+        step_e2e()
+    barrier()
     e0, e1 = ev(), ev(); e0.record(stream)
     for _ in range(args.steps):
-        step(e2e=True)
+        step_e2e()
     e1.record(stream); barrier()
     ems = e0.elapsed_time(e1)
     # work counters of the motion-search kernel (one extra untimed launch)

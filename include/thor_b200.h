@@ -103,6 +103,8 @@ void tb_frame_destroy(tb_frame_t *f);
 /* host <-> device copies of the visible area (planes given with their host pitches in samples) */
 int tb_frame_upload(tb_frame_t *f, const void *y, int ystride, const void *u, const void *v, int cstride);
 int tb_frame_download(const tb_frame_t *f, void *y, int ystride, void *u, void *v, int cstride);
+/* same, without waiting: the host buffers (pinned) are valid once the current stream has been synchronised */
+int tb_frame_download_async(const tb_frame_t *f, void *y, int ystride, void *u, void *v, int cstride);
 /* device pointer to sample (0,0) of plane p (0 Y, 1 U, 2 V) and its pitch in samples */
 void *tb_frame_plane(const tb_frame_t *f, int plane, int *stride);
 
@@ -242,6 +244,8 @@ void *tb_malloc(size_t bytes);
 void tb_free(void *p);
 int tb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int tb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+/* enqueue only (pinned destination); pair with tb_sync() or an event on the stream given to tb_set_stream() */
+int tb_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes);
 void *tb_malloc_host(size_t bytes); /* pinned */
 void tb_free_host(void *p);
 

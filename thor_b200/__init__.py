@@ -72,12 +72,14 @@ lib.tb_malloc_host.argtypes = [C.c_size_t]
 lib.tb_free_host.argtypes = [_vp]
 lib.tb_memcpy_h2d.argtypes = [_vp, _vp, C.c_size_t]
 lib.tb_memcpy_d2h.argtypes = [_vp, _vp, C.c_size_t]
+lib.tb_memcpy_d2h_async.argtypes = [_vp, _vp, C.c_size_t]
 lib.tb_set_stream.argtypes = [_vp]
 lib.tb_frame_create.restype = _vp
 lib.tb_frame_create.argtypes = [_i, _i, _i, _i]
 lib.tb_frame_destroy.argtypes = [_vp]
 lib.tb_frame_upload.argtypes = [_vp, _vp, _i, _vp, _vp, _i]
 lib.tb_frame_download.argtypes = [_vp, _vp, _i, _vp, _vp, _i]
+lib.tb_frame_download_async.argtypes = [_vp, _vp, _i, _vp, _vp, _i]
 lib.tb_frame_plane.restype = _vp
 lib.tb_frame_plane.argtypes = [_vp, _i, C.POINTER(_i)]
 lib.tb_sad_batch.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]

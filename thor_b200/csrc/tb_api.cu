@@ -286,6 +286,12 @@ int tb_memcpy_d2h(void *d, const void *s, size_t n) {
   if (e != cudaSuccess) { set_err("D2H", e); return TB_ERR_CUDA; }
   return TB_OK;
 }
+int tb_memcpy_d2h_async(void *d, const void *s, size_t n) {
+  API_BEGIN();
+  cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g.stream);
+  if (e != cudaSuccess) { set_err("D2H", e); return TB_ERR_CUDA; }
+  return TB_OK;
+}
 void *tb_malloc_host(size_t bytes) {
   if (!ensure_ctx()) return nullptr;
   void *p = nullptr;
@@ -328,7 +334,10 @@ int tb_frame_upload(tb_frame_t *f, const void *y, int ys, const void *u, const v
   }
   return TB_OK;
 }
-int tb_frame_download(const tb_frame_t *f, void *y, int ys, void *u, void *v, int cs) {
+static int frame_download(const tb_frame *f, void *y, int ys, void *u, void *v, int cs, bool sync);
+int tb_frame_download(const tb_frame_t *f, void *y, int ys, void *u, void *v, int cs) { return frame_download(f, y, ys, u, v, cs, true); }
+int tb_frame_download_async(const tb_frame_t *f, void *y, int ys, void *u, void *v, int cs) { return frame_download(f, y, ys, u, v, cs, false); }
+static int frame_download(const tb_frame *f, void *y, int ys, void *u, void *v, int cs, bool sync) {
   API_BEGIN();
   void *dst[3] = {y, u, v};
   for (int p = 0; p < 3; p++) {
@@ -337,7 +346,7 @@ int tb_frame_download(const tb_frame_t *f, void *y, int ys, void *u, void *v, in
                                       cudaMemcpyDeviceToHost, g.stream);
     if (e != cudaSuccess) { set_err("frame download", e); return TB_ERR_CUDA; }
   }
-  cudaError_t e = cudaStreamSynchronize(g.stream);
+  cudaError_t e = sync ? cudaStreamSynchronize(g.stream) : cudaSuccess;
   if (e != cudaSuccess) { set_err("frame download", e); return TB_ERR_CUDA; }
   return TB_OK;
 }
