@@ -356,6 +356,30 @@ def test_batch_motion_estimate(tb, hbd, bd, speed, bip):
 
 
 @pytest.mark.parametrize("hbd,bd", BD)
+def test_motion_estimate_large_blocks(tb, hbd, bd):
+    """64x64 .. 128x128 prediction blocks are searched by a whole CTA (four warps on row bands); same results as the oracle"""
+    rng = np.random.default_rng(131)
+    s = sfx(hbd)
+    w, h = 384, 256
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    n = 36
+    items, call, meta = build_me_items(tb, rng, n, w, h, cur, href, dcur, dref, esz, sizes=(64, 128), speed=0)
+    d_items = tb.DevBuf.from_array(items); d_c = tb.DevBuf.from_array(call); d_out = tb.DevBuf(8 * n)
+    tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, d_c.ptr, esz, bd, 0, 1, w, h, d_out.ptr))
+    got = d_out.download(tb.ME_RESULT, n)
+    for i, (size, bw, bh, ox, oy, xpos, ypos, sign, cc, mvc, mvp, lam) in enumerate(meta):
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur.y[ypos:ypos + size, xpos:xpos + size]
+        m0 = (C.c_int16 * 2)(0, 0)
+        cands = (C.c_int16 * (2 * max(len(cc), 1)))(*[int(v) for v in cc.reshape(-1)] or [0, 0])
+        cost = getattr(O, "orc_motion_estimate_" + s)(P(org, oy * size + ox), P(href.Y, href.origin(0) + (ypos + oy) * href.sy + xpos + ox), size, href.sy, bw, bh, m0,
+                                                       (C.c_int16 * 2)(int(mvc[0]), int(mvc[1])), (C.c_int16 * 2)(int(mvp[0]), int(mvp[1])), C.c_double(lam), 0, bd,
+                                                       sign, w, h, xpos, ypos, cands, len(cc), 1)
+        assert (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])) == (cost & 0xffffffff, m0[0], m0[1]), (i, size, bw, bh)
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
 def test_batch_interp(tb, hbd, bd):
     rng = np.random.default_rng(109)
     s = sfx(hbd)

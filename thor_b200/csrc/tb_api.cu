@@ -370,8 +370,19 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
                              tb_me_result_t *out) {
   API_BEGIN();
   if (n <= 0) return TB_OK;
-  if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
-  else LAUNCH(me_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
+  // stream-ordered scratch: the sorted item list and the scheduler's counters (see me_batch_kernel)
+  int *meta = nullptr, *idx = nullptr;
+  ck(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "me scratch");
+  idx = meta + 128;
+  ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "me scratch");
+  const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
+  LAUNCH(me_hist_kernel, sgrid, 256, 0, items, n, speed, meta);
+  LAUNCH(me_scan_kernel, 1, 32, 0, meta);
+  LAUNCH(me_scatter_kernel, sgrid, 256, 0, items, n, speed, meta, idx);
+  const int grid = std::min((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, g.sm_count * TB_ME_MINBLOCKS);  // persistent: every CTA resident
+  if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
+  else LAUNCH(me_batch_kernel<uint16_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
+  ck(cudaFreeAsync(meta, g.stream), "me scratch");
   API_END();
 }
 int tb_motion_estimate_bi_batch(const tb_me_bi_item_t *items, int n, const int16_t *cand, int sample_bytes, int bitdepth, int bip, int fw, int fh, tb_me_result_t *out) {

@@ -429,11 +429,13 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
 // enc/encode_block.c:625-663) without materialising the predictions: probe t = lane / 4 uses MV (mvx0 + dx[t], mvy0 + dy[t]),
 // its four lanes share the block's samples.  Every lane of probe t returns SAD t.
 template <class S>
-__device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int bip, int pic_w, int pic_h,
-                                      int xpos, int ypos, int bitdepth) {
+__device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *ref, int rs, int w, int hfull, int mvx, int mvy, int sign, int bip, int pic_w, int pic_h,
+                                      int xpos, int ypos, int bitdepth, int row0, int h) {
+  // rows [row0, row0 + h) of the w x hfull block (a team of warps splits the block into row bands; one warp: row0 = 0, h = hfull)
   int hi, vi, xf, yf;
-  split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
-  const S *ip = ref + vi * rs + hi;
+  split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, hfull, hi, vi, xf, yf);
+  const S *ip = ref + (vi + row0) * rs + hi;
+  o += row0 * os;
   const int maxv = (1 << bitdepth) - 1, lw = ilog2(w), sub = lane_id() & 3;
   uint32_t acc = 0;
   if (sizeof(S) == 1) {
@@ -583,10 +585,31 @@ __device__ __forceinline__ int warp_first_min(uint32_t cost, int n, uint32_t &be
   return who ? __ffs(who) - 1 : -1;
 }
 
-template <class S>
-__device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs, MeCtx &c, int mvcx, int mvcy, const int16_t *cand,
-                                     int ncand, int &out_mvx, int &out_mvy, uint32_t &out_cost) {
+// A team of TW warps (TW == 1, or the whole CTA) runs one search: every warp executes the same control flow on the same
+// totals and evaluates the SADs of its own band of h / TW rows; MeTeam::sum adds the per-lane partial SADs of the bands through
+// shared memory (two alternating buffers, one __syncthreads per exchange).
+template <int TW> struct MeTeam {
+  uint32_t *xch;  // [2][TW][32]
+  int warp, phase;
+  __device__ __forceinline__ uint32_t sum(uint32_t v) {
+    if (TW == 1) return v;
+    uint32_t *b = xch + (phase & 1) * TW * 32;
+    phase++;
+    b[warp * 32 + lane_id()] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < TW; k++) t += b[k * 32 + lane_id()];
+    return t;
+  }
+};
+
+template <class S, int TW>
+__device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_full, int rs, MeCtx &c, int mvcx, int mvcy, const int16_t *cand,
+                                     int ncand, int &out_mvx, int &out_mvy, uint32_t &out_cost, MeTeam<TW> &tm) {
   const int lane = lane_id();
+  const int band_h = c.height / TW, row0 = tm.warp * band_h;  // this warp's rows
+  const S *orig = orig_full + row0 * os, *ref = ref_full + row0 * rs;
   const int s = c.s, shift = c.bitdepth - 8;
   uint32_t min_sad = 1u << 31;  // MAX_UINT32, common/global.h:63
   int optx = 0, opty = 0;
@@ -613,14 +636,14 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
         int base = s * (cx >> 2) + s * (cy >> 2) * rs;
 #pragma unroll
         for (int t = 0; t < 5; t++) {
-          uint32_t v = multi_sad<S>(orig, os, ref, rs, c.width, c.height, base + offs[t], n);
+          uint32_t v = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, base + offs[t], n));
           if (v < b) { b = v; bxo = offs[t]; }
         }
         sad = b;
         cx = (int)(int16_t)(cx + (s * bxo << 2));
         c.n_int += 5 * n;
       } else {
-        sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+        sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
         c.n_int += n;
       }
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
@@ -653,14 +676,14 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
       int bxo = 0;
 #pragma unroll
       for (int t = 0; t < 5; t++) {
-        uint32_t v = multi_sad<S>(orig, os, ref, rs, c.width, c.height, pos + offs[t], n);
+        uint32_t v = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, pos + offs[t], n));
         if (v < b) { b = v; bxo = offs[t]; }
       }
       sad = b;
       cx = (int)(int16_t)(cx + (s * bxo << 2));
       c.n_int += 5 * n;
     } else {
-      sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, pos, n);
+      sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, pos, n));
       c.n_int += n;
     }
     uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
@@ -685,7 +708,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
       int dir = (start + lane) % 6;
       int cx = (int)(int16_t)(refx + diy[dir] * 4), cy = (int)(int16_t)(refy + dix[dir] * 4);
       clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
-      uint32_t sad = multi_sad<S>(orig, os, ref, rs, c.width, c.height, s * (cx >> 2) + s * (cy >> 2) * rs, n);
+      uint32_t sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
       c.n_int += n;
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       uint32_t best;
@@ -717,7 +740,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
     {
       const int t = (lane >> 2) + 1;
       int cy = (int)(int16_t)(refy + hm[t]), cx = (int)(int16_t)(refx + hn[t]);
-      uint32_t sad = subpel_stage_sads<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+      uint32_t sad = tm.sum(subpel_stage_sads<S>(orig_full, os, ref_full, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth, row0, band_h));
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       for (int i = 1; i <= 8; i++) {
         uint32_t ci = __shfl_sync(FULL, cost, (i - 1) * 4);
@@ -729,7 +752,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
     {
       const int t = (lane >> 2) + 1;
       int cy = (int)(int16_t)(opty + qm[t]), cx = (int)(int16_t)(optx + qn[t]);
-      uint32_t sad = subpel_stage_sads<S>(orig, os, ref, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth);
+      uint32_t sad = tm.sum(subpel_stage_sads<S>(orig_full, os, ref_full, rs, c.width, c.height, cx, cy, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos, c.bitdepth, row0, band_h));
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       for (int i = 1; i <= 8; i++) {
         uint32_t ci = __shfl_sync(FULL, cost, (i - 1) * 4);
@@ -740,7 +763,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
     // ---- bilinear approximations (:664-703)
     int rx = (int)(int16_t)(refx * s), ry = (int)(int16_t)(refy * s);
     int spx, spy;
-    uint32_t sad = warp_sad_fasthalf<S>(orig, os, ref + (rx >> 2) + (ry >> 2) * rs, rs, c.width, c.height, spx, spy);
+    uint32_t sad = warp_sad_fasthalf<S>(orig_full, os, ref_full + (rx >> 2) + (ry >> 2) * rs, rs, c.width, c.height, spx, spy);
     uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(ry + s * spy - c.mvpy, rx + s * spx - c.mvpx));
     if (cost < cmin) { cmin = cost; xdh = s * spx; ydh = s * spy; }
     spx = xdh;
@@ -750,7 +773,7 @@ __device__ void warp_motion_estimate(const S *orig, int os, const S *ref, int rs
     optx = (int)(int16_t)(optx + xdh);
     opty = (int)(int16_t)(opty + ydh);
     int qx, qy;
-    sad = warp_sad_fastquarter<S>(orig, os, ref + s * (rx >> 2) + s * (ry >> 2) * rs, rs, c.width, c.height, spx, spy, qx, qy);
+    sad = warp_sad_fastquarter<S>(orig_full, os, ref_full + s * (rx >> 2) + s * (ry >> 2) * rs, rs, c.width, c.height, spx, spy, qx, qy);
     cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(ry + s * qy - c.mvpy, rx + s * qx - c.mvpx));
     if (cost < cmin) { cmin = cost; xdq = s * qx; ydq = s * qy; }
   }

@@ -59,27 +59,104 @@ __global__ void fast_subpel_kernel(const S *a, int as, const S *b, int bs, int w
 }
 
 // ---- a5 --------------------------------------------------------------------------------------------------------
+// Scheduling of a search batch.  Searches cost ~ area x probes and a batch mixes 4x4 ... 128x128 blocks; a single warp needs
+// milliseconds for one 128x128 search.  So blocks of >= 2048 samples are searched by the whole CTA (four warps on four row
+// bands, MeTeam), which divides their latency by four: a counting sort (three tiny kernels: histogram, scan, scatter) lists
+// them largest first, and one persistent kernel first draws from that list with an atomic cursor (longest-processing-time
+// first), then draws the remaining searches, one warp each, from the caller's array in its own order.
+// class = ilog2(area), + 16 when the CTA-team form applies (speed 0, height a multiple of 8 rows per warp)
+constexpr int ME_TEAM_WARPS = WARPS_PER_CTA;
+#ifndef TB_ME_DRAW
+#define TB_ME_DRAW 4
+#endif
+__device__ __forceinline__ int me_class(int w, int h, int speed) {
+  const int area = w * h, b = min(ilog2(max(area, 1)), 15);
+  return (speed == 0 && area >= 2048 && (h % (8 * ME_TEAM_WARPS)) == 0) ? 16 + b : b;
+}
+// meta layout (ints): [0,32) histogram, [32,64) first list position of each class, [64,96) fill cursors, 96 = number of team
+// items, 97 = team cursor, 98 = warp cursor
+__global__ void me_hist_kernel(const tb_me_item_t *items, int n, int speed, int *meta) {
+  __shared__ int h[32];
+  if (threadIdx.x < 32) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = me_class(items[i].width, items[i].height, speed);
+    if (c >= 16) atomicAdd(&h[c], 1);  // only team items are listed; the others are drawn from the caller's array in its own order
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(&meta[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void me_scan_kernel(int *meta) {
+  const int b = threadIdx.x;  // 32 threads
+  int before = 0, team = 0;
+  for (int k = 31; k > b; k--) before += meta[k];
+  for (int k = 16; k < 32; k++) team += meta[k];
+  meta[32 + b] = before;
+  meta[64 + b] = 0;
+  if (b == 0) { meta[96] = team; meta[97] = 0; meta[98] = 0; }
+}
+__global__ void me_scatter_kernel(const tb_me_item_t *items, int n, int speed, int *meta, int *idx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = me_class(items[i].width, items[i].height, speed);
+    if (c >= 16) idx[meta[32 + c] + atomicAdd(&meta[64 + c], 1)] = i;
+  }
+}
+
+template <class S, int TW>
+__device__ __noinline__ void me_run_item(const tb_me_item_t *items, int it, const int16_t *cand, int bitdepth, int speed, int bip, int fw, int fh, tb_me_result_t *out,
+                                            unsigned long long *stats, MeTeam<TW> &tm) {
+  tb_me_item_t q = items[it];
+  MeCtx c;
+  c.size = q.size; c.width = q.width; c.height = q.height; c.sign = q.sign; c.s = q.sign ? -1 : 1;
+  c.xpos = q.xpos; c.ypos = q.ypos; c.fw = fw; c.fh = fh; c.bitdepth = bitdepth; c.speed = speed; c.bip = bip;
+  c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda; c.n_int = 0; c.n_sub = 0;
+  int mx, my;
+  uint32_t cost;
+  warp_motion_estimate<S, TW>((const S *)q.orig, q.ostride, (const S *)q.ref, q.rstride, c, q.mvc_x, q.mvc_y, cand + 2 * (size_t)q.cand_ofs, q.ncand, mx, my, cost, tm);
+  if (lane_id() == 0 && tm.warp == 0) {
+    out[it].mvx = (int16_t)mx; out[it].mvy = (int16_t)my; out[it].cost = cost;
+    if (stats) {  // roofline accounting: samples compared at integer positions, samples fetched for sub-pel probes
+      atomicAdd(&stats[0], 1ull);
+      atomicAdd(&stats[1], (unsigned long long)c.n_int);
+      atomicAdd(&stats[2], (unsigned long long)c.n_sub);
+      atomicAdd(&stats[3], (unsigned long long)(c.n_int + 1) * q.width * q.height);
+      atomicAdd(&stats[4], (unsigned long long)c.n_sub * ((q.width + 5) * (q.height + 5) + q.width * q.height));
+    }
+  }
+}
+
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(const tb_me_item_t *items, int n, const int16_t *cand, int bitdepth, int speed, int bip,
-                                                               int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
-  for (int it = global_warp(); it < n; it += total_warps()) {
-    tb_me_item_t q = items[it];
-    MeCtx c;
-    c.size = q.size; c.width = q.width; c.height = q.height; c.sign = q.sign; c.s = q.sign ? -1 : 1;
-    c.xpos = q.xpos; c.ypos = q.ypos; c.fw = fw; c.fh = fh; c.bitdepth = bitdepth; c.speed = speed; c.bip = bip;
-    c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda; c.n_int = 0; c.n_sub = 0;
-    int mx, my;
-    uint32_t cost;
-    warp_motion_estimate<S>((const S *)q.orig, q.ostride, (const S *)q.ref, q.rstride, c, q.mvc_x, q.mvc_y, cand + 2 * (size_t)q.cand_ofs, q.ncand, mx, my,
-                            cost);
-    if (lane_id() == 0) {
-      out[it].mvx = (int16_t)mx; out[it].mvy = (int16_t)my; out[it].cost = cost;
-      if (stats) {  // roofline accounting: samples compared at integer positions, samples fetched for sub-pel probes
-        atomicAdd(&stats[0], 1ull);
-        atomicAdd(&stats[1], (unsigned long long)c.n_int);
-        atomicAdd(&stats[2], (unsigned long long)c.n_sub);
-        atomicAdd(&stats[3], (unsigned long long)(c.n_int + 1) * q.width * q.height);
-        atomicAdd(&stats[4], (unsigned long long)c.n_sub * ((q.width + 5) * (q.height + 5) + q.width * q.height));
+__global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(const tb_me_item_t *items, int n, const int *idx, int *meta, const int16_t *cand, int bitdepth,
+                                                                                 int speed, int bip, int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
+  __shared__ uint32_t xch[2 * ME_TEAM_WARPS * 32];
+  __shared__ int s_next;
+  const int nteam = meta[96];
+  // phase 1: the CTA as a team on the large blocks
+  {
+    MeTeam<ME_TEAM_WARPS> tm;
+    tm.xch = xch; tm.warp = threadIdx.x >> 5; tm.phase = 0;
+    for (;;) {
+      if (threadIdx.x == 0) s_next = atomicAdd(&meta[97], 1);
+      __syncthreads();
+      const int k = s_next;
+      __syncthreads();
+      if (k >= nteam) break;
+      me_run_item<S, ME_TEAM_WARPS>(items, idx[k], cand, bitdepth, speed, bip, fw, fh, out, stats, tm);
+    }
+  }
+  // phase 2: one warp per search, drawn four at a time from the caller's array (neighbouring items share samples: keep them on
+  // neighbouring warps); team items were done in phase 1
+  {
+    MeTeam<1> tm;
+    tm.xch = nullptr; tm.warp = 0; tm.phase = 0;
+    for (;;) {
+      int k = 0;
+      if (lane_id() == 0) k = atomicAdd(&meta[98], TB_ME_DRAW);
+      k = __shfl_sync(FULL, k, 0);
+      if (k >= n) break;
+      for (int it = k; it < min(k + TB_ME_DRAW, n); it++) {
+        if (nteam && me_class(items[it].width, items[it].height, speed) >= 16) continue;
+        me_run_item<S, 1>(items, it, cand, bitdepth, speed, bip, fw, fh, out, stats, tm);
       }
     }
   }
