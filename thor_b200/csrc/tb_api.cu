@@ -50,6 +50,13 @@ bool ensure_ctx() {
   if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) g.sm_count = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking)) != cudaSuccess) { set_err("cudaStreamCreate", e); g.failed = true; return false; }
   g.own_stream = true;
+  {  // stream-ordered scratch (cudaMallocAsync) stays cached in the pool across synchronisations instead of going back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   g.ready = true;
   return true;
 }
@@ -376,9 +383,10 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
   idx = meta + 128;
   ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "me scratch");
   const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
-  LAUNCH(me_hist_kernel, sgrid, 256, 0, items, n, speed, meta);
-  LAUNCH(me_scan_kernel, 1, 32, 0, meta);
-  LAUNCH(me_scatter_kernel, sgrid, 256, 0, items, n, speed, meta, idx);
+  const MeClassOf cls{speed};
+  LAUNCH((sched_hist_kernel<tb_me_item_t, MeClassOf>), sgrid, 256, 0, items, n, cls, meta);
+  LAUNCH(sched_scan_kernel, 1, 32, 0, meta);
+  LAUNCH((sched_scatter_kernel<tb_me_item_t, MeClassOf>), sgrid, 256, 0, items, n, cls, meta, idx);
   const int grid = std::min((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, g.sm_count * TB_ME_MINBLOCKS);  // persistent: every CTA resident
   if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
   else LAUNCH(me_batch_kernel<uint16_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
@@ -415,9 +423,19 @@ int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, in
   API_BEGIN();
   if (n <= 0) return TB_OK;
   size_t smem = ((DCT_TAB8_SIZE * 2 + 15) & ~15) + sizeof(TxScratch) * WARPS_PER_CTA;
-  const int warps = (n + 31) / 32;  // each warp iteration consumes 32 items
-  if (sample_bytes == 1) LAUNCH(txfm_chain_kernel<uint8_t>, grid_for_warps(warps), CTA_THREADS, smem, items, n, bitdepth, out);
-  else LAUNCH(txfm_chain_kernel<uint16_t>, grid_for_warps(warps), CTA_THREADS, smem, items, n, bitdepth, out);
+  int *meta = nullptr, *idx = nullptr;
+  ck(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "txfm scratch");
+  idx = meta + 128;
+  ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "txfm scratch");
+  const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
+  const TxClassOf cls{};
+  LAUNCH((sched_hist_kernel<tb_txfm_item_t, TxClassOf>), sgrid, 256, 0, items, n, cls, meta);
+  LAUNCH(sched_scan_kernel, 1, 32, 0, meta);
+  LAUNCH((sched_scatter_kernel<tb_txfm_item_t, TxClassOf>), sgrid, 256, 0, items, n, cls, meta, idx);
+  const int grid = std::min((n + 31) / 32, g.sm_count * 5);  // persistent: every CTA resident (launch bounds: 5 per SM)
+  if (sample_bytes == 1) LAUNCH(txfm_chain_kernel<uint8_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
+  else LAUNCH(txfm_chain_kernel<uint16_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
+  ck(cudaFreeAsync(meta, g.stream), "txfm scratch");
   API_END();
 }
 int tb_intra_batch(const tb_intra_item_t *items, int n, int sample_bytes, int bitdepth) {

@@ -74,31 +74,42 @@ __device__ __forceinline__ int me_class(int w, int h, int speed) {
   return (speed == 0 && area >= 2048 && (h % (8 * ME_TEAM_WARPS)) == 0) ? 16 + b : b;
 }
 // meta layout (ints): [0,32) histogram, [32,64) first list position of each class, [64,96) fill cursors, 96 = number of team
-// items, 97 = team cursor, 98 = warp cursor
-__global__ void me_hist_kernel(const tb_me_item_t *items, int n, int speed, int *meta) {
+// items, 97 = team cursor, 98 = warp cursor, 99 = number of listed items, 100 = group cursor.  A class functor returns the
+// class (0..31; >= 16: searched/transformed by the whole CTA) of an item, or -1 when the item is not listed.
+struct MeClassOf {
+  int speed;
+  __device__ __forceinline__ int operator()(const tb_me_item_t &q) const {
+    const int c = me_class(q.width, q.height, speed);
+    return c >= 16 ? c : -1;  // only team items are listed; the others are drawn from the caller's array in its own order
+  }
+};
+struct TxClassOf {  // transform blocks > 8x8 are listed (one warp each, the CTA for >= 64x64); 4x4 / 8x8 run one per thread
+  __device__ __forceinline__ int operator()(const tb_txfm_item_t &q) const { return q.size >= 64 ? 16 + ilog2(q.size) : (q.size > 8 ? ilog2(q.size) : -1); }
+};
+template <class Item, class F> __global__ void sched_hist_kernel(const Item *items, int n, F f, int *meta) {
   __shared__ int h[32];
   if (threadIdx.x < 32) h[threadIdx.x] = 0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = me_class(items[i].width, items[i].height, speed);
-    if (c >= 16) atomicAdd(&h[c], 1);  // only team items are listed; the others are drawn from the caller's array in its own order
+    const int c = f(items[i]);
+    if (c >= 0) atomicAdd(&h[c], 1);
   }
   __syncthreads();
   if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(&meta[threadIdx.x], h[threadIdx.x]);
 }
-__global__ void me_scan_kernel(int *meta) {
+__global__ void sched_scan_kernel(int *meta) {
   const int b = threadIdx.x;  // 32 threads
-  int before = 0, team = 0;
+  int before = 0, team = 0, all = 0;
   for (int k = 31; k > b; k--) before += meta[k];
-  for (int k = 16; k < 32; k++) team += meta[k];
+  for (int k = 0; k < 32; k++) { all += meta[k]; if (k >= 16) team += meta[k]; }
   meta[32 + b] = before;
   meta[64 + b] = 0;
-  if (b == 0) { meta[96] = team; meta[97] = 0; meta[98] = 0; }
+  if (b == 0) { meta[96] = team; meta[97] = 0; meta[98] = 0; meta[99] = all; meta[100] = 0; }
 }
-__global__ void me_scatter_kernel(const tb_me_item_t *items, int n, int speed, int *meta, int *idx) {
+template <class Item, class F> __global__ void sched_scatter_kernel(const Item *items, int n, F f, int *meta, int *idx) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = me_class(items[i].width, items[i].height, speed);
-    if (c >= 16) idx[meta[32 + c] + atomicAdd(&meta[64 + c], 1)] = i;
+    const int c = f(items[i]);
+    if (c >= 0) idx[meta[32 + c] + atomicAdd(&meta[64 + c], 1)] = i;
   }
 }
 
@@ -221,19 +232,249 @@ struct alignas(16) TxShared {
 };
 
 // residual on the fly -> forward -> quantise -> de-quantise -> inverse -> reconstruct + SSD.
-// Each warp takes 32 consecutive items per iteration: its 4x4 and 8x8 items run one per LANE (thread_txfm4 in registers,
-// thread_txfm8 in per-thread local arrays); larger blocks are then processed one at a time by the whole warp.
+// One transform block > 8x8 handled by a team of TW warps (TW == 1: a warp; TW == WARPS_PER_CTA: the CTA, for 64x64 and
+// 128x128 whose box-sum load and replicated output are per-sample passes over up to 16384 samples).
+template <class S, int TW>
+__device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth, TxScratch &sc, int16_t *rt, const int8_t *tab8, const int8_t *tab8t, unsigned long long *red,
+                                          int *bc, tb_txfm_result_t *res) {
+  constexpr int PI = 34;  // int16 pitch of the scratch tiles: even (4-byte aligned pairs for DP2A), 17 words -> odd word pitch
+  constexpr int NT = 32 * TW;
+  const int tid = TW == 1 ? lane_id() : (int)threadIdx.x, lane = lane_id(), maxv = (1 << bitdepth) - 1;
+  auto sync = [&]() { if (TW == 1) __syncwarp(); else __syncthreads(); };
+  const S *orig = (const S *)q.orig, *pred = (const S *)q.pred;
+  S *rec = (S *)q.rec;
+  const int size = q.size;
+  int size1 = size, scale = 1;
+  if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
+  const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
+  const int8_t *M1 = tab8 + dct_tab8_ofs(l1);
+  const int mp1 = dct_tab8_pitch(l1);
+  // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform (common/transform.c:261-278:
+  // the sum saturates after every addition, rows outer / columns inner)
+  if (scale == 1) {
+    for (int p = tid; p < (size1 * size1) >> 2; p += NT) {  // four samples per thread and step
+      int i = p >> (l1 - 2), j = (p & ((size1 >> 2) - 1)) << 2;
+      int a[4], b[4];
+      load_row4<S>(orig + i * q.ostride + j, a);
+      load_row4<S>(pred + i * q.pstride + j, b);
+#pragma unroll
+      for (int t = 0; t < 4; t++) sc.in[i * PI + j + t] = (int16_t)(a[t] - b[t]);
+    }
+  } else if (scale == 4) {
+    for (int p = tid; p < size1 * size1; p += NT) {
+      int i = p >> l1, j = p & (size1 - 1), sum = 0;
+      for (int m = 0; m < 4; m++) {
+        int a[4], b[4];
+        load_row4<S>(orig + (i * 4 + m) * q.ostride + j * 4, a);
+        load_row4<S>(pred + (i * 4 + m) * q.pstride + j * 4, b);
+#pragma unroll
+        for (int t = 0; t < 4; t++) sum = iclip(sum + (a[t] - b[t]), -16384, 16383);
+      }
+      sc.in[i * PI + j] = (int16_t)sum;
+    }
+  } else if (scale == 2) {
+    for (int p = tid; p < (size1 * size1) >> 1; p += NT) {  // two outputs (four source columns) per thread and step
+      int i = p >> (l1 - 1), j = (p & ((size1 >> 1) - 1)) << 1, s0 = 0, s1 = 0;
+      for (int m = 0; m < 2; m++) {
+        int a[4], b[4];
+        load_row4<S>(orig + (i * 2 + m) * q.ostride + j * 2, a);
+        load_row4<S>(pred + (i * 2 + m) * q.pstride + j * 2, b);
+        s0 = iclip(s0 + (a[0] - b[0]), -16384, 16383); s0 = iclip(s0 + (a[1] - b[1]), -16384, 16383);
+        s1 = iclip(s1 + (a[2] - b[2]), -16384, 16383); s1 = iclip(s1 + (a[3] - b[3]), -16384, 16383);
+      }
+      sc.in[i * PI + j] = (int16_t)s0;
+      sc.in[i * PI + j + 1] = (int16_t)s1;
+    }
+  } else {
+    for (int p = tid; p < size1 * size1; p += NT) {
+      int i = p >> l1, j = p & (size1 - 1), sum = 0;
+      for (int m = 0; m < scale; m++)
+        for (int nn = 0; nn < scale; nn++) {
+          int y = i * scale + m, x = j * scale + nn;
+          sum = iclip(sum + ((int)orig[y * q.ostride + x] - (int)pred[y * q.pstride + x]), -16384, 16383);
+        }
+      sc.in[i * PI + j] = (int16_t)sum;
+    }
+  }
+  sync();
+  {
+    const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
+    const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
+    // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < qsize, j < size1)
+    for (int p = tid; p < qsize * size1; p += NT) {
+      int i = p >> l1, j = p & (size1 - 1);
+      int sum = dot_s8_s16(M1 + i * mp1, sc.in + j * PI, size1);
+      sc.tmp[i * PI + j] = (int16_t)((sum + add1) >> shift1);
+    }
+    sync();
+    // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < qsize)
+    for (int p = tid; p < qsize * qsize; p += NT) {
+      int i = p >> lq, j = p & (qsize - 1);
+      int sum = dot_s8_s16(M1 + i * mp1, sc.tmp + j * PI, size1);
+      sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
+    }
+    sync();
+  }
+  int cbp;
+  if (TW == 1) cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
+  else {
+    if (threadIdx.x < 32) {
+      int c = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
+      if (lane == 0) *bc = c;
+    }
+    __syncthreads();
+    cbp = *bc;
+  }
+  if (q.coeffq)
+    for (int p = tid; p < qsize * qsize; p += NT) q.coeffq[p] = sc.cq[p];
+  uint64_t ssd = 0;
+  if (cbp) {
+    // de-quantise (common/common_block.c:45-73) straight into the TRANSPOSED tile in[i][k] = rcoeff[k][i], so that the
+    // inverse transform's sums over k read contiguous int16 pairs
+    {
+      const int lshift = q.qp / 6, rshift = ilog2(size) - 1;
+      const int64_t dscale = c_dequant[q.qp % 6];
+      const int64_t dadd = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
+      for (int p = tid; p < qsize * qsize; p += NT) {
+        int k = p >> lq, i = p & (qsize - 1), c = sc.cq[p];
+        sc.in[i * PI + k] = lshift >= rshift ? (int16_t)((c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + dadd) >> (rshift - lshift));
+      }
+      sync();
+    }
+    // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
+    const int core = min(size, 32), rep = size / core, lc = ilog2(core);
+    const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
+    const int8_t *Mt = tab8t + dct_tab8_ofs(lc);
+    const int mpc = dct_tab8_pitch(lc);
+    // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < qsize, j < core)
+    int16_t *tmp2 = sc.in + 16 * PI;  // rows 16.. of the `in` tile are free here (rcoeff^T uses rows 0..15)
+    for (int p = tid; p < qsize * core; p += NT) {
+      int i = p >> lc, j = p & (core - 1);
+      int sum = dot_s8_s16(Mt + j * mpc, sc.in + i * PI, qsize);
+      tmp2[j * PI + i] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+    }
+    sync();
+    // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core)
+    if (rep == 1) {
+      for (int p = tid; p < (core * core) >> 2; p += NT) {  // four samples per thread and step: word loads/stores
+        int i = p >> (lc - 2), j = (p & ((core >> 2) - 1)) << 2;
+        int pv[4], ov[4], v[4];
+        load_row4<S>(pred + i * q.pstride + j, pv);
+        load_row4<S>(orig + i * q.ostride + j, ov);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          int sum = dot_s8_s16(Mt + (j + t) * mpc, tmp2 + i * PI, qsize);
+          int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+          v[t] = sat_px(r + pv[t], maxv);
+          int d = ov[t] - v[t];
+          ssd += (uint64_t)(uint32_t)(d * d);
+        }
+        if (rec) store_row4<S>(rec + i * q.rstride + j, v);
+      }
+    } else if (TW > 1 && (rep == 2 || rep == 4)) {
+      // the core x core residual goes to a second tile, then one per-sample pass replicates it (common/transform.c:481-492)
+      for (int p = tid; p < core * core; p += NT) {
+        int i = p >> lc, j = p & (core - 1);
+        int sum = dot_s8_s16(Mt + j * mpc, tmp2 + i * PI, qsize);
+        rt[i * PI + j] = (int16_t)iclip((sum + addB) >> shiftB, -32768, 32767);
+      }
+      __syncthreads();
+      const int ls = ilog2(size), lr = ilog2(rep);
+      for (int p = tid; p < (size * size) >> 2; p += NT) {
+        int y = p >> (ls - 2), x = (p & ((size >> 2) - 1)) << 2;
+        int pv[4], ov[4], v[4];
+        load_row4<S>(pred + y * q.pstride + x, pv);
+        load_row4<S>(orig + y * q.ostride + x, ov);
+        const int16_t *rr = rt + (y >> lr) * PI;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          v[t] = sat_px((int)rr[(x + t) >> lr] + pv[t], maxv);
+          int d = ov[t] - v[t];
+          ssd += (uint64_t)(uint32_t)(d * d);
+        }
+        if (rec) store_row4<S>(rec + y * q.rstride + x, v);
+      }
+    } else {
+      for (int p = tid; p < core * core; p += NT) {
+        int i = p >> lc, j = p & (core - 1);
+        int sum = dot_s8_s16(Mt + j * mpc, tmp2 + i * PI, qsize);
+        int r = iclip((sum + addB) >> shiftB, -32768, 32767);
+        for (int m = 0; m < rep; m++)
+          for (int nn = 0; nn < rep; nn++) {
+            int y = i * rep + m, x = j * rep + nn;
+            int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
+            if (rec) rec[y * q.rstride + x] = (S)v;
+            int d = (int)orig[y * q.ostride + x] - v;
+            ssd += (uint64_t)(uint32_t)(d * d);
+          }
+      }
+    }
+  } else {
+    // cbp == 0: the reference copies the prediction (enc/encode_block.c:1145-1166 "memcpy pred -> rec")
+    const int ls = ilog2(size);
+    for (int p = tid; p < (size * size) >> 2; p += NT) {
+      int y = p >> (ls - 2), x = (p & ((size >> 2) - 1)) << 2;
+      int pv[4], ov[4];
+      load_row4<S>(pred + y * q.pstride + x, pv);
+      load_row4<S>(orig + y * q.ostride + x, ov);
+      if (rec) store_row4<S>(rec + y * q.rstride + x, pv);
+#pragma unroll
+      for (int t = 0; t < 4; t++) { int d = ov[t] - pv[t]; ssd += (uint64_t)(uint32_t)(d * d); }
+    }
+  }
+  ssd = warp_sum64(ssd);
+  if (TW > 1) {
+    if (lane == 0) red[threadIdx.x >> 5] = ssd;
+    __syncthreads();
+    ssd = 0;
+#pragma unroll
+    for (int k = 0; k < TW; k++) ssd += red[k];
+  }
+  if (tid == 0) { res->ssd = ssd; res->cbp = cbp; res->pad = 0; }
+  sync();
+}
+
+// Scheduling as for the motion search (me_batch_kernel): blocks > 8x8 are listed largest first by the counting sort; the
+// persistent kernel (1) works through the 64x64 / 128x128 blocks as a CTA team, (2) gives the 16x16 / 32x32 blocks one warp
+// each, (3) draws groups of 32 consecutive items from the caller's array and runs their 4x4 and 8x8 blocks one per LANE
+// (thread_txfm4 in registers, thread_txfm8 in per-thread local arrays; consecutive items are spatial neighbours, so the
+// lanes' loads and stores coalesce).
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txfm_item_t *items, int n, int bitdepth, tb_txfm_result_t *out) {
+__global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txfm_item_t *items, int n, const int *idx, int *meta, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long red[WARPS_PER_CTA];
+  __shared__ int bc, s_next;
   int8_t *tab8 = (int8_t *)smem_raw, *tab8t = tab8 + DCT_TAB8_SIZE;
-  TxScratch &sc = ((TxScratch *)(smem_raw + ((DCT_TAB8_SIZE * 2 + 15) & ~15)))[threadIdx.x >> 5];
+  TxScratch *scs = (TxScratch *)(smem_raw + ((DCT_TAB8_SIZE * 2 + 15) & ~15));
   dct_tab8_fill(tab8, tab8t);
   __syncthreads();
-  const int lane = lane_id(), maxv = (1 << bitdepth) - 1;
-  constexpr int PI = 34;  // int16 pitch of the scratch tiles: even (4-byte aligned pairs for DP2A), 17 words -> odd word pitch
-  for (int base = global_warp() * 32; base < n; base += total_warps() * 32) {
-    const int mine = base + lane;
+  const int lane = lane_id();
+  const int nteam = meta[96], nlisted = meta[99];
+  for (;;) {  // (1)
+    if (threadIdx.x == 0) s_next = atomicAdd(&meta[97], 1);
+    __syncthreads();
+    const int k = s_next;
+    __syncthreads();
+    if (k >= nteam) break;
+    const int it = idx[k];
+    tx_big_chain<S, WARPS_PER_CTA>(items[it], bitdepth, scs[0], scs[1].in, tab8, tab8t, red, &bc, out + it);
+  }
+  TxScratch &sc = scs[threadIdx.x >> 5];
+  for (;;) {  // (2)
+    int k = 0;
+    if (lane == 0) k = atomicAdd(&meta[98], 1);
+    k = nteam + __shfl_sync(FULL, k, 0);
+    if (k >= nlisted) break;
+    const int it = idx[k];
+    tx_big_chain<S, 1>(items[it], bitdepth, sc, nullptr, tab8, tab8t, nullptr, nullptr, out + it);
+  }
+  const int ngroups = (n + 31) >> 5;
+  for (;;) {  // (3)
+    int gidx = 0;
+    if (lane == 0) gidx = atomicAdd(&meta[100], 1);
+    gidx = __shfl_sync(FULL, gidx, 0);
+    if (gidx >= ngroups) break;
+    const int mine = gidx * 32 + lane;
     int my_size = 0;
     if (mine < n) my_size = items[mine].size;
     if (my_size == 4) {
@@ -247,137 +488,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
       int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, ssd);
       out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
     }
-    unsigned big = __ballot_sync(FULL, my_size > 8);
-    while (big) {
-      const int it = base + __ffs(big) - 1;
-      big &= big - 1;
-      tb_txfm_item_t q = items[it];
-      const S *orig = (const S *)q.orig, *pred = (const S *)q.pred;
-      S *rec = (S *)q.rec;
-      const int size = q.size;
-      int size1 = size, scale = 1;
-      if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
-      const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
-      const int8_t *M1 = tab8 + dct_tab8_ofs(l1);
-      const int mp1 = dct_tab8_pitch(l1);
-      // residual (enc/encode_block.c:162-171) fused with the box-sum load of the forward transform
-      if (scale == 1) {
-        for (int p = lane; p < (size1 * size1) >> 2; p += 32) {  // four samples per lane and step
-          int i = p >> (l1 - 2), j = (p & ((size1 >> 2) - 1)) << 2;
-          int a[4], b[4];
-          load_row4<S>(orig + i * q.ostride + j, a);
-          load_row4<S>(pred + i * q.pstride + j, b);
-#pragma unroll
-          for (int t = 0; t < 4; t++) sc.in[i * PI + j + t] = (int16_t)(a[t] - b[t]);
-        }
-      } else {
-        for (int p = lane; p < size1 * size1; p += 32) {
-          int i = p >> l1, j = p & (size1 - 1), sum = 0;
-          for (int m = 0; m < scale; m++)
-            for (int nn = 0; nn < scale; nn++) {
-              int y = i * scale + m, x = j * scale + nn;
-              sum = iclip(sum + ((int)orig[y * q.ostride + x] - (int)pred[y * q.pstride + x]), -16384, 16383);
-            }
-          sc.in[i * PI + j] = (int16_t)sum;
-        }
-      }
-      __syncwarp();
-      {
-        const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
-        const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
-        // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < qsize, j < size1)
-        for (int p = lane; p < qsize * size1; p += 32) {
-          int i = p >> l1, j = p & (size1 - 1);
-          int sum = dot_s8_s16(M1 + i * mp1, sc.in + j * PI, size1);
-          sc.tmp[i * PI + j] = (int16_t)((sum + add1) >> shift1);
-        }
-        __syncwarp();
-        // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < qsize)
-        for (int p = lane; p < qsize * qsize; p += 32) {
-          int i = p >> lq, j = p & (qsize - 1);
-          int sum = dot_s8_s16(M1 + i * mp1, sc.tmp + j * PI, size1);
-          sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
-        }
-        __syncwarp();
-      }
-      int cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
-      if (q.coeffq)
-        for (int p = lane; p < qsize * qsize; p += 32) q.coeffq[p] = sc.cq[p];
-      uint64_t ssd = 0;
-      if (cbp) {
-        // de-quantise (common/common_block.c:45-73) straight into the TRANSPOSED tile in[i][k] = rcoeff[k][i], so that the
-        // inverse transform's sums over k read contiguous int16 pairs
-        {
-          const int lshift = q.qp / 6, rshift = ilog2(size) - 1;
-          const int64_t dscale = c_dequant[q.qp % 6];
-          const int64_t dadd = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
-          for (int p = lane; p < qsize * qsize; p += 32) {
-            int k = p >> lq, i = p & (qsize - 1), c = sc.cq[p];
-            sc.in[i * PI + k] = lshift >= rshift ? (int16_t)((c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + dadd) >> (rshift - lshift));
-          }
-          __syncwarp();
-        }
-        // inverse transform with the reconstruction (common/common_block.c:75-83) and SSD fused into its output stage
-        const int core = min(size, 32), rep = size / core, lc = ilog2(core);
-        const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
-        const int8_t *Mt = tab8t + dct_tab8_ofs(lc);
-        const int mpc = dct_tab8_pitch(lc);
-        // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < qsize, j < core)
-        int16_t *tmp2 = sc.in + 16 * PI;  // rows 16.. of the `in` tile are free here (rcoeff^T uses rows 0..15)
-        for (int p = lane; p < qsize * core; p += 32) {
-          int i = p >> lc, j = p & (core - 1);
-          int sum = dot_s8_s16(Mt + j * mpc, sc.in + i * PI, qsize);
-          tmp2[j * PI + i] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
-        }
-        __syncwarp();
-        // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core)
-        if (rep == 1) {
-          for (int p = lane; p < (core * core) >> 2; p += 32) {  // four samples per lane and step: word loads/stores
-            int i = p >> (lc - 2), j = (p & ((core >> 2) - 1)) << 2;
-            int pv[4], ov[4], v[4];
-            load_row4<S>(pred + i * q.pstride + j, pv);
-            load_row4<S>(orig + i * q.ostride + j, ov);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-              int sum = dot_s8_s16(Mt + (j + t) * mpc, tmp2 + i * PI, qsize);
-              int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-              v[t] = sat_px(r + pv[t], maxv);
-              int d = ov[t] - v[t];
-              ssd += (uint64_t)(uint32_t)(d * d);
-            }
-            if (rec) store_row4<S>(rec + i * q.rstride + j, v);
-          }
-        } else {
-          for (int p = lane; p < core * core; p += 32) {
-            int i = p >> lc, j = p & (core - 1);
-            int sum = dot_s8_s16(Mt + j * mpc, tmp2 + i * PI, qsize);
-            int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-            for (int m = 0; m < rep; m++)
-              for (int nn = 0; nn < rep; nn++) {
-                int y = i * rep + m, x = j * rep + nn;
-                int v = sat_px(r + (int)(int16_t)pred[y * q.pstride + x], maxv);
-                if (rec) rec[y * q.rstride + x] = (S)v;
-                int d = (int)orig[y * q.ostride + x] - v;
-                ssd += (uint64_t)(uint32_t)(d * d);
-              }
-          }
-        }
-        __syncwarp();
-      } else {
-        // cbp == 0: the reference copies the prediction (enc/encode_block.c:1145-1166 "memcpy pred -> rec")
-        const int ls = ilog2(size);
-        for (int p = lane; p < size * size; p += 32) {
-          int y = p >> ls, x = p & (size - 1);
-          int v = pred[y * q.pstride + x];
-          if (rec) rec[y * q.rstride + x] = (S)v;
-          int d = (int)orig[y * q.ostride + x] - v;
-          ssd += (uint64_t)(uint32_t)(d * d);
-        }
-      }
-      ssd = warp_sum64(ssd);
-      if (lane == 0) { out[it].ssd = ssd; out[it].cbp = cbp; out[it].pad = 0; }
-      __syncwarp();
-    }
+    __syncwarp();
   }
 }
 
