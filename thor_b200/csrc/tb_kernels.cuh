@@ -115,12 +115,12 @@ template <class Item, class F> __global__ void sched_scatter_kernel(const Item *
 
 template <class S, int TW>
 __device__ __noinline__ void me_run_item(const tb_me_item_t *items, int it, const int16_t *cand, int bitdepth, int speed, int bip, int fw, int fh, tb_me_result_t *out,
-                                            unsigned long long *stats, MeTeam<TW> &tm) {
+                                            unsigned long long *stats, MeTeam<TW> &tm, SubpelShared *sps) {
   tb_me_item_t q = items[it];
   MeCtx c;
   c.size = q.size; c.width = q.width; c.height = q.height; c.sign = q.sign; c.s = q.sign ? -1 : 1;
   c.xpos = q.xpos; c.ypos = q.ypos; c.fw = fw; c.fh = fh; c.bitdepth = bitdepth; c.speed = speed; c.bip = bip;
-  c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda; c.n_int = 0; c.n_sub = 0;
+  c.mvpx = q.mvp_x; c.mvpy = q.mvp_y; c.lambda = q.lambda; c.n_int = 0; c.n_sub = 0; c.sps = sps;
   int mx, my;
   uint32_t cost;
   warp_motion_estimate<S, TW>((const S *)q.orig, q.ostride, (const S *)q.ref, q.rstride, c, q.mvc_x, q.mvc_y, cand + 2 * (size_t)q.cand_ofs, q.ncand, mx, my, cost, tm);
@@ -141,6 +141,12 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
                                                                                  int speed, int bip, int fw, int fh, tb_me_result_t *out, unsigned long long *stats) {
   __shared__ uint32_t xch[2 * ME_TEAM_WARPS * 32];
   __shared__ int s_next;
+#if TB_SUBPEL_SHARED
+  __shared__ SubpelShared sps_all[WARPS_PER_CTA];
+  SubpelShared *sps = &sps_all[threadIdx.x >> 5];
+#else
+  SubpelShared *sps = nullptr;
+#endif
   const int nteam = meta[96];
   // phase 1: the CTA as a team on the large blocks
   {
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
       const int k = s_next;
       __syncthreads();
       if (k >= nteam) break;
-      me_run_item<S, ME_TEAM_WARPS>(items, idx[k], cand, bitdepth, speed, bip, fw, fh, out, stats, tm);
+      me_run_item<S, ME_TEAM_WARPS>(items, idx[k], cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
     }
   }
   // phase 2: one warp per search, drawn four at a time from the caller's array (neighbouring items share samples: keep them on
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
       if (k >= n) break;
       for (int it = k; it < min(k + TB_ME_DRAW, n); it++) {
         if (nteam && me_class(items[it].width, items[it].height, speed) >= 16) continue;
-        me_run_item<S, 1>(items, it, cand, bitdepth, speed, bip, fw, fh, out, stats, tm);
+        me_run_item<S, 1>(items, it, cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
       }
     }
   }
