@@ -107,9 +107,17 @@ __global__ void sched_scan_kernel(int *meta) {
   if (b == 0) { meta[96] = team; meta[97] = 0; meta[98] = 0; meta[99] = all; meta[100] = 0; }
 }
 template <class Item, class F> __global__ void sched_scatter_kernel(const Item *items, int n, F f, int *meta, int *idx) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = f(items[i]);
-    if (c >= 0) idx[meta[32 + c] + atomicAdd(&meta[64 + c], 1)] = i;
+  // warp-aggregated: the lanes of a warp that hold the same class reserve their list positions with ONE atomic
+  const int nround = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (int k = 0; k < nround; k++) {
+    const int i = (k * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int c = i < n ? f(items[i]) : -1;
+    const unsigned peers = __match_any_sync(FULL, c);
+    int base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (c >= 0 && lane_id() == leader) base = atomicAdd(&meta[64 + c], __popc(peers));
+    base = __shfl_sync(FULL, base, leader);
+    if (c >= 0) idx[meta[32 + c] + base + __popc(peers & ((1u << lane_id()) - 1))] = i;
   }
 }
 
