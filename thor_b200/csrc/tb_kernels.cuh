@@ -251,7 +251,7 @@ struct alignas(16) TxShared {
 template <class S, int TW>
 __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth, TxScratch &sc, int16_t *rt, const int8_t *tab8, const int8_t *tab8t, unsigned long long *red,
                                           int *bc, tb_txfm_result_t *res) {
-  constexpr int PI = 34;  // int16 pitch of the scratch tiles: even (4-byte aligned pairs for DP2A), 17 words -> odd word pitch
+  constexpr int PI = 40;  // int16 pitch of the scratch tiles: 80-byte rows (16-byte aligned; eight consecutive rows cover all 32 banks with 128-bit loads)
   constexpr int NT = 32 * TW;
   const int tid = TW == 1 ? lane_id() : (int)threadIdx.x, lane = lane_id(), maxv = (1 << bitdepth) - 1;
   auto sync = [&]() { if (TW == 1) __syncwarp(); else __syncthreads(); };
@@ -271,8 +271,7 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
       int a[4], b[4];
       load_row4<S>(orig + i * q.ostride + j, a);
       load_row4<S>(pred + i * q.pstride + j, b);
-#pragma unroll
-      for (int t = 0; t < 4; t++) sc.in[i * PI + j + t] = (int16_t)(a[t] - b[t]);
+      *(uint2 *)&sc.in[i * PI + j] = make_uint2(((uint32_t)(a[0] - b[0]) & 0xffffu) | ((uint32_t)(a[1] - b[1]) << 16), ((uint32_t)(a[2] - b[2]) & 0xffffu) | ((uint32_t)(a[3] - b[3]) << 16));
     }
   } else if (scale == 4) {
     for (int p = tid; p < size1 * size1; p += NT) {
@@ -311,21 +310,43 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
     }
   }
   sync();
+  // The transform phases run on one warp (the first warp of a team: they are a small part of a 64x64/128x128 chain).  Lane
+  // (ia = lane >> 3, jb = lane & 7) owns the outputs {4 ia .. 4 ia + 3} x {jb, jb + 8, ..}: the matrix rows are uniform per
+  // quarter-warp (broadcast) and the vectors of a quarter-warp are eight consecutive 80-byte rows (conflict-free).
+  const bool dct_warp = TW == 1 || threadIdx.x < 32;
+  const int ia = lane >> 3, jb = lane & 7;
   {
     const int shift1 = ilog2(size) + ilog2(scale) + bitdepth - 8, add1 = 1 << (shift1 - 1);
     const int shift2 = l1 + 5, add2 = 1 << (shift2 - 1);
-    // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < qsize, j < size1)
-    for (int p = tid; p < qsize * size1; p += NT) {
-      int i = p >> l1, j = p & (size1 - 1);
-      int sum = dot_s8_s16(M1 + i * mp1, sc.in + j * PI, size1);
-      sc.tmp[i * PI + j] = (int16_t)((sum + add1) >> shift1);
+    // tmp[i][j] = (M[i][.] . in[j][.] + add1) >> shift1   (i < 16, j < size1)
+    if (dct_warp) {
+      if (size1 == 16) {
+        int acc[4][2] = {};
+        dot16_block<4, 2>(M1 + 4 * ia * mp1, mp1, sc.in + jb * PI, 8 * PI, acc);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) sc.tmp[(4 * ia + r) * PI + jb + 8 * c] = (int16_t)((acc[r][c] + add1) >> shift1);
+      } else {
+        int acc[4][4] = {};
+        dot16_block<4, 4>(M1 + 4 * ia * mp1, mp1, sc.in + jb * PI, 8 * PI, acc);
+        dot16_block<4, 4>(M1 + 4 * ia * mp1 + 16, mp1, sc.in + jb * PI + 16, 8 * PI, acc);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int c = 0; c < 4; c++) sc.tmp[(4 * ia + r) * PI + jb + 8 * c] = (int16_t)((acc[r][c] + add1) >> shift1);
+      }
     }
     sync();
-    // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < qsize)
-    for (int p = tid; p < qsize * qsize; p += NT) {
-      int i = p >> lq, j = p & (qsize - 1);
-      int sum = dot_s8_s16(M1 + i * mp1, sc.tmp + j * PI, size1);
-      sc.rc[i * qsize + j] = (int16_t)((sum + add2) >> shift2);
+    // coef[i][j] = (M[i][.] . tmp[j][.] + add2) >> shift2  (i, j < 16)
+    if (dct_warp) {
+      int acc[4][2] = {};
+      dot16_block<4, 2>(M1 + 4 * ia * mp1, mp1, sc.tmp + jb * PI, 8 * PI, acc);
+      if (size1 == 32) dot16_block<4, 2>(M1 + 4 * ia * mp1 + 16, mp1, sc.tmp + jb * PI + 16, 8 * PI, acc);
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) sc.rc[(4 * ia + r) * 16 + jb + 8 * c] = (int16_t)((acc[r][c] + add2) >> shift2);
     }
     sync();
   }
@@ -360,37 +381,68 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
     const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
     const int8_t *Mt = tab8t + dct_tab8_ofs(lc);
     const int mpc = dct_tab8_pitch(lc);
-    // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < qsize, j < core)
+    // T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: tmp2[j][i]   (i < 16, j < core)
     int16_t *tmp2 = sc.in + 16 * PI;  // rows 16.. of the `in` tile are free here (rcoeff^T uses rows 0..15)
-    for (int p = tid; p < qsize * core; p += NT) {
-      int i = p >> lc, j = p & (core - 1);
-      int sum = dot_s8_s16(Mt + j * mpc, sc.in + i * PI, qsize);
-      tmp2[j * PI + i] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+    if (dct_warp) {
+      if (core == 16) {
+        int acc[4][2] = {};
+        dot16_block<4, 2>(Mt + 4 * ia * mpc, mpc, sc.in + jb * PI, 8 * PI, acc);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+          for (int c = 0; c < 2; c++) tmp2[(4 * ia + r) * PI + jb + 8 * c] = (int16_t)iclip((acc[r][c] + 64) >> 7, -32768, 32767);
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          int acc[4][2] = {};
+          dot16_block<4, 2>(Mt + (16 * half + 4 * ia) * mpc, mpc, sc.in + jb * PI, 8 * PI, acc);
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) tmp2[(16 * half + 4 * ia + r) * PI + jb + 8 * c] = (int16_t)iclip((acc[r][c] + 64) >> 7, -32768, 32767);
+        }
+      }
     }
     sync();
-    // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core)
+    // out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j][.] . tmp2[i][.]   (i, j < core); lane (jg = lane >> 3,
+    // il = lane & 7) owns columns 4 jg .. 4 jg + 3 (+16 in a second pass for core 32) of rows il, il + 8, ..
     if (rep == 1) {
-      for (int p = tid; p < (core * core) >> 2; p += NT) {  // four samples per thread and step: word loads/stores
-        int i = p >> (lc - 2), j = (p & ((core >> 2) - 1)) << 2;
-        int pv[4], ov[4], v[4];
-        load_row4<S>(pred + i * q.pstride + j, pv);
-        load_row4<S>(orig + i * q.ostride + j, ov);
+      if (dct_warp) {
+        for (int jg = ia; jg < (core >> 2); jg += 4) {
+          for (int i0 = jb; i0 < core; i0 += 16) {
+            int acc[4][2] = {};
+            dot16_block<4, 2>(Mt + 4 * jg * mpc, mpc, tmp2 + i0 * PI, 8 * PI, acc);
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-          int sum = dot_s8_s16(Mt + (j + t) * mpc, tmp2 + i * PI, qsize);
-          int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-          v[t] = sat_px(r + pv[t], maxv);
-          int d = ov[t] - v[t];
-          ssd += (uint64_t)(uint32_t)(d * d);
+            for (int c = 0; c < 2; c++) {
+              const int i = i0 + 8 * c, j = 4 * jg;
+              int pv[4], ov[4], v[4];
+              load_row4<S>(pred + i * q.pstride + j, pv);
+              load_row4<S>(orig + i * q.ostride + j, ov);
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                int r = iclip((acc[t][c] + addB) >> shiftB, -32768, 32767);
+                v[t] = sat_px(r + pv[t], maxv);
+                int d = ov[t] - v[t];
+                ssd += (uint64_t)(uint32_t)(d * d);
+              }
+              if (rec) store_row4<S>(rec + i * q.rstride + j, v);
+            }
+          }
         }
-        if (rec) store_row4<S>(rec + i * q.rstride + j, v);
       }
     } else if (TW > 1 && (rep == 2 || rep == 4)) {
       // the core x core residual goes to a second tile, then one per-sample pass replicates it (common/transform.c:481-492)
-      for (int p = tid; p < core * core; p += NT) {
-        int i = p >> lc, j = p & (core - 1);
-        int sum = dot_s8_s16(Mt + j * mpc, tmp2 + i * PI, qsize);
-        rt[i * PI + j] = (int16_t)iclip((sum + addB) >> shiftB, -32768, 32767);
+      if (dct_warp) {
+        for (int jg = ia; jg < (core >> 2); jg += 4) {
+          for (int i0 = jb; i0 < core; i0 += 16) {
+            int acc[4][2] = {};
+            dot16_block<4, 2>(Mt + 4 * jg * mpc, mpc, tmp2 + i0 * PI, 8 * PI, acc);
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+              for (int t = 0; t < 4; t++) rt[(i0 + 8 * c) * PI + 4 * jg + t] = (int16_t)iclip((acc[t][c] + addB) >> shiftB, -32768, 32767);
+          }
+        }
       }
       __syncthreads();
       const int ls = ilog2(size), lr = ilog2(rep);
