@@ -15,6 +15,9 @@
 #ifndef TB_EXP_NOSUBPEL
 #define TB_EXP_NOSUBPEL 0  // 1: skip the sub-pel SADs (timing experiment only: measures the integer stages alone)
 #endif
+#ifndef TB_HALFPEL_PLANES
+#define TB_HALFPEL_PLANES 1  // half-pel stage from three shared planes (halfpel_stage_sads_u8)
+#endif
 #ifndef TB_SUBPEL_SHARED
 // 1: sub-pel stages through subpel_stage_sads_shared (horizontally filtered rows shared between the eight probes via shared
 // memory).  Bit-exact, but measured SLOWER on B200 (sub-pel share of the 1080p batch 9.4 ms vs 6.8 ms): per 16x16 tile it
@@ -630,6 +633,127 @@ __device__ __noinline__ uint32_t subpel_stage_sads_shared(const uint8_t *o, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The half-pel stage (enc/encode_block.c:625-645) for 8-bit samples when the centre is an integer position: its eight
+// probes read only THREE interpolated planes — the horizontal half-pel plane (probes (0,-2), (0,+2) in (dy,dx)), the vertical
+// one ((-2,0), (+2,0)) and the 12-tap centre-kernel plane (the four diagonals) — each shifted by 0 or 1 sample.  So every plane
+// sample is computed once and compared with the original at its two (four) shifts, instead of interpolating eight blocks:
+// three flat passes over (plane row, 4-sample strip) units, one unit per lane and step, no state carried between units.
+//   H pass: five outputs of the 6-tap row filter (two DP4A each), rounded (H + 32) >> 6 (= (64 H + 2048) >> 12), two SADs;
+//   V pass: the six row words of a strip are byte-transposed with PRMT so that the column filter is two DP4A per sample;
+//   C pass: H1 = [0 0 1 1 0 0] on rows r-1, r+2 and H2 = [0 1 2 2 1 0] on rows r, r+1 accumulate in one DP4A chain, four SADs.
+// Lane t < 8 returns the SAD of probe t + 1; 0xffffffff = geometry not of this form (clamped vectors): use the per-probe path.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row12_u8(const uint8_t *p, uint32_t &b0, uint32_t &b1, uint32_t &b2) {  // bytes p[0..11]
+  const uintptr_t a = (uintptr_t)p;
+  const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
+}
+__device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os, const uint8_t *ref, int rs, int w, int hfull, int bx, int by, const int8_t *dxs,
+                                                       const int8_t *dys, int sign, int bip, int pic_w, int pic_h, int xpos, int ypos, int row0, int h) {
+  const int lane = lane_id(), t = lane & 7;
+  const int mvx = (int)(int16_t)(bx + dxs[t + 1]), mvy = (int)(int16_t)(by + dys[t + 1]);
+  int hi, vi, xf, yf;
+  split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, hfull, hi, vi, xf, yf);
+  const int hmin = __reduce_min_sync(FULL, hi), vmin = __reduce_min_sync(FULL, vi);
+  const int ho = hi - hmin, vo = vi - vmin;
+  const int cls = (xf == 2 && yf == 0) ? 0 : ((xf == 0 && yf == 2) ? 1 : ((xf == 2 && yf == 2) ? 2 : 3));
+  const unsigned mH = __ballot_sync(FULL, cls == 0), mV = __ballot_sync(FULL, cls == 1);
+  const int voH = __shfl_sync(FULL, vo, mH ? __ffs(mH) - 1 : 0), hoV = __shfl_sync(FULL, ho, mV ? __ffs(mV) - 1 : 0);
+  const bool ok = bip < 2 && cls != 3 && ho <= 1 && vo <= 1 && (cls != 0 || vo == voH) && (cls != 1 || ho == hoV);
+  if (!__all_sync(FULL, ok)) return 0xffffffffu;
+  const int8_t *fh = c_luma_taps[bip ? 1 : 0][2];
+  const uint32_t tlo = pack_s8x4(fh[0], fh[1], fh[2], fh[3]), thi = pack_s8x4(fh[4], fh[5], 0, 0);
+  const int ns = w >> 2, lns = ilog2(ns);
+  const uint8_t *rb = ref + (row0 + vmin) * rs + hmin;  // plane sample (r, c) <-> rb[r * rs + c]
+  const uint8_t *ob = o + row0 * os;
+  uint32_t aH0 = 0, aH1 = 0, aV0 = 0, aV1 = 0, aC00 = 0, aC01 = 0, aC10 = 0, aC11 = 0;  // aC<vo><ho>
+  // ---- H pass: block rows y (plane rows y + voH), plane columns 4 s .. 4 s + 4
+  if (mH) {
+    for (int u = lane; u < h * ns; u += 32) {
+      const int y = u >> lns, st = u & (ns - 1);
+      uint32_t b0, b1, b2;
+      row12_u8(rb + (y + voH) * rs + 4 * st - 2, b0, b1, b2);
+      int v[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const uint32_t lo = k < 4 ? __funnelshift_r(b0, b1, 8 * k) : b1, hi4 = k < 4 ? __funnelshift_r(b1, b2, 8 * k) : b2;
+        v[k] = (dp4a_us(lo, tlo, dp4a_us(hi4, thi, 32))) >> 6;
+      }
+      const uint32_t ow = __ldg((const uint32_t *)(ob + y * os + 4 * st));
+      aH0 += __vsadu4(ow, pack_sat_u8x4(v[0], v[1], v[2], v[3]));
+      aH1 += __vsadu4(ow, pack_sat_u8x4(v[1], v[2], v[3], v[4]));
+    }
+  }
+  // ---- V pass: plane rows r = 0 .. h, plane columns 4 s + hoV .. + 3; row r serves block row r (vo 0) and r - 1 (vo 1)
+  if (mV) {
+    for (int u = lane; u < (h + 1) * ns; u += 32) {
+      const int r = u >> lns, st = u & (ns - 1);
+      const uint8_t *p = rb + (r - 2) * rs + 4 * st + hoV;
+      const uintptr_t a = (uintptr_t)p;
+      const uint32_t *wq = (const uint32_t *)(a & ~(uintptr_t)3);
+      const unsigned sh = (unsigned)(a & 3) * 8;
+      const int rsw = rs >> 2;
+      uint32_t W[6];
+#pragma unroll
+      for (int m = 0; m < 6; m++) W[m] = __funnelshift_r(__ldg(wq + m * rsw), __ldg(wq + m * rsw + 1), sh);
+      int v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t sel = (uint32_t)k | ((uint32_t)(4 + k) << 4);
+        const uint32_t t01 = __byte_perm(W[0], W[1], sel), t23 = __byte_perm(W[2], W[3], sel), t45 = __byte_perm(W[4], W[5], sel);
+        v[k] = dp4a_us(__byte_perm(t01, t23, 0x5410), tlo, dp4a_us(t45, thi, 32)) >> 6;  // thi has zero taps on the two upper bytes
+      }
+      const uint32_t pk = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+      if (r < h) aV0 += __vsadu4(__ldg((const uint32_t *)(ob + r * os + 4 * st)), pk);
+      if (r > 0) aV1 += __vsadu4(__ldg((const uint32_t *)(ob + (r - 1) * os + 4 * st)), pk);
+    }
+  }
+  // ---- C pass: plane rows r = 0 .. h, plane columns 4 s .. 4 s + 4
+  {
+    const uint32_t a_lo = 0x01010000u, b_lo = 0x02020100u, b_hi = 0x00000001u;
+    for (int u = lane; u < (h + 1) * ns; u += 32) {
+      const int r = u >> lns, st = u & (ns - 1);
+      const uint8_t *p = rb + r * rs + 4 * st - 2;
+      int acc[5] = {8, 8, 8, 8, 8};
+      uint32_t b0, b1, b2;
+      row12_u8(p - rs, b0, b1, b2);
+#pragma unroll
+      for (int k = 0; k < 5; k++) acc[k] = dp4a_us(k < 4 ? __funnelshift_r(b0, b1, 8 * k) : b1, a_lo, acc[k]);
+      row12_u8(p + 2 * rs, b0, b1, b2);
+#pragma unroll
+      for (int k = 0; k < 5; k++) acc[k] = dp4a_us(k < 4 ? __funnelshift_r(b0, b1, 8 * k) : b1, a_lo, acc[k]);
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        row12_u8(p + rr * rs, b0, b1, b2);
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+          acc[k] = dp4a_us(k < 4 ? __funnelshift_r(b0, b1, 8 * k) : b1, b_lo, dp4a_us(k < 4 ? __funnelshift_r(b1, b2, 8 * k) : b2, b_hi, acc[k]));
+      }
+      // (s + 8) >> 4 <= 255: plain byte packing
+      const uint32_t q0 = (uint32_t)(acc[0] >> 4), q1 = (uint32_t)(acc[1] >> 4), q2 = (uint32_t)(acc[2] >> 4), q3 = (uint32_t)(acc[3] >> 4), q4 = (uint32_t)(acc[4] >> 4);
+      const uint32_t pk0 = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24), pk1 = q1 | (q2 << 8) | (q3 << 16) | (q4 << 24);
+      if (r < h) {
+        const uint32_t ow = __ldg((const uint32_t *)(ob + r * os + 4 * st));
+        aC00 += __vsadu4(ow, pk0);
+        aC01 += __vsadu4(ow, pk1);
+      }
+      if (r > 0) {
+        const uint32_t ow = __ldg((const uint32_t *)(ob + (r - 1) * os + 4 * st));
+        aC10 += __vsadu4(ow, pk0);
+        aC11 += __vsadu4(ow, pk1);
+      }
+    }
+  }
+  aH0 = warp_sum(aH0); aH1 = warp_sum(aH1); aV0 = warp_sum(aV0); aV1 = warp_sum(aV1);
+  aC00 = warp_sum(aC00); aC01 = warp_sum(aC01); aC10 = warp_sum(aC10); aC11 = warp_sum(aC11);
+  if (cls == 0) return ho ? aH1 : aH0;
+  if (cls == 1) return vo ? aV1 : aV0;
+  return vo ? (ho ? aC11 : aC10) : (ho ? aC01 : aC00);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // a4: bilinear sub-pel SAD approximations.  enc/encode_block.c:174-283 and :286-414.
 // up = (a+b+1)>>1, dn = (a+b)>>1.  Results: acc[0..7] in the reference's comparison order.
 // ---------------------------------------------------------------------------------------------------------------
@@ -910,8 +1034,13 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
       const int8_t *dm = stage ? qm : hm, *dn = stage ? qn : hn;
       const int bx = optx, by = opty;
       uint32_t sad = 0xffffffffu;
+#if !TB_EXP_NOSUBPEL && TB_HALFPEL_PLANES
+      if (sizeof(S) == 1 && stage == 0 && !((bx | by) & 3))
+        sad = halfpel_stage_sads_u8((const uint8_t *)orig_full, os, (const uint8_t *)ref_full, rs, c.width, c.height, bx, by, dn, dm, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos,
+                                    row0, band_h);
+#endif
 #if !TB_EXP_NOSUBPEL && TB_SUBPEL_SHARED
-      if (sizeof(S) == 1 && c.sps)
+      if (sad == 0xffffffffu && sizeof(S) == 1 && c.sps)
         sad = subpel_stage_sads_shared((const uint8_t *)orig_full, os, (const uint8_t *)ref_full, rs, c.width, c.height, bx, by, dn, dm, c.sign, c.bip, c.fw, c.fh, c.xpos,
                                        c.ypos, row0, band_h, *c.sps);
 #endif
@@ -1213,24 +1342,26 @@ __device__ __forceinline__ int zigzag_index(int r, int c, int n) {
   return before + k;
 }
 
-__device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc) {
+// T = int when every intermediate fits 32 bits (scale <= 26214, |coef| <= 32768 -> product < 2^30; offsets <= 115 << (shift2 - 8)
+// stay below 2^27 for shift2 <= 28), int64_t otherwise: same values, a third of the multiply instructions.
+template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc, int shift2) {
   const int lane = lane_id();
   const int intra = (coeff_type >> 1) & 1, qsize = min(size, 16), nq = qsize * qsize, lq = ilog2(qsize);
-  const int64_t scale = c_quant[qp % 6];
-  const int shift2 = 21 - ilog2(size) + qp / 6;
-  int *scan = (int *)sc.in;  // reuse: 256 ints of scan-ordered coefficients (sc.in holds 32*33 int16 = 2112 B)
+  const T scale = c_quant[qp % 6];
+  int *scan = (int *)sc.in;  // reuse: 256 ints of scan-ordered coefficients
   for (int p = lane; p < nq; p += 32) scan[zigzag_index(p >> lq, p & (qsize - 1), qsize)] = coef[p];
   __syncwarp();
   // last_pos: highest scan position whose level (with the "last" offset) is non-zero
-  const int64_t off_last = (int64_t)(intra ? 38 : -26) << (shift2 - 8);
+  const T unit = (T)1 << (shift2 - 8);
+  const T off_last = (T)(intra ? 38 : -26) * unit;
   int last = -1;
   for (int p = lane; p < nq; p += 32) {
-    int64_t l64 = (int64_t)iabs(scan[p]) * scale + off_last;
-    int lev = (int)((l64 > 0 ? l64 : -l64) >> shift2);
+    T l = (T)iabs(scan[p]) * scale + off_last;
+    int lev = (int)((l > 0 ? l : -l) >> shift2);
     if (lev) last = p;  // p ascending per lane -> keeps the lane's maximum
   }
   last = (int)__reduce_max_sync(FULL, (unsigned)(last + 1)) - 1;
-  const int off0 = intra ? 102 : 51, off1 = intra ? 115 : 90;
+  const T off0 = (T)(intra ? 102 : 51) * unit, off1 = (T)(intra ? 115 : 90) * unit;
   // chunk = 8 consecutive scan positions per lane (256/32)
   const int per = (nq + 31) / 32, p0 = lane * per;
   unsigned map = 0;  // bit s = end state when the chunk is entered in state s
@@ -1239,10 +1370,9 @@ __device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int si
     for (int t = 0; t < per; t++) {
       int p = p0 + t;
       if (p > last || p >= nq) break;
-      int64_t ac = scale * iabs(scan[p]);
+      T ac = scale * (T)iabs(scan[p]);
       int level0 = (int)(ac >> shift2);
-      int off = ((level0 > (1 - mode)) ? off1 : off0) << (shift2 - 8);
-      int level = (int)((ac + off) >> shift2);
+      int level = (int)((ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2);
       if (mode) { if (level == 0) mode = 0; }
       else if (level > 1) mode = 1;
     }
@@ -1267,10 +1397,9 @@ __device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int si
     int q = 0;
     if (p <= last) {
       int cc = scan[p];
-      int64_t ac = scale * iabs(cc);
+      T ac = scale * (T)iabs(cc);
       int level0 = (int)(ac >> shift2);
-      int off = ((level0 > (1 - mode)) ? off1 : off0) << (shift2 - 8);
-      int level = (int)((ac + off) >> shift2);
+      int level = (int)((ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2);
       q = cc < 0 ? -level : level;
       cbp |= level != 0;
       if (mode) { if (level == 0) mode = 0; }
@@ -1282,6 +1411,10 @@ __device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int si
   for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[zigzag_index(p >> lq, p & (qsize - 1), qsize)];
   __syncwarp();
   return __any_sync(FULL, cbp);
+}
+__device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc) {
+  const int shift2 = 21 - ilog2(size) + qp / 6;
+  return shift2 <= 28 ? warp_quantize_t<int>(coef, coefq, qp, size, coeff_type, sc, shift2) : warp_quantize_t<int64_t>(coef, coefq, qp, size, coeff_type, sc, shift2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

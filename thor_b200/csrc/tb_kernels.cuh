@@ -368,11 +368,11 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
     // inverse transform's sums over k read contiguous int16 pairs
     {
       const int lshift = q.qp / 6, rshift = ilog2(size) - 1;
-      const int64_t dscale = c_dequant[q.qp % 6];
-      const int64_t dadd = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
+      const int dscale = c_dequant[q.qp % 6];  // |c * dscale| <= 32768 * 72 and the shift is <= qp / 6: 32-bit arithmetic is exact
+      const int dadd = lshift < rshift ? (1 << (rshift - lshift - 1)) : 0;
       for (int p = tid; p < qsize * qsize; p += NT) {
         int k = p >> lq, i = p & (qsize - 1), c = sc.cq[p];
-        sc.in[i * PI + k] = lshift >= rshift ? (int16_t)((c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + dadd) >> (rshift - lshift));
+        sc.in[i * PI + k] = lshift >= rshift ? (int16_t)((unsigned)(c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + dadd) >> (rshift - lshift));
       }
       sync();
     }
