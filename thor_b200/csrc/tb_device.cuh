@@ -300,6 +300,7 @@ __device__ __forceinline__ void split_mv(int mvx, int mvy, int sign, int shift, 
   hor_int = max(hor_int, -xpos - w);
 }
 
+__device__ void warp_interp_strips_u8(uint8_t *dst, int ds, const uint8_t *ip, int rs, int w, int h, int xf, int yf, int bip);
 // Whole-warp prediction of one block into dst (common/inter_prediction.c:117-183 / :65-115).
 template <class S>
 __device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int chroma, int bip, int pic_w,
@@ -308,6 +309,11 @@ __device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, 
   split_mv(mvx, mvy, sign, chroma ? 3 : 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
   const S *ip = ref + vi * rs + hi;
   const int maxv = (1 << bitdepth) - 1, lw = ilog2(w);
+  if (sizeof(S) == 1 && !chroma && (xf | yf) && w * h >= 256 && !(h & 7) && !((((uintptr_t)dst) | (unsigned)ds | (unsigned)rs) & 3)) {
+    // large 8-bit luma blocks: separable DP4A strips (same arithmetic as the search's sub-pel SAD), word stores
+    warp_interp_strips_u8((uint8_t *)dst, ds, (const uint8_t *)ip, rs, w, h, xf, yf, bip);
+    return;
+  }
   for (int p = lane_id(); p < (h << lw); p += 32) {
     int row = p >> lw, col = p & (w - 1);
     const S *q = ip + row * rs + col;
@@ -356,7 +362,9 @@ __device__ __forceinline__ void hfilt4_u8(const uint8_t *p, uint32_t tlo, uint32
   }
 }
 // SAD of the rows [y0, y0+nrows) of one 4-wide strip at column x0 of the block; ip = integer-position sample (0,0)
-__device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os, const uint8_t *ip, int rs, int x0, int y0, int nrows, int xf, int yf, int bip) {
+// STORE = false: SAD against the original rows o; STORE = true: the prediction is written to o (a uint8_t *, 4-byte aligned rows)
+template <bool STORE>
+__device__ __forceinline__ uint32_t strip_subpel_u8(const uint8_t *o, int os, const uint8_t *ip, int rs, int x0, int y0, int nrows, int xf, int yf, int bip) {
   uint32_t acc = 0;
   if (xf == 2 && yf == 2 && bip < 2) {
     const uint32_t a_lo = pack_s8x4(0, 0, 1, 1), b_lo = pack_s8x4(0, 1, 2, 2), b_hi = pack_s8x4(1, 0, 0, 0);
@@ -378,7 +386,8 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
         int v = (h1m[k] + h2a[k] + h2b[k] + h1p[k] + 8) >> 4;  // max 12*255+8 -> <= 191: already inside 0..255
         pk |= (uint32_t)v << (8 * k);
       }
-      acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
+      if (STORE) *(uint32_t *)(const_cast<uint8_t *>(o) + y * os + x0) = pk;
+      else acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
 #pragma unroll
       for (int k = 0; k < 4; k++) { h1m[k] = t1[k]; t1[k] = t2[k]; t2[k] = h1p[k]; h2a[k] = h2b[k]; h2b[k] = n2[k]; }
     }
@@ -402,7 +411,8 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
     for (int k = 0; k < 4; k++)
       r4[k] = (v0 * H[0][k] + v1 * H[1][k] + v2 * H[2][k] + v3 * H[3][k] + v4 * H[4][k] + v5 * H[5][k] + 2048) >> 12;
     const uint32_t pk = pack_sat_u8x4(r4[0], r4[1], r4[2], r4[3]);
-    acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
+    if (STORE) *(uint32_t *)(const_cast<uint8_t *>(o) + y * os + x0) = pk;
+    else acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
   }
   return acc;
 }
@@ -430,7 +440,8 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
                     fvr[4] * H[(ph + 4) % 6][k] + fvr[5] * H[(ph + 5) % 6][k];
           pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
         }
-        acc += __vsadu4(__ldg((const uint32_t *)orow), pk);
+        if (STORE) *(uint32_t *)const_cast<uint8_t *>(orow) = pk;
+        else acc += __vsadu4(__ldg((const uint32_t *)orow), pk);
         orow += os;
       }
     }
@@ -438,6 +449,18 @@ __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os
   return acc;
 }
 #endif
+
+__device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os, const uint8_t *ip, int rs, int x0, int y0, int nrows, int xf, int yf, int bip) {
+  return strip_subpel_u8<false>(o, os, ip, rs, x0, y0, nrows, xf, yf, bip);
+}
+// prediction of a w x h luma block (w * h >= 256, h a multiple of 8): (4-column, 8-row) units dealt to the 32 lanes
+__device__ __noinline__ void warp_interp_strips_u8(uint8_t *dst, int ds, const uint8_t *ip, int rs, int w, int h, int xf, int yf, int bip) {
+  const int nseg = h >> 3, units = (w >> 2) * nseg;
+  for (int u = lane_id(); u < units; u += 32) {
+    const int strip = u / nseg, seg = u - strip * nseg;
+    strip_subpel_u8<true>(dst, ds, ip, rs, strip * 4, seg * 8, 8, xf, yf, bip);
+  }
+}
 
 // SADs between the original block and the luma predictions at EIGHT fractional MVs (one half-pel or quarter-pel stage of
 // enc/encode_block.c:625-663) without materialising the predictions: probe t = lane / 4 uses MV (mvx0 + dx[t], mvy0 + dy[t]),
