@@ -187,9 +187,11 @@ typedef struct {
   void *rec;               /* device ptr: reconstruction out (may alias nothing) */
   int16_t *coeffq;         /* device ptr: min(size,16)^2 quantised coefficients out (raster order) */
   int32_t ostride, pstride, rstride;
-  uint8_t size, qp, coeff_type, fast; /* coeff_type: COEFF_TYPE_* (common/global.h:103-106) */
+  uint8_t size, qp, coeff_type, fast; /* coeff_type: COEFF_TYPE_* (common/global.h:103-106); fast: TB_TXFM_* flags */
 } tb_txfm_item_t;
-typedef struct { uint64_t ssd; int32_t cbp; int32_t pad; } tb_txfm_result_t;
+#define TB_TXFM_FAST 1 /* encoder_info->params->encoder_speed > 1: 16-point transform for 32x32 (common/transform.c:252) */
+#define TB_TXFM_BITS 2 /* also count the bits write_coeff() would emit for the block (enc/write_bits.c:145-242), SURVEY 8f.2 */
+typedef struct { uint64_t ssd; int32_t cbp; int32_t bits; } tb_txfm_result_t; /* bits: 0 unless TB_TXFM_BITS and cbp != 0 */
 int tb_txfm_chain_batch(const tb_txfm_item_t *items_dev, int n, int sample_bytes, int bitdepth, tb_txfm_result_t *out_dev);
 
 /* ---- a15/a16: intra prediction from gathered neighbours (common/intra_prediction.c:185-428) and CfL */

@@ -371,3 +371,69 @@ int orc_cdef_select(const uint64_t *mse0, const uint64_t *mse1, int sb_count, in
 #include "thor_oracle_tmpl.h"
 #undef S
 #undef FN
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SURVEY 8f.2 (first part): number of bits write_coeff() emits for one transform block.  enc/write_bits.c:145-242 with the
+ * code lengths of put_vlc(), enc/putvlc.c:73-161 (tables 0/1: Golomb-like with e = 5; 6: cn+1 on table 2 with a 2-bit zero;
+ * 10: Elias-gamma of cn+1).  coeff: min(size,16)^2 quantised coefficients in raster order.  Returns 0 for an all-zero block
+ * (the reference never calls write_coeff for one).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static int orc_log2u(unsigned x) { int n = 0; while (x >>= 1) n++; return n; }
+int orc_vlc_len(int n, unsigned cn) {
+  if (n == 6) {
+    if (!cn) return 2;
+    cn++;
+    n = 2;
+  } else if (n == 10)
+    return 1 + 2 * orc_log2u(cn + 1);
+  if ((int)cn < 5 * (1 << n)) return 1 + n + (int)(cn >> n);
+  return (5 - n) + 1 + 2 * orc_log2u(cn - 5u * (1u << n) + (1u << n));
+}
+int orc_coeff_bits(const int16_t *coeff, int size, int type) {
+  int16_t sc[256];
+  const int qsize = size < 16 ? size : 16, N = qsize * qsize;
+  const int chroma = type & 1, intra = (type >> 1) & 1;
+  int vlc_adaptive = intra && !chroma;
+  const unsigned eob_pos = chroma ? 0 : 2;
+  const int run_tab = chroma && size <= 8 ? 10 : 6;
+  const int *zz = orc_zigzag(qsize);
+  int bits = 0, pos, last_pos, level_mode = 1, level = 1, c = 0;
+  for (int i = 0; i < N; i++) sc[zz[i]] = coeff[i];
+  for (pos = N - 1; !sc[pos] && pos; pos--);
+  if (!pos && !sc[0]) return 0;
+  last_pos = pos;
+  pos = 0;
+  if (chroma) {
+    if (last_pos == 0 && (sc[0] == 1 || sc[0] == -1)) { bits += 2; pos = N; }
+    else bits += 1;
+  }
+  while (pos <= last_pos) {
+    if (level_mode) {
+      while (pos <= last_pos && level > 0) {
+        c = sc[pos++];
+        level = c < 0 ? -c : c;
+        bits += orc_vlc_len(vlc_adaptive, (unsigned)level);
+        if (level > 0) bits += 1;
+        if (!chroma) vlc_adaptive = level > 3;
+      }
+    }
+    int run = 0;
+    c = 0;
+    while (c == 0 && pos <= last_pos) {
+      c = sc[pos++];
+      run += !c;
+      if (c) {
+        unsigned cn;
+        level = c < 0 ? -c : c;
+        cn = level == 1 ? (unsigned)(run * 5) / 4 : (unsigned)(run * 5 + 4);
+        bits += orc_vlc_len(run_tab, cn + (cn >= eob_pos));
+        level_mode = level > 1;
+        bits += level > 1 ? orc_vlc_len(0, (unsigned)((level - 2) * 2 + (c < 0))) : 1;
+        run = 0;
+      }
+    }
+  }
+  if (pos < N && level_mode) { bits += orc_vlc_len(vlc_adaptive, 0); pos++; }
+  if (pos < N) bits += orc_vlc_len(run_tab, eob_pos);
+  return bits;
+}

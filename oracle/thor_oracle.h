@@ -42,6 +42,8 @@ int            orc_chroma_qp(int qp);                  /* common/common_tables.c
 /* bit-depth independent */
 void orc_transform(const int16_t *block, int16_t *coeff, int size, int fast, int bitdepth);
 void orc_inverse_transform(const int16_t *coeff, int16_t *block, int size, int bitdepth);
+int  orc_vlc_len(int n, unsigned cn);
+int  orc_coeff_bits(const int16_t *coeff, int size, int type);
 int  orc_quantize(const int16_t *coeff, int16_t *coeffq, int qp, int size, int coeff_block_type, const uint16_t *wmatrix);
 void orc_dequantize(const int16_t *coeff, int16_t *rcoeff, int qp, int size, const uint16_t *wmatrix);
 int  orc_calc_cbp(const int16_t *block, int size, int threshold);       /* SIMD semantics, enc/enc_kernels.c:828 */

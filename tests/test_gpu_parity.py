@@ -443,7 +443,8 @@ def test_batch_txfm_chain(tb, hbd, bd):
         x = 4 * int(rng.integers(0, (w - size) // 4 + 1)); y = 4 * int(rng.integers(0, (h - size) // 4 + 1))
         px, py = x + int(rng.integers(-4, 5)), y + int(rng.integers(-4, 5))
         qp = int(rng.choice([10, 22, 30, 32, 37, 44, 51])); typ = int(rng.integers(0, 4)); fast = int(rng.integers(0, 2))
-        items[i] = (optr + (y * ost + x) * esz, pptr + (py * pst + px) * esz, recbuf.ptr + recofs * esz, cqbuf.ptr + i * 512, ost, pst, size, size, qp, typ, fast)
+        bits_flag = tb.TXFM_BITS if i % 5 else 0  # most items also ask for the write_coeff bit count
+        items[i] = (optr + (y * ost + x) * esz, pptr + (py * pst + px) * esz, recbuf.ptr + recofs * esz, cqbuf.ptr + i * 512, ost, pst, size, size, qp, typ, fast | bits_flag)
         meta.append((size, x, y, px, py, qp, typ, fast, recofs))
         recofs += size * size
     d_items = tb.DevBuf.from_array(items); d_out = tb.DevBuf(16 * n)
@@ -472,6 +473,8 @@ def test_batch_txfm_chain(tb, hbd, bd):
         assert (cq[i, :q * q] == cq0).all(), (i, size, qp, typ)
         assert (rec[ro:ro + size * size].reshape(size, size) == want).all(), (i, size, qp)
         assert int(res[i]["ssd"]) == ssd, (i, size)
+        want_bits = O.orc_coeff_bits(P(cq0), size, typ) if (i % 5 and cbp) else 0
+        assert int(res[i]["bits"]) == want_bits, (i, size, qp, typ, int(res[i]["bits"]), want_bits)
         ncbp += cbp
     assert 0 < ncbp < n
 

@@ -629,3 +629,42 @@ def test_cdef_search(hbd, bd):
                     if (fb % ((w + 63) // 64)) * 64 + n * 8 < w and (fb // ((w + 63) // 64)) * 64 + m * 8 < h:
                         assert od[fb, m * 8 + n] == dirs[fb * 64 + m * 8 + n] and ov[fb, m * 8 + n] == vars_[fb * 64 + m * 8 + n]
         assert sbits.value == bits * len(live)
+
+
+def test_coeff_bits():
+    """bits emitted by write_coeff (enc/write_bits.c:145) — oracle length count against the reference's bit writer"""
+    R = ref()
+    class Stream(C.Structure):
+        _fields_ = [("bytesize", C.c_uint32), ("bytepos", C.c_uint32), ("bitstream", C.c_void_p), ("bitbuf", C.c_uint32), ("bitrest", C.c_uint32)]
+    buf = (C.c_uint8 * 8192)()
+    rng = np.random.default_rng(23)
+    # put_vlc code lengths
+    st = Stream(8192, 0, C.addressof(buf), 0, 32)
+    R.put_vlc.restype = C.c_uint; R.put_vlc.argtypes = [C.c_int, C.c_uint, C.c_void_p]
+    for n in (0, 1, 6, 10):
+        for cn in list(range(0, 80)) + [127, 128, 255, 1000, 4097, 32768, 65535]:
+            assert O.orc_vlc_len(n, cn) == R.put_vlc(n, cn, C.byref(st)), (n, cn)
+            st.bytepos = 0
+    R.write_coeff.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]; R.write_coeff.restype = None
+    R.get_bit_pos.argtypes = [C.c_void_p]
+    n = 0
+    for size in (4, 8, 16, 32, 64):
+        q = min(size, 16)
+        for typ in range(4):
+            for trial in range(120):
+                dens = [0.02, 0.1, 0.3, 0.7, 1.0][trial % 5]
+                amp = [1, 2, 5, 40, 3000][(trial // 5) % 5]
+                c = aligned((q, q), np.int16)
+                c[...] = rng.integers(-amp, amp + 1, (q, q)) * (rng.random((q, q)) < dens)
+                if trial % 7 == 0:
+                    c[...] = 0; c[0, 0] = rng.choice([-1, 1, 2, -3])
+                if trial % 11 == 0:
+                    c[q - 1, q - 1] = 1
+                if not c.any():
+                    assert O.orc_coeff_bits(P(c), size, typ) == 0
+                    continue
+                st = Stream(8192, 0, C.addressof(buf), 0, 32)
+                R.write_coeff(C.byref(st), P(c), size, typ)
+                assert O.orc_coeff_bits(P(c), size, typ) == R.get_bit_pos(C.byref(st)), (size, typ, trial)
+                n += 1
+    assert n > 1500

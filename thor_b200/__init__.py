@@ -52,7 +52,8 @@ INTERP_ITEM = np.dtype([("ref", "u8"), ("dst", "u8"), ("rstride", "i4"), ("dstri
                         ("pad", "u4")], align=True)
 TXFM_ITEM = np.dtype([("orig", "u8"), ("pred", "u8"), ("rec", "u8"), ("coeffq", "u8"), ("ostride", "i4"), ("pstride", "i4"), ("rstride", "i4"),
                       ("size", "u1"), ("qp", "u1"), ("coeff_type", "u1"), ("fast", "u1")], align=True)
-TXFM_RESULT = np.dtype([("ssd", "u8"), ("cbp", "i4"), ("pad", "i4")], align=True)
+TXFM_RESULT = np.dtype([("ssd", "u8"), ("cbp", "i4"), ("bits", "i4")], align=True)
+TXFM_FAST, TXFM_BITS = 1, 2
 INTRA_ITEM = np.dtype([("rec", "u8"), ("dst", "u8"), ("rstride", "i4"), ("xpos", "i2"), ("ypos", "i2"), ("size", "u1"), ("mode", "u1"),
                        ("upright", "u1"), ("downleft", "u1")], align=True)
 BLKINFO = np.dtype([("mode", "u1"), ("cbp_y", "u1"), ("size", "u1"), ("tb_split", "u1"), ("pb_part", "u1"), ("pad", "u1", 3), ("mv0x", "i2"),

@@ -1441,6 +1441,142 @@ __device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int si
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// bits that write_coeff() (enc/write_bits.c:145-242) emits for the quantised block, from the code lengths of
+// put_vlc() (enc/putvlc.c:73-161).  The coder walks the zig-zag scan in two modes — level mode (every position coded,
+// left by coding a zero) and run mode (zero runs + the next level; re-enters level mode after a level > 1) — so, like the
+// quantiser's hysteresis, it is a two-state machine over the scan: state entering position p, the adaptive-table flag
+// (level of position p - 1 if that was coded in level mode) and the run length (distance to the last coded position)
+// are all prefix quantities.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int vlc_len(int n, unsigned cn) {  // tables 0, 1, 6, 10
+  if (n == 10) return 1 + 2 * ilog2((int)cn + 1);
+  if (n == 6) {
+    if (!cn) return 2;
+    cn++;
+    n = 2;
+  }
+  if ((int)cn < (5 << n)) return 1 + n + (int)(cn >> n);
+  return (5 - n) + 1 + 2 * ilog2((int)(cn - (5u << n) + (1u << n)));
+}
+struct CoeffBitCtx {
+  int chroma, intra, run_tab;
+  unsigned eob_pos;
+  __device__ __forceinline__ CoeffBitCtx(int size, int type) : chroma(type & 1), intra((type >> 1) & 1), run_tab(((type & 1) && size <= 8) ? 10 : 6), eob_pos((type & 1) ? 0u : 2u) {}
+  // bits of one position; S = mode entering it (1 level, 0 run), A = adaptive-table flag, run = zeros since the last coded position
+  __device__ __forceinline__ int pos_bits(int c, int S, int A, int run) const {
+    const int lev = iabs(c);
+    if (S) return vlc_len(A, (unsigned)lev) + (lev > 0);
+    if (!c) return 0;
+    const unsigned cn = lev == 1 ? (unsigned)(run * 5) >> 2 : (unsigned)(run * 5 + 4);
+    return vlc_len(run_tab, cn + (cn >= eob_pos)) + (lev > 1 ? vlc_len(0, (unsigned)((lev - 2) * 2 + (c < 0))) : 1);
+  }
+  __device__ __forceinline__ int tail_bits(int last, int N, int S_last, int c_last) const {  // after the last non-zero position
+    const int lev = iabs(c_last), S_end = S_last ? 1 : lev > 1;
+    const int A_end = (!chroma && S_last) ? lev > 3 : 0;
+    int pos = last + 1, bits = 0;
+    if (pos < N && S_end) { bits += vlc_len(A_end, 0); pos++; }
+    if (pos < N) bits += vlc_len(run_tab, eob_pos);
+    return bits;
+  }
+};
+// one thread, N scan-ordered levels (registers when the loops unroll, local memory otherwise)
+template <int N, class Q> __device__ __forceinline__ int thread_coeff_bits(const Q &q, int size, int type) {
+  const CoeffBitCtx cx(size, type);
+  int last = -1;
+#pragma unroll(N <= 16 ? N : 1)
+  for (int p = 0; p < N; p++)
+    if (q[p]) last = p;
+  if (last < 0) return 0;
+  int bits = 0;
+  if (cx.chroma) {
+    if (last == 0 && iabs(q[0]) == 1) return 2;
+    bits = 1;
+  }
+  int S = 1, A = cx.intra && !cx.chroma, ev = -1, S_last = 1;
+#pragma unroll(N <= 16 ? N : 1)
+  for (int p = 0; p < N; p++) {
+    if (p <= last) {
+      const int c = q[p], lev = iabs(c);
+      bits += cx.pos_bits(c, S, A, p - 1 - ev);
+      if (p == last) S_last = S;
+      if (S) { if (!cx.chroma) A = lev > 3; if (!lev) S = 0; ev = p; }
+      else if (c) { S = lev > 1; ev = p; }
+    }
+  }
+  return bits + cx.tail_bits(last, N, S_last, q[last]);
+}
+// whole warp, nq (<= 256) scan-ordered levels in shared memory; every lane returns the total
+__device__ int warp_coeff_bits(const int16_t *scan, int nq, int size, int type) {
+  const CoeffBitCtx cx(size, type);
+  const int lane = lane_id(), per = (nq + 31) >> 5, p0 = lane * per;
+  int mylast = -1;
+  for (int t = 0; t < per; t++)
+    if (p0 + t < nq && scan[p0 + t]) mylast = p0 + t;
+  const int last = (int)__reduce_max_sync(FULL, (unsigned)(mylast + 1)) - 1;
+  if (last < 0) return 0;
+  int bits = 0;
+  if (cx.chroma) {
+    if (last == 0 && iabs(scan[0]) == 1) return 2;
+    bits = lane == 0 ? 1 : 0;
+  }
+  // state map of the chunk for both entry states, composed across lanes (see warp_quantize_t)
+  unsigned map = 0;
+  for (int st = 0; st < 2; st++) {
+    int S = st;
+    for (int t = 0; t < per; t++) {
+      const int p = p0 + t;
+      if (p > last) break;
+      const int lev = iabs(scan[p]);
+      S = S ? lev != 0 : lev > 1;
+    }
+    map |= (unsigned)S << st;
+  }
+  unsigned incl = map;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned prev = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) {
+      unsigned r0 = (incl >> ((prev >> 0) & 1)) & 1, r1 = (incl >> ((prev >> 1) & 1)) & 1;
+      incl = r0 | (r1 << 1);
+    }
+  }
+  const unsigned before = __shfl_up_sync(FULL, incl, 1);
+  const int S0 = lane == 0 ? 1 : (int)((before >> 1) & 1);  // the scan starts in level mode
+  // first walk: state entering the chunk's last position and the chunk's last coded position
+  int S = S0, Sin_last = S0, ev = -1;
+  for (int t = 0; t < per; t++) {
+    const int p = p0 + t;
+    if (p > last) break;
+    const int lev = iabs(scan[p]);
+    Sin_last = S;
+    if (S || lev) ev = p;
+    S = S ? lev != 0 : lev > 1;
+  }
+  // previous lane's last position: its entry state and level (for the adaptive flag); exclusive prefix maximum of ev
+  const int pS = __shfl_up_sync(FULL, Sin_last, 1), pc = lane ? (int)scan[p0 - 1] : 0;
+  int evx = ev;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(FULL, evx, o);
+    if (lane >= o) evx = max(evx, v);
+  }
+  int evprev = __shfl_up_sync(FULL, evx, 1);
+  if (lane == 0) evprev = -1;
+  // second walk: bits
+  S = S0;
+  int A = lane == 0 ? (cx.intra && !cx.chroma) : ((!cx.chroma && pS) ? iabs(pc) > 3 : 0);
+  ev = evprev;
+  for (int t = 0; t < per; t++) {
+    const int p = p0 + t;
+    if (p > last) break;
+    const int c = scan[p], lev = iabs(c);
+    bits += cx.pos_bits(c, S, A, p - 1 - ev);
+    if (p == last) bits += cx.tail_bits(last, nq, S, c);
+    if (S) { A = cx.chroma ? 0 : lev > 3; if (!lev) S = 0; ev = p; }
+    else if (c) { S = lev > 1; ev = p; A = 0; }
+  }
+  return (int)warp_sum((uint32_t)bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 4x4 transform blocks (68 % of all transform blocks in the HDB mix): ONE THREAD runs the whole chain
 // residual -> 4-point DCT x2 -> quantize -> dequantize -> inverse DCT x2 -> reconstruct -> SSD in registers.
 // Same arithmetic as the generic routines (common/transform.c:281-307, 411-465 with the 4x4 matrix :63-68,
@@ -1480,7 +1616,7 @@ template <class S> __device__ __forceinline__ void store_row4(S *p, const int (&
 // returns cbp; ssd out
 template <class S>
 __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
-                            uint64_t &ssd_out) {
+                            uint64_t &ssd_out, int want_bits, int &bits_out) {
   constexpr int ZZ[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};  // raster -> scan (common/common_tables.c:29-34)
   const int maxv = (1 << bitdepth) - 1;
   int o[16], p[16], t[16], c[16];
@@ -1538,6 +1674,7 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
 #pragma unroll
     for (int r = 0; r < 16; r++) coeffq_out[r] = (int16_t)q[ZZ[r]];
   }
+  bits_out = (want_bits && cbp) ? thread_coeff_bits<16>(q, 4, coeff_type) : 0;
   uint64_t ssd = 0;
   if (cbp) {
     // dequantize (common/common_block.c:45-73), size 4: rshift = 1
@@ -1594,7 +1731,7 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
 // warp_quantize / warp_dequantize / warp_inv_transform.
 template <class S>
 __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
-                            const int8_t *tab8, uint64_t &ssd_out) {
+                            const int8_t *tab8, uint64_t &ssd_out, int want_bits, int &bits_out) {
   const int8_t *M = tab8 + dct_tab8_ofs(3);  // pitch 8
   const int maxv = (1 << bitdepth) - 1;
   int16_t a[64], b[64];  // a: residual -> coefficients (scan order) ; b: intermediate
@@ -1639,6 +1776,7 @@ __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec
   if (coeffq_out)
     for (int i = 0; i < 8; i++)
       for (int j = 0; j < 8; j++) coeffq_out[i * 8 + j] = b[zigzag_index(i, j, 8)];
+  bits_out = (want_bits && cbp) ? thread_coeff_bits<64>(b, 8, coeff_type) : 0;
   uint64_t ssd = 0;
   if (cbp) {
     const int lshift = qp / 6, dscale = c_dequant[qp % 6];  // rshift = 2

@@ -259,7 +259,8 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
   S *rec = (S *)q.rec;
   const int size = q.size;
   int size1 = size, scale = 1;
-  if (size > (32 >> q.fast)) { size1 = 32 >> q.fast; scale = size / size1; }
+  const int fast = q.fast & 1, want_bits = q.fast & 2;  // flags byte: TB_TXFM_FAST | TB_TXFM_BITS
+  if (size > (32 >> fast)) { size1 = 32 >> fast; scale = size / size1; }
   const int l1 = ilog2(size1), qsize = min(size, 16), lq = ilog2(qsize);
   const int8_t *M1 = tab8 + dct_tab8_ofs(l1);
   const int mp1 = dct_tab8_pitch(l1);
@@ -362,6 +363,8 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
   }
   if (q.coeffq)
     for (int p = tid; p < qsize * qsize; p += NT) q.coeffq[p] = sc.cq[p];
+  int bits = 0;
+  if (want_bits && cbp && dct_warp) bits = warp_coeff_bits(sc.tmp, qsize * qsize, size, q.coeff_type);  // sc.tmp: the levels in scan order (warp_quantize)
   uint64_t ssd = 0;
   if (cbp) {
     // de-quantise (common/common_block.c:45-73) straight into the TRANSPOSED tile in[i][k] = rcoeff[k][i], so that the
@@ -496,7 +499,7 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
 #pragma unroll
     for (int k = 0; k < TW; k++) ssd += red[k];
   }
-  if (tid == 0) { res->ssd = ssd; res->cbp = cbp; res->pad = 0; }
+  if (tid == 0) { res->ssd = ssd; res->cbp = cbp; res->bits = bits; }
   sync();
 }
 
@@ -546,13 +549,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
     if (my_size == 4) {
       tb_txfm_item_t q = items[mine];
       uint64_t ssd;
-      int cbp = thread_txfm4<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, ssd);
-      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
+      int bits;
+      int cbp = thread_txfm4<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, ssd, q.fast & 2, bits);
+      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].bits = bits;
     } else if (my_size == 8) {
       tb_txfm_item_t q = items[mine];
       uint64_t ssd;
-      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, ssd);
-      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].pad = 0;
+      int bits;
+      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, ssd, q.fast & 2,
+                                bits);
+      out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].bits = bits;
     }
     __syncwarp();
   }

@@ -15,6 +15,8 @@ tmp = tb.Frame(B.W, B.H, B.ESZ); tmp.upload(*fr[1]); ref = tb.Frame(B.W, B.H, B.
 rec = tb.Frame(B.W, B.H, B.ESZ)
 tus = B.tu_list(B.block_grid())
 items = B.build_txfm(tb, tus, [cur.plane(0), cur.plane(1)], [ref.plane(0), ref.plane(1)], [rec.plane(0), rec.plane(1)], rng)
+if '--bits' in sys.argv:
+    items['fast'] |= tb.TXFM_BITS  # also count the write_coeff bits
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); tb.check(L.tb_set_stream(C.c_void_p(stream.cuda_stream)))
 def run(name, sel):
     it = np.ascontiguousarray(items[sel]); d = tb.DevBuf.from_array(it); out = tb.DevBuf(16 * len(it))
