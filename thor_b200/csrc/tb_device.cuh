@@ -15,6 +15,9 @@
 #ifndef TB_EXP_NOSUBPEL
 #define TB_EXP_NOSUBPEL 0  // 1: skip the sub-pel SADs (timing experiment only: measures the integer stages alone)
 #endif
+#ifndef TB_SAD_V4
+#define TB_SAD_V4 1  // 128-bit loads for block rows of >= 16 bytes
+#endif
 #ifndef TB_HALFPEL_PLANES
 #define TB_HALFPEL_PLANES 1  // half-pel stage from three shared planes (halfpel_stage_sads_u8)
 #endif
@@ -107,7 +110,30 @@ __device__ __forceinline__ uint32_t sad_tile(const uint32_t *q, int qstep, const
   return acc;
 }
 
-template <class S>
+// Rows of >= 16 bytes with 128-bit loads: one aligned LDG.128 per 16 reference bytes (+1 per row) and one per 16 original
+// bytes instead of eight 32-bit loads — the search is bound by L1 wavefronts (59 % of the l1tex data-pipe peak in ncu), so
+// request count matters more than bytes.  J = word offset of the row inside its first 16-byte chunk (uniform per lane group:
+// all pitches are multiples of 16 bytes), sh = remaining byte offset in bits.
+template <class S, int J>
+__device__ __forceinline__ uint32_t sad_rows_v4(const uint4 *rq, int rsv, const uint4 *oq, int osv, int nch, int h, int sub, int nl, unsigned sh) {
+  uint32_t acc = 0;
+  for (int row = sub; row < h; row += nl) {
+    const uint4 *q = rq + row * rsv, *a = oq + row * osv;
+    uint4 P = __ldg(q);
+    for (int c = 0; c < nch; c++) {
+      const uint4 N = __ldg(q + c + 1), A = __ldg(a + c);
+      const uint32_t w0 = J == 0 ? P.x : (J == 1 ? P.y : (J == 2 ? P.z : P.w)), w1 = J == 0 ? P.y : (J == 1 ? P.z : (J == 2 ? P.w : N.x)),
+                     w2 = J == 0 ? P.z : (J == 1 ? P.w : (J == 2 ? N.x : N.y)), w3 = J == 0 ? P.w : (J == 1 ? N.x : (J == 2 ? N.y : N.z)),
+                     w4 = J == 0 ? N.x : (J == 1 ? N.y : (J == 2 ? N.z : N.w));
+      acc += word_sad<S>(A.x, __funnelshift_r(w0, w1, sh)) + word_sad<S>(A.y, __funnelshift_r(w1, w2, sh)) + word_sad<S>(A.z, __funnelshift_r(w2, w3, sh)) +
+             word_sad<S>(A.w, __funnelshift_r(w3, w4, sh));
+      P = N;
+    }
+  }
+  return acc;
+}
+
+template <class S, bool V4 = false>
 __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, int rs, int w, int h, int sub, int nl) {
   // Lane `sub` of `nl` takes the rows sub, sub+nl, ... (nl <= h).  Row pitches are multiples of 4 bytes, so the byte
   // misalignment of the reference row is the same for every row: one aligned word stream per row, one funnel shift per word.
@@ -118,6 +144,18 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   const uint32_t *rq = (const uint32_t *)(ra & ~(uintptr_t)3);
   const uint32_t *oq = (const uint32_t *)o;
   const int rsw = (rs * (int)sizeof(S)) >> 2, osw = (os * (int)sizeof(S)) >> 2;  // pitches in words
+#if TB_SAD_V4
+  if (V4 && !(ww & 3) && !((((uintptr_t)o) | (unsigned)(osw << 2) | (unsigned)(rsw << 2)) & 15)) {
+    const uint4 *rv = (const uint4 *)(ra & ~(uintptr_t)15), *ov = (const uint4 *)o;
+    const unsigned sh8 = (unsigned)(ra & 3) * 8;
+    switch ((unsigned)(ra >> 2) & 3) {
+      case 0: return sad_rows_v4<S, 0>(rv, rsw >> 2, ov, osw >> 2, ww >> 2, h, sub, nl, sh8);
+      case 1: return sad_rows_v4<S, 1>(rv, rsw >> 2, ov, osw >> 2, ww >> 2, h, sub, nl, sh8);
+      case 2: return sad_rows_v4<S, 2>(rv, rsw >> 2, ov, osw >> 2, ww >> 2, h, sub, nl, sh8);
+      default: return sad_rows_v4<S, 3>(rv, rsw >> 2, ov, osw >> 2, ww >> 2, h, sub, nl, sh8);
+    }
+  }
+#endif
   uint32_t acc = 0;
 #if TB_SAD_TILE
   int row = sub;
@@ -156,7 +194,7 @@ template <class S> __device__ __forceinline__ uint32_t warp_sad(const S *o, int 
 // (i < n); lane i receives SAD i.  L = lanes cooperating on one position = words/16 (1 for blocks up to 8x8 u8: the
 // whole 5x5 telescope grid is then evaluated in ONE pass, one position per lane, no shuffles), 32 for >= 512 words.
 template <class S>
-__device__ __noinline__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+__device__ __noinline__ uint32_t multi_sad_narrow(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
   constexpr int PW = Word<S>::PW;
   const int lane = lane_id();
   const int nwords = (w / PW) * h;
@@ -186,6 +224,46 @@ __device__ __noinline__ uint32_t multi_sad(const S *o, int os, const S *r, int r
     }
   }
   return out;
+}
+
+// The same for blocks of >= 256 words whose rows are >= 16 bytes: 16 or 32 lanes per position, so at most two positions (two
+// chunk offsets) are in flight per pass and the 128-bit row loads of sad_rows_v4 stay (nearly) uniform.  A separate function:
+// its larger register footprint must not be paid around the calls for small blocks.
+template <class S>
+__device__ __noinline__ uint32_t multi_sad_wide(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+  constexpr int PW = Word<S>::PW;
+  const int lane = lane_id();
+  const int nwords = (w / PW) * h;
+  int L = nwords >= 512 ? 32 : 16;
+  if (L > h) L = h;  // h >= 16 here
+  uint32_t out = 0;
+  if (L == 32) {
+    for (int p = 0; p < n; p++) {
+      int off = __shfl_sync(FULL, roff, p);
+      uint32_t s = warp_sum(lane < h ? sad_partial<S, true>(o, os, r + off, rs, w, h, lane, 32) : 0u);
+      if (lane == p) out = s;
+    }
+  } else {
+    const int sub = lane & 15, grp = lane >> 4;
+    for (int base = 0; base < n; base += 2) {
+      int p = base + grp;
+      int off = __shfl_sync(FULL, roff, p & 31);
+      uint32_t s = (p < n) ? sad_partial<S, true>(o, os, r + off, rs, w, h, sub, 16) : 0u;
+      s = group_sum(s, 16);
+      uint32_t got = __shfl_sync(FULL, s, ((lane - base) * 16) & 31);
+      if (lane >= base && lane < base + 2 && lane < n) out = got;
+    }
+  }
+  return out;
+}
+template <class S, int TW = 1>
+__device__ __forceinline__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+#if TB_SAD_V4
+  // only the CTA-team searches (blocks >= 2048 samples) take the wide form: a second callee at the call sites of the one-warp
+  // searches costs them more in spills than the 32x32 blocks would gain
+  if (TW > 1 && (w / Word<S>::PW) * h >= 256 && h >= 16 && w * (int)sizeof(S) >= 16) return multi_sad_wide<S>(o, os, r, rs, w, h, roff, n);
+#endif
+  return multi_sad_narrow<S>(o, os, r, rs, w, h, roff, n);
 }
 
 // a3: SSD.  enc/encode_block.c:455-465
@@ -952,14 +1030,14 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
         int base = s * (cx >> 2) + s * (cy >> 2) * rs;
 #pragma unroll
         for (int t = 0; t < 5; t++) {
-          uint32_t v = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, base + offs[t], n));
+          uint32_t v = tm.sum(multi_sad<S, TW>(orig, os, ref, rs, c.width, band_h, base + offs[t], n));
           if (v < b) { b = v; bxo = offs[t]; }
         }
         sad = b;
         cx = (int)(int16_t)(cx + (s * bxo << 2));
         c.n_int += 5 * n;
       } else {
-        sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
+        sad = tm.sum(multi_sad<S, TW>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
         c.n_int += n;
       }
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
@@ -992,14 +1070,14 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
       int bxo = 0;
 #pragma unroll
       for (int t = 0; t < 5; t++) {
-        uint32_t v = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, pos + offs[t], n));
+        uint32_t v = tm.sum(multi_sad<S, TW>(orig, os, ref, rs, c.width, band_h, pos + offs[t], n));
         if (v < b) { b = v; bxo = offs[t]; }
       }
       sad = b;
       cx = (int)(int16_t)(cx + (s * bxo << 2));
       c.n_int += 5 * n;
     } else {
-      sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, pos, n));
+      sad = tm.sum(multi_sad<S, TW>(orig, os, ref, rs, c.width, band_h, pos, n));
       c.n_int += n;
     }
     uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
@@ -1024,7 +1102,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
       int dir = (start + lane) % 6;
       int cx = (int)(int16_t)(refx + diy[dir] * 4), cy = (int)(int16_t)(refy + dix[dir] * 4);
       clip_mv(cx, cy, c.ypos, c.xpos, c.fw, c.fh, c.size, c.size, c.sign);
-      uint32_t sad = tm.sum(multi_sad<S>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
+      uint32_t sad = tm.sum(multi_sad<S, TW>(orig, os, ref, rs, c.width, band_h, s * (cx >> 2) + s * (cy >> 2) * rs, n));
       c.n_int += n;
       uint32_t cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(cy - c.mvpy, cx - c.mvpx));
       uint32_t best;
