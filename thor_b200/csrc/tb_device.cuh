@@ -1807,29 +1807,40 @@ __device__ int thread_txfm4(const S *orig, int os, const S *pred, int ps, S *rec
 // interleaves per thread, so the lock-step (uniform-index) accesses of a warp coalesce into L1 lines; the DCT matrix is
 // read from the shared-memory table with a warp-uniform index (broadcast).  Same arithmetic as warp_fwd_transform /
 // warp_quantize / warp_dequantize / warp_inv_transform.
+__constant__ uint8_t c_zz8[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+                                   10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+// eight-term dot product of an int8 matrix row (two words) with eight int16 values (four words): four DP2A
+__device__ __forceinline__ int dot8(uint2 m, uint4 v, int acc) {
+  acc = __dp2a_lo((int)v.x, (int)m.x, acc);
+  acc = __dp2a_hi((int)v.y, (int)m.x, acc);
+  acc = __dp2a_lo((int)v.z, (int)m.y, acc);
+  return __dp2a_hi((int)v.w, (int)m.y, acc);
+}
 template <class S>
 __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *coeffq_out, int qp, int coeff_type, int bitdepth,
-                            const int8_t *tab8, uint64_t &ssd_out, int want_bits, int &bits_out) {
-  const int8_t *M = tab8 + dct_tab8_ofs(3);  // pitch 8
+                            const int8_t *tab8, const int8_t *tab8t, uint64_t &ssd_out, int want_bits, int &bits_out) {
+  const uint2 *M = (const uint2 *)(tab8 + dct_tab8_ofs(3)), *Mt = (const uint2 *)(tab8t + dct_tab8_ofs(3));  // rows of 8 int8, warp-uniform index
   const int maxv = (1 << bitdepth) - 1;
-  int16_t a[64], b[64];  // a: residual -> coefficients (scan order) ; b: intermediate
-  for (int r = 0; r < 8; r++)
-    for (int c = 0; c < 8; c++) a[r * 8 + c] = (int16_t)((int)orig[r * os + c] - (int)pred[r * ps + c]);
+  alignas(16) int16_t a[64], b[64];  // 16-byte rows: each row is one 128-bit local load in the matrix phases
+  for (int r = 0; r < 8; r++) {
+    int o0[4], o1[4], p0[4], p1[4];
+    load_row4<S>(orig + r * os, o0); load_row4<S>(orig + r * os + 4, o1);
+    load_row4<S>(pred + r * ps, p0); load_row4<S>(pred + r * ps + 4, p1);
+    *(uint4 *)&a[r * 8] = make_uint4(((uint32_t)(o0[0] - p0[0]) & 0xffffu) | ((uint32_t)(o0[1] - p0[1]) << 16), ((uint32_t)(o0[2] - p0[2]) & 0xffffu) | ((uint32_t)(o0[3] - p0[3]) << 16),
+                                     ((uint32_t)(o1[0] - p1[0]) & 0xffffu) | ((uint32_t)(o1[1] - p1[1]) << 16), ((uint32_t)(o1[2] - p1[2]) & 0xffffu) | ((uint32_t)(o1[3] - p1[3]) << 16));
+  }
+  // forward: b[i][j] = (M[i] . res[j] + add1) >> shift1, then a[scan(i, j)] = (M[i] . b[j] + 128) >> 8
   const int shift1 = 3 + bitdepth - 8, add1 = 1 << (shift1 - 1);
-  for (int i = 0; i < 8; i++)
-    for (int j = 0; j < 8; j++) {
-      int sum = 0;
+  for (int j = 0; j < 8; j++) {
+    const uint4 v = *(const uint4 *)&a[j * 8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) sum += (int)M[i * 8 + k] * (int)a[j * 8 + k];
-      b[i * 8 + j] = (int16_t)((sum + add1) >> shift1);
-    }
-  for (int i = 0; i < 8; i++)
-    for (int j = 0; j < 8; j++) {
-      int sum = 0;
+    for (int i = 0; i < 8; i++) b[i * 8 + j] = (int16_t)(dot8(M[i], v, add1) >> shift1);
+  }
+  for (int j = 0; j < 8; j++) {
+    const uint4 v = *(const uint4 *)&b[j * 8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) sum += (int)M[i * 8 + k] * (int)b[j * 8 + k];
-      a[zigzag_index(i, j, 8)] = (int16_t)((sum + 128) >> 8);  // scan order
-    }
+    for (int i = 0; i < 8; i++) a[c_zz8[i * 8 + j]] = (int16_t)(dot8(M[i], v, 128) >> 8);  // scan order
+  }
   const int intra = (coeff_type >> 1) & 1, scale = c_quant[qp % 6], shift2 = 18 + qp / 6;
   const int off_last = (intra ? 38 : -26) * (1 << (shift2 - 8));
   int last = -1;
@@ -1852,45 +1863,53 @@ __device__ int thread_txfm8(const S *orig, int os, const S *pred, int ps, S *rec
     b[pos] = (int16_t)(cc < 0 ? -lev : lev);  // quantised, scan order
   }
   if (coeffq_out)
-    for (int i = 0; i < 8; i++)
-      for (int j = 0; j < 8; j++) coeffq_out[i * 8 + j] = b[zigzag_index(i, j, 8)];
+    for (int p = 0; p < 64; p++) coeffq_out[p] = b[c_zz8[p]];
   bits_out = (want_bits && cbp) ? thread_coeff_bits<64>(b, 8, coeff_type) : 0;
   uint64_t ssd = 0;
   if (cbp) {
+    // de-quantise into the TRANSPOSED block a[i][k] = rcoeff[k][i], so that both inverse stages are row . row products
     const int lshift = qp / 6, dscale = c_dequant[qp % 6];  // rshift = 2
-    for (int i = 0; i < 8; i++)
-      for (int j = 0; j < 8; j++) {
-        int v = (int)b[zigzag_index(i, j, 8)] * dscale;
-        a[i * 8 + j] = lshift >= 2 ? (int16_t)((unsigned)v << (lshift - 2)) : (int16_t)((v + (1 << (1 - lshift))) >> (2 - lshift));
-      }
-    // inverse 1st dimension: b[i][j] = clip16((sum_k M[k][j] * a[k][i] + 64) >> 7)
-    for (int i = 0; i < 8; i++)
-      for (int j = 0; j < 8; j++) {
-        int sum = 0;
+    for (int k = 0; k < 8; k++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) sum += (int)M[k * 8 + j] * (int)a[k * 8 + i];
-        b[i * 8 + j] = (int16_t)iclip((sum + 64) >> 7, -32768, 32767);
+      for (int i = 0; i < 8; i++) {
+        int v = (int)b[c_zz8[k * 8 + i]] * dscale;
+        a[i * 8 + k] = lshift >= 2 ? (int16_t)((unsigned)v << (lshift - 2)) : (int16_t)((v + (1 << (1 - lshift))) >> (2 - lshift));
       }
+    // inverse 1st dimension: T[i][j] = clip16((sum_k M[k][j] * rcoeff[k][i] + 64) >> 7), stored transposed: b[j][i]
+    for (int i = 0; i < 8; i++) {
+      const uint4 v = *(const uint4 *)&a[i * 8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) b[j * 8 + i] = (int16_t)iclip(dot8(Mt[j], v, 64) >> 7, -32768, 32767);
+    }
+    // 2nd dimension + reconstruction: out[i][j] = clip16((sum_k M[k][j] * T[k][i] + addB) >> shiftB) = Mt[j] . b[i]
     const int shiftB = 20 - bitdepth, addB = 1 << (shiftB - 1);
-    for (int i = 0; i < 8; i++)
-      for (int j = 0; j < 8; j++) {
-        int sum = 0;
+    for (int i = 0; i < 8; i++) {
+      const uint4 v = *(const uint4 *)&b[i * 8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) sum += (int)M[k * 8 + j] * (int)b[k * 8 + i];
-        int r = iclip((sum + addB) >> shiftB, -32768, 32767);
-        int pv = pred[i * ps + j];
-        int v = sat_px(r + pv, maxv);
-        if (rec) rec[i * rs + j] = (S)v;
-        int d = (int)orig[i * os + j] - v;
-        ssd += (uint32_t)(d * d);
+      for (int h2 = 0; h2 < 2; h2++) {
+        int pv[4], ov[4], o4[4];
+        load_row4<S>(pred + i * ps + 4 * h2, pv);
+        load_row4<S>(orig + i * os + 4 * h2, ov);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          int r = iclip(dot8(Mt[4 * h2 + t], v, addB) >> shiftB, -32768, 32767);
+          o4[t] = sat_px(r + pv[t], maxv);
+          int d = ov[t] - o4[t];
+          ssd += (uint32_t)(d * d);
+        }
+        if (rec) store_row4<S>(rec + i * rs + 4 * h2, o4);
       }
+    }
   } else {
     for (int i = 0; i < 8; i++)
-      for (int j = 0; j < 8; j++) {
-        int v = pred[i * ps + j];
-        if (rec) rec[i * rs + j] = (S)v;
-        int d = (int)orig[i * os + j] - v;
-        ssd += (uint32_t)(d * d);
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        int pv[4], ov[4];
+        load_row4<S>(pred + i * ps + 4 * h2, pv);
+        load_row4<S>(orig + i * os + 4 * h2, ov);
+        if (rec) store_row4<S>(rec + i * rs + 4 * h2, pv);
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int d = ov[t] - pv[t]; ssd += (uint32_t)(d * d); }
       }
   }
   ssd_out = ssd;

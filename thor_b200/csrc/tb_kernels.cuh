@@ -556,8 +556,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
       tb_txfm_item_t q = items[mine];
       uint64_t ssd;
       int bits;
-      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, ssd, q.fast & 2,
-                                bits);
+      int cbp = thread_txfm8<S>((const S *)q.orig, q.ostride, (const S *)q.pred, q.pstride, (S *)q.rec, q.rstride, q.coeffq, q.qp, q.coeff_type, bitdepth, tab8, tab8t, ssd,
+                                q.fast & 2, bits);
       out[mine].ssd = ssd; out[mine].cbp = cbp; out[mine].bits = bits;
     }
     __syncwarp();
