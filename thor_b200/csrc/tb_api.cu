@@ -422,7 +422,7 @@ int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int 
 int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, int bitdepth, tb_txfm_result_t *out) {
   API_BEGIN();
   if (n <= 0) return TB_OK;
-  size_t smem = ((DCT_TAB8_SIZE * 2 + 15) & ~15) + sizeof(TxScratch) * WARPS_PER_CTA;
+  size_t smem = TX_TABLE_BYTES + sizeof(TxScratch) * WARPS_PER_CTA;
   int *meta = nullptr, *idx = nullptr;
   ck(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "txfm scratch");
   idx = meta + 128;

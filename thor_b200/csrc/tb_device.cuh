@@ -1445,12 +1445,13 @@ __device__ __forceinline__ int zigzag_index(int r, int c, int n) {
 
 // T = int when every intermediate fits 32 bits (scale <= 26214, |coef| <= 32768 -> product < 2^30; offsets <= 115 << (shift2 - 8)
 // stay below 2^27 for shift2 <= 28), int64_t otherwise: same values, a third of the multiply instructions.
-template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc, int shift2) {
+template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc, int shift2, const uint8_t *zz16) {
   const int lane = lane_id();
   const int intra = (coeff_type >> 1) & 1, qsize = min(size, 16), nq = qsize * qsize, lq = ilog2(qsize);
   const T scale = c_quant[qp % 6];
   int *scan = (int *)sc.in;  // reuse: 256 ints of scan-ordered coefficients
-  for (int p = lane; p < nq; p += 32) scan[zigzag_index(p >> lq, p & (qsize - 1), qsize)] = coef[p];
+  const bool tab = zz16 != nullptr && qsize == 16;  // 16x16 scan positions from a shared-memory table instead of the closed form
+  for (int p = lane; p < nq; p += 32) scan[tab ? (int)zz16[p] : zigzag_index(p >> lq, p & (qsize - 1), qsize)] = coef[p];
   __syncwarp();
   // last_pos: highest scan position whose level (with the "last" offset) is non-zero
   const T unit = (T)1 << (shift2 - 8);
@@ -1509,13 +1510,13 @@ template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t 
     sc.tmp[p] = (int16_t)q;  // scan order
   }
   __syncwarp();
-  for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[zigzag_index(p >> lq, p & (qsize - 1), qsize)];
+  for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[tab ? (int)zz16[p] : zigzag_index(p >> lq, p & (qsize - 1), qsize)];
   __syncwarp();
   return __any_sync(FULL, cbp);
 }
-__device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc) {
+__device__ int warp_quantize(const int16_t *coef, int16_t *coefq, int qp, int size, int coeff_type, TxScratch &sc, const uint8_t *zz16 = nullptr) {
   const int shift2 = 21 - ilog2(size) + qp / 6;
-  return shift2 <= 28 ? warp_quantize_t<int>(coef, coefq, qp, size, coeff_type, sc, shift2) : warp_quantize_t<int64_t>(coef, coefq, qp, size, coeff_type, sc, shift2);
+  return shift2 <= 28 ? warp_quantize_t<int>(coef, coefq, qp, size, coeff_type, sc, shift2, zz16) : warp_quantize_t<int64_t>(coef, coefq, qp, size, coeff_type, sc, shift2, zz16);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

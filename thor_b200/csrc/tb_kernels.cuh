@@ -245,12 +245,14 @@ struct alignas(16) TxShared {
   TxScratch sc;
 };
 
+constexpr int TX_TABLE_BYTES = (DCT_TAB8_SIZE * 2 + 256 + 15) & ~15;  // int8 matrices (plain, transposed) + 16x16 zig-zag table
 // residual on the fly -> forward -> quantise -> de-quantise -> inverse -> reconstruct + SSD.
 // One transform block > 8x8 handled by a team of TW warps (TW == 1: a warp; TW == WARPS_PER_CTA: the CTA, for 64x64 and
 // 128x128 whose box-sum load and replicated output are per-sample passes over up to 16384 samples).
 template <class S, int TW>
 __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth, TxScratch &sc, int16_t *rt, const int8_t *tab8, const int8_t *tab8t, unsigned long long *red,
                                           int *bc, tb_txfm_result_t *res) {
+  const uint8_t *zz16 = (const uint8_t *)(tab8 + 2 * DCT_TAB8_SIZE);  // 16x16 zig-zag table behind the two matrix tables
   constexpr int PI = 40;  // int16 pitch of the scratch tiles: 80-byte rows (16-byte aligned; eight consecutive rows cover all 32 banks with 128-bit loads)
   constexpr int NT = 32 * TW;
   const int tid = TW == 1 ? lane_id() : (int)threadIdx.x, lane = lane_id(), maxv = (1 << bitdepth) - 1;
@@ -352,10 +354,10 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
     sync();
   }
   int cbp;
-  if (TW == 1) cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
+  if (TW == 1) cbp = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc, zz16);
   else {
     if (threadIdx.x < 32) {
-      int c = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc);
+      int c = warp_quantize(sc.rc, sc.cq, q.qp, size, q.coeff_type, sc, zz16);
       if (lane == 0) *bc = c;
     }
     __syncthreads();
@@ -514,8 +516,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txf
   __shared__ unsigned long long red[WARPS_PER_CTA];
   __shared__ int bc, s_next;
   int8_t *tab8 = (int8_t *)smem_raw, *tab8t = tab8 + DCT_TAB8_SIZE;
-  TxScratch *scs = (TxScratch *)(smem_raw + ((DCT_TAB8_SIZE * 2 + 15) & ~15));
+  TxScratch *scs = (TxScratch *)(smem_raw + TX_TABLE_BYTES);
   dct_tab8_fill(tab8, tab8t);
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) ((uint8_t *)(tab8 + 2 * DCT_TAB8_SIZE))[t] = (uint8_t)zigzag_index(t >> 4, t & 15, 16);
   __syncthreads();
   const int lane = lane_id();
   const int nteam = meta[96], nlisted = meta[99];
