@@ -415,8 +415,8 @@ int tb_me_set_stats(uint64_t *stats_dev) {
 int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int bitdepth, int bipred) {
   API_BEGIN();
   if (n <= 0) return TB_OK;
-  if (sample_bytes == 1) LAUNCH(interp_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, bitdepth, bipred);
-  else LAUNCH(interp_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, bitdepth, bipred);
+  if (sample_bytes == 1) LAUNCH(interp_batch_kernel<uint8_t>, grid_for_warps((n + 3) / 4), CTA_THREADS, 0, items, n, bitdepth, bipred);
+  else LAUNCH(interp_batch_kernel<uint16_t>, grid_for_warps((n + 3) / 4), CTA_THREADS, 0, items, n, bitdepth, bipred);
   API_END();
 }
 int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, int bitdepth, tb_txfm_result_t *out) {

@@ -382,17 +382,19 @@ __device__ void warp_interp_strips_u8(uint8_t *dst, int ds, const uint8_t *ip, i
 // Whole-warp prediction of one block into dst (common/inter_prediction.c:117-183 / :65-115).
 template <class S>
 __device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, int mvx, int mvy, int sign, int chroma, int bip, int pic_w,
-                            int pic_h, int xpos, int ypos, int bitdepth) {
+                            int pic_h, int xpos, int ypos, int bitdepth, int sub = -1, int nl = 32) {
+  // sub/nl: the block is shared by the nl lanes sub = 0 .. nl - 1 (default: the whole warp; lane groups of 8 for small blocks)
+  if (sub < 0) sub = lane_id();
   int hi, vi, xf, yf;
   split_mv(mvx, mvy, sign, chroma ? 3 : 2, pic_w, pic_h, xpos, ypos, w, h, hi, vi, xf, yf);
   const S *ip = ref + vi * rs + hi;
   const int maxv = (1 << bitdepth) - 1, lw = ilog2(w);
-  if (sizeof(S) == 1 && !chroma && (xf | yf) && w * h >= 256 && !(h & 7) && !((((uintptr_t)dst) | (unsigned)ds | (unsigned)rs) & 3)) {
+  if (nl == 32 && sizeof(S) == 1 && !chroma && (xf | yf) && w * h >= 256 && !(h & 7) && !((((uintptr_t)dst) | (unsigned)ds | (unsigned)rs) & 3)) {
     // large 8-bit luma blocks: separable DP4A strips (same arithmetic as the search's sub-pel SAD), word stores
     warp_interp_strips_u8((uint8_t *)dst, ds, (const uint8_t *)ip, rs, w, h, xf, yf, bip);
     return;
   }
-  for (int p = lane_id(); p < (h << lw); p += 32) {
+  for (int p = sub; p < (h << lw); p += nl) {
     int row = p >> lw, col = p & (w - 1);
     const S *q = ip + row * rs + col;
     int v;

@@ -216,11 +216,32 @@ template <class S> __global__ void __launch_bounds__(CTA_THREADS) combine_batch_
 }
 
 // ---- a7/a8 -----------------------------------------------------------------------------------------------------
+// Four consecutive items per warp and step.  85 % of the predictions of an encode are blocks of <= 64 samples (4x4 ... 8x8 luma,
+// 2x2 ... 8x8 chroma) whose cost is one dependent chain item -> samples -> store: when all four are that small, each gets a group
+// of eight lanes and the four chains overlap; otherwise the warp takes them one after the other.  (Eight groups of four lanes for
+// blocks of <= 16 samples were measured slower: 96 registers instead of 72, 1.81 ms instead of 1.57 ms for the 1080p batch.)
 template <class S> __global__ void __launch_bounds__(CTA_THREADS) interp_batch_kernel(const tb_interp_item_t *items, int n, int bitdepth, int bip) {
-  for (int it = global_warp(); it < n; it += total_warps()) {
-    tb_interp_item_t q = items[it];
-    warp_interp<S>((S *)q.dst, q.dstride, (const S *)q.ref, q.rstride, q.width, q.height, q.mvx, q.mvy, q.sign, q.chroma, q.chroma ? 0 : bip, q.pic_w, q.pic_h,
-                   q.xpos, q.ypos, bitdepth);
+  const int lane = lane_id(), grp = lane >> 3;
+  for (int base = global_warp() * 4; base < n; base += total_warps() * 4) {
+    const int mine = base + grp;
+    tb_interp_item_t q;
+    bool small = true;
+    if (mine < n) {
+      q = items[mine];
+      small = (int)q.width * (int)q.height <= 64;
+    }
+    if (__all_sync(FULL, small)) {
+      if (mine < n)
+        warp_interp<S>((S *)q.dst, q.dstride, (const S *)q.ref, q.rstride, q.width, q.height, q.mvx, q.mvy, q.sign, q.chroma, q.chroma ? 0 : bip, q.pic_w, q.pic_h, q.xpos,
+                       q.ypos, bitdepth, lane & 7, 8);
+    } else {
+      for (int it = base; it < min(base + 4, n); it++) {
+        const tb_interp_item_t t = items[it];
+        warp_interp<S>((S *)t.dst, t.dstride, (const S *)t.ref, t.rstride, t.width, t.height, t.mvx, t.mvy, t.sign, t.chroma, t.chroma ? 0 : bip, t.pic_w, t.pic_h, t.xpos,
+                       t.ypos, bitdepth);
+      }
+    }
+    __syncwarp();
   }
 }
 // fractional-offset form of the drop-in symbols (ip already at the integer position)
