@@ -1455,30 +1455,37 @@ template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t 
   const bool tab = zz16 != nullptr && qsize == 16;  // 16x16 scan positions from a shared-memory table instead of the closed form
   for (int p = lane; p < nq; p += 32) scan[tab ? (int)zz16[p] : zigzag_index(p >> lq, p & (qsize - 1), qsize)] = coef[p];
   __syncwarp();
-  // last_pos: highest scan position whose level (with the "last" offset) is non-zero
+  // each lane owns `per` (<= 8) consecutive scan positions; their three candidate levels are computed ONCE and kept in registers:
+  // level0 = ac >> shift2 decides between the two rounding offsets, lvA / lvB are the levels with off0 / off1
   const T unit = (T)1 << (shift2 - 8);
   const T off_last = (T)(intra ? 38 : -26) * unit;
+  const T off0 = (T)(intra ? 102 : 51) * unit, off1 = (T)(intra ? 115 : 90) * unit;
+  const int per = (nq + 31) / 32, p0 = lane * per;
+  int cv[8], l0[8], lvA[8], lvB[8];
   int last = -1;
-  for (int p = lane; p < nq; p += 32) {
-    T l = (T)iabs(scan[p]) * scale + off_last;
-    int lev = (int)((l > 0 ? l : -l) >> shift2);
-    if (lev) last = p;  // p ascending per lane -> keeps the lane's maximum
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int p = p0 + t;
+    cv[t] = (t < per && p < nq) ? scan[p] : 0;
+    const T ac = scale * (T)iabs(cv[t]);
+    l0[t] = (int)(ac >> shift2);
+    lvA[t] = (int)((ac + off0) >> shift2);
+    lvB[t] = (int)((ac + off1) >> shift2);
+    const T l = ac + off_last;
+    if (t < per && p < nq && (int)((l > 0 ? l : -l) >> shift2)) last = p;  // last_pos: highest position whose level with the "last" offset is non-zero
   }
   last = (int)__reduce_max_sync(FULL, (unsigned)(last + 1)) - 1;
-  const T off0 = (T)(intra ? 102 : 51) * unit, off1 = (T)(intra ? 115 : 90) * unit;
-  // chunk = 8 consecutive scan positions per lane (256/32)
-  const int per = (nq + 31) / 32, p0 = lane * per;
   unsigned map = 0;  // bit s = end state when the chunk is entered in state s
+#pragma unroll
   for (int st = 0; st < 2; st++) {
     int mode = st;
-    for (int t = 0; t < per; t++) {
-      int p = p0 + t;
-      if (p > last || p >= nq) break;
-      T ac = scale * (T)iabs(scan[p]);
-      int level0 = (int)(ac >> shift2);
-      int level = (int)((ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2);
-      if (mode) { if (level == 0) mode = 0; }
-      else if (level > 1) mode = 1;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      if (t < per && p0 + t <= last) {
+        const int level = (l0[t] > (1 - mode)) ? lvB[t] : lvA[t];
+        if (mode) { if (level == 0) mode = 0; }
+        else if (level > 1) mode = 1;
+      }
     }
     map |= (unsigned)mode << st;
   }
@@ -1495,21 +1502,20 @@ template <class T> __device__ __forceinline__ int warp_quantize_t(const int16_t 
   unsigned before = __shfl_up_sync(FULL, incl, 1);
   int mode = lane == 0 ? 1 : (int)((before >> 1) & 1);  // initial level_mode = 1
   int cbp = 0;
-  for (int t = 0; t < per; t++) {
-    int p = p0 + t;
-    if (p >= nq) break;
-    int q = 0;
-    if (p <= last) {
-      int cc = scan[p];
-      T ac = scale * (T)iabs(cc);
-      int level0 = (int)(ac >> shift2);
-      int level = (int)((ac + ((level0 > (1 - mode)) ? off1 : off0)) >> shift2);
-      q = cc < 0 ? -level : level;
-      cbp |= level != 0;
-      if (mode) { if (level == 0) mode = 0; }
-      else if (level > 1) mode = 1;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int p = p0 + t;
+    if (t < per && p < nq) {
+      int q = 0;
+      if (p <= last) {
+        const int level = (l0[t] > (1 - mode)) ? lvB[t] : lvA[t];
+        q = cv[t] < 0 ? -level : level;
+        cbp |= level != 0;
+        if (mode) { if (level == 0) mode = 0; }
+        else if (level > 1) mode = 1;
+      }
+      sc.tmp[p] = (int16_t)q;  // scan order
     }
-    sc.tmp[p] = (int16_t)q;  // scan order
   }
   __syncwarp();
   for (int p = lane; p < nq; p += 32) coefq[p] = sc.tmp[tab ? (int)zz16[p] : zigzag_index(p >> lq, p & (qsize - 1), qsize)];
