@@ -388,15 +388,15 @@ def run_gpu(args):
         filters_and_ref()
 
     # End-to-end step: the same work fed from pinned host memory and drained to pinned host memory INSIDE the step.  Three
-    # streams: uploads (source frame, candidate lists, search items in NCH chunks), compute, downloads (search results,
+    # streams: uploads (source frame, candidate lists, search items in chunks), compute, downloads (search results,
     # transform results per chunk, filtered frame); chunk i of a kernel waits only for chunk i of its upload and chunk i of a
     # download waits only for chunk i of its kernel, so PCIe traffic hides behind the kernels.  Nothing is carried over from
     # one step to the next: the step ends when the last download has landed.
-    NCH = 4
     up, down = torch.cuda.Stream(), torch.cuda.Stream()
     use = lambda st: tb.check(L.tb_set_stream(C.c_void_p(st.cuda_stream)))
-    bounds = lambda n: [n * k // NCH for k in range(NCH + 1)]
-    mb, xb = bounds(len(me_items)), bounds(len(tx_items))
+    # search items: a small first chunk so the first kernel starts early; transform results: eight chunks so the last download is short
+    mb = [int(len(me_items) * f) for f in (0, 1 / 16, 1 / 4, 1 / 2, 1)]
+    xb = [len(tx_items) * k // 8 for k in range(9)]
     ME_SZ, TX_SZ = me_items.dtype.itemsize, tx_items.dtype.itemsize
 
     def step_e2e():
@@ -406,18 +406,18 @@ def run_gpu(args):
         tb.check(L.tb_frame_upload(cur.h, h_y, W, h_u, h_v, W // 2))
         tb.check(L.tb_memcpy_h2d(d_cand.ptr, h_cand, cand_bytes))
         up_done = []
-        for k in range(NCH):
+        for k in range(len(mb) - 1):
             tb.check(L.tb_memcpy_h2d(d_me.ptr + mb[k] * ME_SZ, h_me + mb[k] * ME_SZ, (mb[k + 1] - mb[k]) * ME_SZ))
             e = torch.cuda.Event(); e.record(up); up_done.append(e)
         use(stream)
         tb.check(L.tb_create_reference_frame(rec.h, pristine.h))
-        for k in range(NCH):
+        for k in range(len(mb) - 1):
             stream.wait_event(up_done[k])
             tb.check(L.tb_motion_estimate_batch(d_me.ptr + mb[k] * ME_SZ, mb[k + 1] - mb[k], d_cand.ptr, ESZ, BD, 0, 1, W, H, d_me_out.ptr + 8 * mb[k]))
         me_done = torch.cuda.Event(); me_done.record(stream)
         tb.check(L.tb_interp_batch(d_ip.ptr, len(ip_items), ESZ, BD, 1))
         tx_done = []
-        for k in range(NCH):
+        for k in range(len(xb) - 1):
             tb.check(L.tb_txfm_chain_batch(d_tx.ptr + xb[k] * TX_SZ, xb[k + 1] - xb[k], ESZ, BD, d_tx_out.ptr + 16 * xb[k]))
             e = torch.cuda.Event(); e.record(stream); tx_done.append(e)
         tb.check(L.tb_intra_batch(d_in.ptr, len(in_items), ESZ, BD))
@@ -426,7 +426,7 @@ def run_gpu(args):
         use(down)
         down.wait_event(me_done)
         tb.check(L.tb_memcpy_d2h_async(h_me_out, d_me_out.ptr, 8 * len(me_items)))
-        for k in range(NCH):
+        for k in range(len(xb) - 1):
             down.wait_event(tx_done[k])
             tb.check(L.tb_memcpy_d2h_async(h_tx_out + 16 * xb[k], d_tx_out.ptr + 16 * xb[k], 16 * (xb[k + 1] - xb[k])))
         down.wait_event(all_done)
