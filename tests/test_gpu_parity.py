@@ -356,6 +356,34 @@ def test_batch_motion_estimate(tb, hbd, bd, speed, bip):
 
 
 @pytest.mark.parametrize("hbd,bd", BD)
+@pytest.mark.parametrize("sizes,n,bip", [((8,), 160, 1), ((8, 16), 480, 1), ((8,), 96, 0)])
+def test_motion_estimate_small_blocks(tb, hbd, bd, sizes, n, bip):
+    """blocks of <= 64 samples: four searches share a warp on 8-bit frames (quad_motion_estimate), incl. the wide-SAD candidates of
+    8x8 partitions of 16x16 coding blocks; same results as the oracle"""
+    rng = np.random.default_rng(137 + n)
+    s = sfx(hbd)
+    w, h = 256, 192
+    esz = 2 if hbd else 1
+    href, cur, dref, dcur, _ = make_frames(tb, rng, w, h, bd, hbd)
+    items, call, meta = build_me_items(tb, rng, n, w, h, cur, href, dcur, dref, esz, sizes=sizes, speed=0)
+    d_items = tb.DevBuf.from_array(items); d_c = tb.DevBuf.from_array(call); d_out = tb.DevBuf(8 * n)
+    tb.check(tb.lib.tb_motion_estimate_batch(d_items.ptr, n, d_c.ptr, esz, bd, 0, bip, w, h, d_out.ptr))
+    got = d_out.download(tb.ME_RESULT, n)
+    bad = []
+    for i, (size, bw, bh, ox, oy, xpos, ypos, sign, cc, mvc, mvp, lam) in enumerate(meta):
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur.y[ypos:ypos + size, xpos:xpos + size]
+        m0 = (C.c_int16 * 2)(0, 0)
+        cands = (C.c_int16 * (2 * max(len(cc), 1)))(*[int(v) for v in cc.reshape(-1)] or [0, 0])
+        cost = getattr(O, "orc_motion_estimate_" + s)(P(org, oy * size + ox), P(href.Y, href.origin(0) + (ypos + oy) * href.sy + xpos + ox), size, href.sy, bw, bh, m0,
+                                                       (C.c_int16 * 2)(int(mvc[0]), int(mvc[1])), (C.c_int16 * 2)(int(mvp[0]), int(mvp[1])), C.c_double(lam), 0, bd,
+                                                       sign, w, h, xpos, ypos, cands, len(cc), bip)
+        if (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])) != (cost & 0xffffffff, m0[0], m0[1]):
+            bad.append((i, size, bw, bh, sign, len(cc), (int(got[i]["cost"]), int(got[i]["mvx"]), int(got[i]["mvy"])), (cost, m0[0], m0[1])))
+    assert not bad, (len(bad), bad[:6])
+
+
+@pytest.mark.parametrize("hbd,bd", BD)
 def test_motion_estimate_large_blocks(tb, hbd, bd):
     """64x64 .. 128x128 prediction blocks are searched by a whole CTA (four warps on row bands); same results as the oracle"""
     rng = np.random.default_rng(131)

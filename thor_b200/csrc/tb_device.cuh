@@ -15,6 +15,12 @@
 #ifndef TB_EXP_NOSUBPEL
 #define TB_EXP_NOSUBPEL 0  // 1: skip the sub-pel SADs (timing experiment only: measures the integer stages alone)
 #endif
+#ifndef TB_ME_QUAD
+#define TB_ME_QUAD 1  // four searches per warp for 8-bit blocks of <= 64 samples (quad_motion_estimate)
+#endif
+#ifndef TB_ME_QUAD_SIZE16
+#define TB_ME_QUAD_SIZE16 1  // also the 8x8 partitions of 16x16 coding blocks (wide-SAD candidate stage)
+#endif
 #ifndef TB_SAD_V4
 #define TB_SAD_V4 1  // 128-bit loads for block rows of >= 16 bytes
 #endif
@@ -1189,6 +1195,167 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
     sad = warp_sad_fastquarter<S>(orig_full, os, ref_full + s * (rx >> 2) + s * (ry >> 2) * rs, rs, c.width, c.height, spx, spy, qx, qy);
     cost = (sad >> shift) + mv_cost(c.lambda, quote_mv_bits(ry + s * qy - c.mvpy, rx + s * qx - c.mvpx));
     if (cost < cmin) { cmin = cost; xdq = s * qx; ydq = s * qy; }
+  }
+  out_mvx = (int)(int16_t)(optx + xdq);
+  out_mvy = (int)(int16_t)(opty + ydq);
+  out_cost = cmin < min_sad ? cmin : min_sad;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// a5 for small blocks: FOUR searches per warp, eight lanes each.  A search over a block of <= 64 samples spends most of its
+// instructions in stages that can use only 3-8 lanes (candidate list, hexagon rounds, the eight sub-pel probes) and in per-stage
+// scalar work (clipping, pricing, winner selection); sharing the warp between four searches issues that work once for four
+// (profiles/r1_ncu_summary.md section E: 4.2 k warp instructions per search, a third of the stalls are instruction fetches).
+// Every lane of a group carries its search's state; all collectives use the group's 8-lane mask, so groups diverge freely.
+// Same stages, visiting order and tie rules as warp_motion_estimate (8-bit samples, speed 0).
+// ---------------------------------------------------------------------------------------------------------------
+struct QuadItem {
+  const uint8_t *orig, *ref;
+  const int16_t *cand;
+  double lambda;
+  int os, rs, size, w, h, sign, xpos, ypos, mvpx, mvpy, mvcx, mvcy, ncand;
+};
+__device__ __forceinline__ int group_first_min(unsigned gm, uint32_t cost, bool valid, uint32_t &best) {  // lowest lane among the minima; -1 if none valid
+  const uint32_t c = valid ? cost : 0xffffffffu;
+  best = __reduce_min_sync(gm, c);
+  const unsigned who = __ballot_sync(gm, valid && c == best);
+  return who ? __ffs(who) - 1 : -1;
+}
+__device__ __noinline__ void quad_motion_estimate(const QuadItem &q, int fw, int fh, int bip, int &out_mvx, int &out_mvy, uint32_t &out_cost, unsigned &n_int) {
+  const int lane = lane_id(), gl = lane & 7, g0 = lane & 24;
+  const unsigned gm = 0xffu << g0;
+  const int s = q.sign ? -1 : 1;
+  uint32_t min_sad = 1u << 31;
+  int optx = 0, opty = 0;
+  int refx = (int)(int16_t)(((q.mvcx + 2) >> 2) << 2), refy = (int)(int16_t)(((q.mvcy + 2) >> 2) << 2);
+  n_int = 0;
+  // SAD + rate of one integer position (this lane's probe)
+  auto int_cost = [&](int cx, int cy, uint32_t &sad_out) {
+    const uint8_t *r = q.ref + s * (cx >> 2) + s * (cy >> 2) * q.rs;
+    sad_out = sad_partial<uint8_t>(q.orig, q.os, r, q.rs, q.w, q.h, 0, 1);
+  };
+  // ---- telescope (:531-561): 25 / 24 grid points per step, eight per pass; a lane keeps its earliest minimum, the group then takes the
+  // smallest cost and, among equal costs, the earliest visiting index
+  for (int step = 32; step >= 4; step >>= 1) {
+    const int n = step < 32 ? 24 : 25;
+    uint32_t bc = 0xffffffffu;
+    int bidx = 64, bx = 0, by = 0;
+    for (int pass = 0; pass < 4; pass++) {
+      const int vi = pass * 8 + gl;
+      if (vi < n) {
+        int idx = vi;
+        if (step < 32 && idx >= 12) idx++;
+        int cx = (int)(int16_t)(refx + (idx % 5 - 2) * step), cy = (int)(int16_t)(refy + (idx / 5 - 2) * step);
+        clip_mv(cx, cy, q.ypos, q.xpos, fw, fh, q.size, q.size, q.sign);
+        uint32_t sad;
+        int_cost(cx, cy, sad);
+        const uint32_t c = sad + mv_cost(q.lambda, quote_mv_bits(cy - q.mvpy, cx - q.mvpx));
+        if (c < bc) { bc = c; bidx = vi; bx = cx; by = cy; }
+      }
+    }
+    n_int += n;
+    const uint32_t m = __reduce_min_sync(gm, bc);
+    const unsigned mi = __reduce_min_sync(gm, bc == m ? (unsigned)bidx : 64u);
+    const unsigned who = __ballot_sync(gm, bc == m && (unsigned)bidx == mi);
+    const int wl = __ffs(who) - 1;
+    const int wx = __shfl_sync(gm, bx, wl), wy = __shfl_sync(gm, by, wl);
+    if (m < min_sad) { min_sad = m; optx = wx; opty = wy; }
+    refx = optx;
+    refy = opty;
+  }
+  // ---- candidates (:564-581); blocks of a 16x16 coding block use the five-position wide SAD
+  for (int base = 0; base < q.ncand; base += 8) {
+    const int n = min(8, q.ncand - base);
+    const bool valid = gl < n;
+    int cx = 0, cy = 0;
+    uint32_t cost = 0;
+    if (valid) {
+      cx = (int)(int16_t)(q.cand[2 * (base + gl)] << 2);
+      cy = (int)(int16_t)(q.cand[2 * (base + gl) + 1] << 2);
+      clip_mv(cx, cy, q.ypos, q.xpos, fw, fh, q.size, q.size, q.sign);
+      uint32_t sad;
+      if (q.size == 16) {
+        const int offs[5] = {-3, -1, 0, 1, 3};
+        const uint8_t *r = q.ref + s * (cx >> 2) + s * (cy >> 2) * q.rs;
+        uint32_t b = 0xffffffffu;
+        int bxo = 0;
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+          const uint32_t v = sad_partial<uint8_t>(q.orig, q.os, r + offs[t], q.rs, q.w, q.h, 0, 1);
+          if (v < b) { b = v; bxo = offs[t]; }
+        }
+        sad = b;
+        cx = (int)(int16_t)(cx + (s * bxo << 2));
+      } else
+        int_cost(cx, cy, sad);
+      cost = sad + mv_cost(q.lambda, quote_mv_bits(cy - q.mvpy, cx - q.mvpx));
+    }
+    n_int += (q.size == 16 ? 5 : 1) * n;
+    uint32_t best;
+    const int wl = group_first_min(gm, cost, valid, best);
+    const int wx = __shfl_sync(gm, cx, wl < 0 ? g0 : wl), wy = __shfl_sync(gm, cy, wl < 0 ? g0 : wl);
+    if (wl >= 0 && best < min_sad) { min_sad = best; optx = wx; opty = wy; }
+  }
+  refx = optx;
+  refy = opty;
+  // ---- hexagon refinement (:583-616)
+  {
+    int start = 0, end = 5;
+    for (int step = 1; step < 6; step++) {
+      const int diy[6] = {1, 2, 1, -1, -2, -1}, dix[6] = {-1, 0, 1, 1, 0, -1};
+      const int n = ((end - start + 6) % 6) + 1;
+      const bool valid = gl < n;
+      const int dir = (start + gl) % 6;
+      int cx = (int)(int16_t)(refx + diy[dir] * 4), cy = (int)(int16_t)(refy + dix[dir] * 4);
+      uint32_t cost = 0;
+      if (valid) {
+        clip_mv(cx, cy, q.ypos, q.xpos, fw, fh, q.size, q.size, q.sign);
+        uint32_t sad;
+        int_cost(cx, cy, sad);
+        cost = sad + mv_cost(q.lambda, quote_mv_bits(cy - q.mvpy, cx - q.mvpx));
+      }
+      n_int += n;
+      uint32_t best;
+      const int wl = group_first_min(gm, cost, valid, best);
+      const int wx = __shfl_sync(gm, cx, wl), wy = __shfl_sync(gm, cy, wl);
+      int best_dir = -1;
+      if (best < min_sad) { min_sad = best; optx = wx; opty = wy; best_dir = (start + (wl - g0)) % 6; }
+      refx = optx;
+      refy = opty;
+      start = best_dir ? best_dir - 1 : 5;
+      end = start + 2;
+      end -= (end >= 6) * 6;
+      if (best_dir < 0) break;
+    }
+  }
+  // ---- half-pel, then quarter-pel probes (:625-663): probe i on lane i - 1 of the group
+  int ydh = 0, xdh = 0, ydq = 0, xdq = 0;
+  uint32_t cmin = min_sad;
+  for (int stage = 0; stage < 2; stage++) {
+    const int8_t *dm = stage ? c_qm : c_hm, *dn = stage ? c_qn : c_hn;
+    const int cy = (int)(int16_t)(opty + dm[gl + 1]), cx = (int)(int16_t)(optx + dn[gl + 1]);
+    int hi, vi, xf, yf;
+    split_mv(cx, cy, q.sign, 2, fw, fh, q.xpos, q.ypos, q.w, q.h, hi, vi, xf, yf);
+    const uint8_t *ip = q.ref + vi * q.rs + hi;
+    const int RH = q.h >= 8 ? 8 : q.h, nseg = q.h / RH, units = (q.w >> 2) * nseg;
+    uint32_t sad = 0;
+    for (int u = 0; u < units; u++) {
+      const int strip = u / nseg, seg = u - strip * nseg;
+      sad += strip_sad_subpel_u8(q.orig, q.os, ip, q.rs, strip * 4, seg * RH, RH, xf, yf, bip);
+    }
+    const uint32_t cost = sad + mv_cost(q.lambda, quote_mv_bits(cy - q.mvpy, cx - q.mvpx));
+    int yd = 0, xd = 0;
+    for (int i = 1; i <= 8; i++) {
+      const uint32_t ci = __shfl_sync(gm, cost, g0 + i - 1);
+      if (ci < cmin) { cmin = ci; yd = dm[i]; xd = dn[i]; }
+    }
+    if (stage == 0) {
+      ydh = yd; xdh = xd;
+      optx = (int)(int16_t)(optx + xdh);
+      opty = (int)(int16_t)(opty + ydh);
+    } else {
+      ydq = yd; xdq = xd;
+    }
   }
   out_mvx = (int)(int16_t)(optx + xdq);
   out_mvy = (int)(int16_t)(opty + ydq);

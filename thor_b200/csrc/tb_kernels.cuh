@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
       me_run_item<S, ME_TEAM_WARPS>(items, idx[k], cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
     }
   }
-  // phase 2: one warp per search, drawn four at a time from the caller's array (neighbouring items share samples: keep them on
-  // neighbouring warps); team items were done in phase 1
+  // phase 2: drawn four at a time from the caller's array (neighbouring items share samples: keep them on neighbouring warps); team
+  // items were done in phase 1.  Four 8-bit blocks of <= 64 samples share the warp (quad_motion_estimate), anything else gets the warp.
   {
     MeTeam<1> tm;
     tm.xch = nullptr; tm.warp = 0; tm.phase = 0;
@@ -179,6 +179,41 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
       if (lane_id() == 0) k = atomicAdd(&meta[98], TB_ME_DRAW);
       k = __shfl_sync(FULL, k, 0);
       if (k >= n) break;
+#if TB_ME_QUAD
+      if (sizeof(S) == 1 && speed == 0 && TB_ME_DRAW == 4) {
+        const int mine = k + (lane_id() >> 3);
+        bool ok = true;
+        tb_me_item_t q;
+        if (mine < n) {
+          q = items[mine];
+          ok = (int)q.width * (int)q.height <= 64 && (TB_ME_QUAD_SIZE16 || q.size != 16) && !((q.width | q.height) & 3) && !(q.ostride & 3) && !(q.rstride & 3) && !((uintptr_t)q.orig & 3);
+        }
+        if (__all_sync(FULL, ok)) {
+          if (mine < n) {
+            QuadItem qi;
+            qi.orig = (const uint8_t *)q.orig; qi.ref = (const uint8_t *)q.ref; qi.cand = cand + 2 * (size_t)q.cand_ofs; qi.lambda = q.lambda;
+            qi.os = q.ostride; qi.rs = q.rstride; qi.size = q.size; qi.w = q.width; qi.h = q.height; qi.sign = q.sign; qi.xpos = q.xpos; qi.ypos = q.ypos;
+            qi.mvpx = q.mvp_x; qi.mvpy = q.mvp_y; qi.mvcx = q.mvc_x; qi.mvcy = q.mvc_y; qi.ncand = q.ncand;
+            int mx, my;
+            uint32_t cost;
+            unsigned n_int;
+            quad_motion_estimate(qi, fw, fh, bip, mx, my, cost, n_int);
+            if ((lane_id() & 7) == 0) {
+              out[mine].mvx = (int16_t)mx; out[mine].mvy = (int16_t)my; out[mine].cost = cost;
+              if (stats) {
+                atomicAdd(&stats[0], 1ull);
+                atomicAdd(&stats[1], (unsigned long long)n_int);
+                atomicAdd(&stats[2], 16ull);
+                atomicAdd(&stats[3], (unsigned long long)(n_int + 1) * q.width * q.height);
+                atomicAdd(&stats[4], 16ull * ((q.width + 5) * (q.height + 5) + q.width * q.height));
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+      }
+#endif
       for (int it = k; it < min(k + TB_ME_DRAW, n); it++) {
         if (nteam && me_class(items[it].width, items[it].height, speed) >= 16) continue;
         me_run_item<S, 1>(items, it, cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
