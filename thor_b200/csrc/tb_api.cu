@@ -383,7 +383,7 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
   idx = meta + 128;
   ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "me scratch");
   const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
-  const MeClassOf cls{speed};
+  const MeClassOf cls{speed, (TB_ME_QUAD && sample_bytes == 1 && speed == 0) ? 1 : 0};
   LAUNCH((sched_hist_kernel<tb_me_item_t, MeClassOf>), sgrid, 256, 0, items, n, cls, meta);
   LAUNCH(sched_scan_kernel, 1, 32, 0, meta);
   LAUNCH((sched_scatter_kernel<tb_me_item_t, MeClassOf>), sgrid, 256, 0, items, n, cls, meta, idx);

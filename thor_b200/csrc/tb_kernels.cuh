@@ -77,10 +77,14 @@ __device__ __forceinline__ int me_class(int w, int h, int speed) {
 // items, 97 = team cursor, 98 = warp cursor, 99 = number of listed items, 100 = group cursor.  A class functor returns the
 // class (0..31; >= 16: searched/transformed by the whole CTA) of an item, or -1 when the item is not listed.
 struct MeClassOf {
-  int speed;
+  int speed, quad;  // quad: 8-bit samples and speed 0 -> blocks of <= 64 samples are listed too (class 1) and searched four per warp
   __device__ __forceinline__ int operator()(const tb_me_item_t &q) const {
     const int c = me_class(q.width, q.height, speed);
-    return c >= 16 ? c : -1;  // only team items are listed; the others are drawn from the caller's array in its own order
+    if (c >= 16) return c;  // team items, largest first
+    if (quad && (int)q.width * (int)q.height <= 64 && (TB_ME_QUAD_SIZE16 || q.size != 16) && !((q.width | q.height) & 3) && !(q.ostride & 3) && !(q.rstride & 3) &&
+        !((uintptr_t)q.orig & 3))
+      return 1;
+    return -1;  // the others are drawn from the caller's array in its own order
   }
 };
 struct TxClassOf {  // transform blocks > 8x8 are listed (one warp each, the CTA for >= 64x64); 4x4 / 8x8 run one per thread
@@ -155,7 +159,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
 #else
   SubpelShared *sps = nullptr;
 #endif
-  const int nteam = meta[96];
+  const int nteam = meta[96], nlisted = meta[99];
+  const int quad = TB_ME_QUAD && sizeof(S) == 1 && speed == 0;
   // phase 1: the CTA as a team on the large blocks
   {
     MeTeam<ME_TEAM_WARPS> tm;
@@ -169,57 +174,60 @@ __global__ void __launch_bounds__(CTA_THREADS, TB_ME_MINBLOCKS) me_batch_kernel(
       me_run_item<S, ME_TEAM_WARPS>(items, idx[k], cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
     }
   }
-  // phase 2: drawn four at a time from the caller's array (neighbouring items share samples: keep them on neighbouring warps); team
-  // items were done in phase 1.  Four 8-bit blocks of <= 64 samples share the warp (quad_motion_estimate), anything else gets the warp.
+  // phase 2: the searches that are neither team nor quad items, one warp each, drawn four at a time from the caller's array
+  // (neighbouring items share samples: keep them on neighbouring warps)
+  const MeClassOf cls{speed, quad};
   {
     MeTeam<1> tm;
     tm.xch = nullptr; tm.warp = 0; tm.phase = 0;
     for (;;) {
       int k = 0;
-      if (lane_id() == 0) k = atomicAdd(&meta[98], TB_ME_DRAW);
+      if (lane_id() == 0) k = atomicAdd(&meta[100], TB_ME_DRAW);
       k = __shfl_sync(FULL, k, 0);
       if (k >= n) break;
-#if TB_ME_QUAD
-      if (sizeof(S) == 1 && speed == 0 && TB_ME_DRAW == 4) {
-        const int mine = k + (lane_id() >> 3);
-        bool ok = true;
-        tb_me_item_t q;
-        if (mine < n) {
-          q = items[mine];
-          ok = (int)q.width * (int)q.height <= 64 && (TB_ME_QUAD_SIZE16 || q.size != 16) && !((q.width | q.height) & 3) && !(q.ostride & 3) && !(q.rstride & 3) && !((uintptr_t)q.orig & 3);
-        }
-        if (__all_sync(FULL, ok)) {
-          if (mine < n) {
-            QuadItem qi;
-            qi.orig = (const uint8_t *)q.orig; qi.ref = (const uint8_t *)q.ref; qi.cand = cand + 2 * (size_t)q.cand_ofs; qi.lambda = q.lambda;
-            qi.os = q.ostride; qi.rs = q.rstride; qi.size = q.size; qi.w = q.width; qi.h = q.height; qi.sign = q.sign; qi.xpos = q.xpos; qi.ypos = q.ypos;
-            qi.mvpx = q.mvp_x; qi.mvpy = q.mvp_y; qi.mvcx = q.mvc_x; qi.mvcy = q.mvc_y; qi.ncand = q.ncand;
-            int mx, my;
-            uint32_t cost;
-            unsigned n_int;
-            quad_motion_estimate(qi, fw, fh, bip, mx, my, cost, n_int);
-            if ((lane_id() & 7) == 0) {
-              out[mine].mvx = (int16_t)mx; out[mine].mvy = (int16_t)my; out[mine].cost = cost;
-              if (stats) {
-                atomicAdd(&stats[0], 1ull);
-                atomicAdd(&stats[1], (unsigned long long)n_int);
-                atomicAdd(&stats[2], 16ull);
-                atomicAdd(&stats[3], (unsigned long long)(n_int + 1) * q.width * q.height);
-                atomicAdd(&stats[4], 16ull * ((q.width + 5) * (q.height + 5) + q.width * q.height));
-              }
-            }
-          }
-          __syncwarp();
-          continue;
-        }
-      }
-#endif
       for (int it = k; it < min(k + TB_ME_DRAW, n); it++) {
-        if (nteam && me_class(items[it].width, items[it].height, speed) >= 16) continue;
+        if (nlisted && cls(items[it]) >= 0) continue;
         me_run_item<S, 1>(items, it, cand, bitdepth, speed, bip, fw, fh, out, stats, tm, sps);
       }
     }
   }
+#if TB_ME_QUAD
+  // phase 3: the listed small blocks (8-bit, <= 64 samples), four per warp (quad_motion_estimate).  They come last: the launch
+  // ends on its cheapest searches, and the two code paths do not alternate in the instruction cache.
+  if (sizeof(S) == 1) {
+    const int nsmall = nlisted - nteam;
+    for (;;) {
+      int k = 0;
+      if (lane_id() == 0) k = atomicAdd(&meta[98], 4);
+      k = __shfl_sync(FULL, k, 0);
+      if (k >= nsmall) break;
+      const int slot = k + (lane_id() >> 3);
+      if (slot < nsmall) {
+        const int mine = idx[nteam + slot];
+        const tb_me_item_t q = items[mine];
+        QuadItem qi;
+        qi.orig = (const uint8_t *)q.orig; qi.ref = (const uint8_t *)q.ref; qi.cand = cand + 2 * (size_t)q.cand_ofs; qi.lambda = q.lambda;
+        qi.os = q.ostride; qi.rs = q.rstride; qi.size = q.size; qi.w = q.width; qi.h = q.height; qi.sign = q.sign; qi.xpos = q.xpos; qi.ypos = q.ypos;
+        qi.mvpx = q.mvp_x; qi.mvpy = q.mvp_y; qi.mvcx = q.mvc_x; qi.mvcy = q.mvc_y; qi.ncand = q.ncand;
+        int mx, my;
+        uint32_t cost;
+        unsigned n_int;
+        quad_motion_estimate(qi, fw, fh, bip, mx, my, cost, n_int);
+        if ((lane_id() & 7) == 0) {
+          out[mine].mvx = (int16_t)mx; out[mine].mvy = (int16_t)my; out[mine].cost = cost;
+          if (stats) {
+            atomicAdd(&stats[0], 1ull);
+            atomicAdd(&stats[1], (unsigned long long)n_int);
+            atomicAdd(&stats[2], 16ull);
+            atomicAdd(&stats[3], (unsigned long long)(n_int + 1) * q.width * q.height);
+            atomicAdd(&stats[4], 16ull * ((q.width + 5) * (q.height + 5) + q.width * q.height));
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+#endif
 }
 
 template <class S>
