@@ -21,6 +21,9 @@
 #ifndef TB_ME_QUAD_SIZE16
 #define TB_ME_QUAD_SIZE16 1  // also the 8x8 partitions of 16x16 coding blocks (wide-SAD candidate stage)
 #endif
+#ifndef TB_QUAD_HALFPEL_PLANES
+#define TB_QUAD_HALFPEL_PLANES 0  // group form of the half-pel planes inside quad_motion_estimate (untested on hardware: off)
+#endif
 #ifndef TB_SAD_V4
 #define TB_SAD_V4 1  // 128-bit loads for block rows of >= 16 bytes
 #endif
@@ -759,19 +762,22 @@ __device__ __forceinline__ void row12_u8(const uint8_t *p, uint32_t &b0, uint32_
   const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
 }
+// NL = 32: the warp works on one search; NL = 8: each group of eight lanes on its own search (quad_motion_estimate)
+template <int NL>
 __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os, const uint8_t *ref, int rs, int w, int hfull, int bx, int by, const int8_t *dxs,
                                                        const int8_t *dys, int sign, int bip, int pic_w, int pic_h, int xpos, int ypos, int row0, int h) {
-  const int lane = lane_id(), t = lane & 7;
+  const int lane = lane_id(), t = lane & 7, sub = lane & (NL - 1);
+  const unsigned gm = NL == 32 ? FULL : 0xffu << (lane & 24);
   const int mvx = (int)(int16_t)(bx + dxs[t + 1]), mvy = (int)(int16_t)(by + dys[t + 1]);
   int hi, vi, xf, yf;
   split_mv(mvx, mvy, sign, 2, pic_w, pic_h, xpos, ypos, w, hfull, hi, vi, xf, yf);
-  const int hmin = __reduce_min_sync(FULL, hi), vmin = __reduce_min_sync(FULL, vi);
+  const int hmin = __reduce_min_sync(gm, hi), vmin = __reduce_min_sync(gm, vi);
   const int ho = hi - hmin, vo = vi - vmin;
   const int cls = (xf == 2 && yf == 0) ? 0 : ((xf == 0 && yf == 2) ? 1 : ((xf == 2 && yf == 2) ? 2 : 3));
-  const unsigned mH = __ballot_sync(FULL, cls == 0), mV = __ballot_sync(FULL, cls == 1);
-  const int voH = __shfl_sync(FULL, vo, mH ? __ffs(mH) - 1 : 0), hoV = __shfl_sync(FULL, ho, mV ? __ffs(mV) - 1 : 0);
+  const unsigned mH = __ballot_sync(gm, cls == 0), mV = __ballot_sync(gm, cls == 1);
+  const int voH = __shfl_sync(gm, vo, mH ? __ffs(mH) - 1 : (lane & ~(NL - 1))), hoV = __shfl_sync(gm, ho, mV ? __ffs(mV) - 1 : (lane & ~(NL - 1)));
   const bool ok = bip < 2 && cls != 3 && ho <= 1 && vo <= 1 && (cls != 0 || vo == voH) && (cls != 1 || ho == hoV);
-  if (!__all_sync(FULL, ok)) return 0xffffffffu;
+  if (!__all_sync(gm, ok)) return 0xffffffffu;
   const int8_t *fh = c_luma_taps[bip ? 1 : 0][2];
   const uint32_t tlo = pack_s8x4(fh[0], fh[1], fh[2], fh[3]), thi = pack_s8x4(fh[4], fh[5], 0, 0);
   const int ns = w >> 2, lns = ilog2(ns);
@@ -780,7 +786,7 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
   uint32_t aH0 = 0, aH1 = 0, aV0 = 0, aV1 = 0, aC00 = 0, aC01 = 0, aC10 = 0, aC11 = 0;  // aC<vo><ho>
   // ---- H pass: block rows y (plane rows y + voH), plane columns 4 s .. 4 s + 4
   if (mH) {
-    for (int u = lane; u < h * ns; u += 32) {
+    for (int u = sub; u < h * ns; u += NL) {
       const int y = u >> lns, st = u & (ns - 1);
       uint32_t b0, b1, b2;
       row12_u8(rb + (y + voH) * rs + 4 * st - 2, b0, b1, b2);
@@ -797,7 +803,7 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
   }
   // ---- V pass: plane rows r = 0 .. h, plane columns 4 s + hoV .. + 3; row r serves block row r (vo 0) and r - 1 (vo 1)
   if (mV) {
-    for (int u = lane; u < (h + 1) * ns; u += 32) {
+    for (int u = sub; u < (h + 1) * ns; u += NL) {
       const int r = u >> lns, st = u & (ns - 1);
       const uint8_t *p = rb + (r - 2) * rs + 4 * st + hoV;
       const uintptr_t a = (uintptr_t)p;
@@ -822,7 +828,7 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
   // ---- C pass: plane rows r = 0 .. h, plane columns 4 s .. 4 s + 4
   {
     const uint32_t a_lo = 0x01010000u, b_lo = 0x02020100u, b_hi = 0x00000001u;
-    for (int u = lane; u < (h + 1) * ns; u += 32) {
+    for (int u = sub; u < (h + 1) * ns; u += NL) {
       const int r = u >> lns, st = u & (ns - 1);
       const uint8_t *p = rb + r * rs + 4 * st - 2;
       int acc[5] = {8, 8, 8, 8, 8};
@@ -855,8 +861,8 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
       }
     }
   }
-  aH0 = warp_sum(aH0); aH1 = warp_sum(aH1); aV0 = warp_sum(aV0); aV1 = warp_sum(aV1);
-  aC00 = warp_sum(aC00); aC01 = warp_sum(aC01); aC10 = warp_sum(aC10); aC11 = warp_sum(aC11);
+  aH0 = __reduce_add_sync(gm, aH0); aH1 = __reduce_add_sync(gm, aH1); aV0 = __reduce_add_sync(gm, aV0); aV1 = __reduce_add_sync(gm, aV1);
+  aC00 = __reduce_add_sync(gm, aC00); aC01 = __reduce_add_sync(gm, aC01); aC10 = __reduce_add_sync(gm, aC10); aC11 = __reduce_add_sync(gm, aC11);
   if (cls == 0) return ho ? aH1 : aH0;
   if (cls == 1) return vo ? aV1 : aV0;
   return vo ? (ho ? aC11 : aC10) : (ho ? aC01 : aC00);
@@ -1145,7 +1151,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
       uint32_t sad = 0xffffffffu;
 #if !TB_EXP_NOSUBPEL && TB_HALFPEL_PLANES
       if (sizeof(S) == 1 && stage == 0 && !((bx | by) & 3))
-        sad = halfpel_stage_sads_u8((const uint8_t *)orig_full, os, (const uint8_t *)ref_full, rs, c.width, c.height, bx, by, dn, dm, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos,
+        sad = halfpel_stage_sads_u8<32>((const uint8_t *)orig_full, os, (const uint8_t *)ref_full, rs, c.width, c.height, bx, by, dn, dm, c.sign, c.bip, c.fw, c.fh, c.xpos, c.ypos,
                                     row0, band_h);
 #endif
 #if !TB_EXP_NOSUBPEL && TB_SUBPEL_SHARED
@@ -1338,10 +1344,17 @@ __device__ __noinline__ void quad_motion_estimate(const QuadItem &q, int fw, int
     split_mv(cx, cy, q.sign, 2, fw, fh, q.xpos, q.ypos, q.w, q.h, hi, vi, xf, yf);
     const uint8_t *ip = q.ref + vi * q.rs + hi;
     const int RH = q.h >= 8 ? 8 : q.h, nseg = q.h / RH, units = (q.w >> 2) * nseg;
-    uint32_t sad = 0;
-    for (int u = 0; u < units; u++) {
-      const int strip = u / nseg, seg = u - strip * nseg;
-      sad += strip_sad_subpel_u8(q.orig, q.os, ip, q.rs, strip * 4, seg * RH, RH, xf, yf, bip);
+    uint32_t sad = 0xffffffffu;
+#if TB_HALFPEL_PLANES && TB_QUAD_HALFPEL_PLANES
+    if (stage == 0 && !((optx | opty) & 3))  // three shared planes instead of eight interpolations; also avoids the centre-kernel / general divergence
+      sad = halfpel_stage_sads_u8<8>(q.orig, q.os, q.ref, q.rs, q.w, q.h, optx, opty, dn, dm, q.sign, bip, fw, fh, q.xpos, q.ypos, 0, q.h);
+#endif
+    if (sad == 0xffffffffu) {
+      sad = 0;
+      for (int u = 0; u < units; u++) {
+        const int strip = u / nseg, seg = u - strip * nseg;
+        sad += strip_sad_subpel_u8(q.orig, q.os, ip, q.rs, strip * 4, seg * RH, RH, xf, yf, bip);
+      }
     }
     const uint32_t cost = sad + mv_cost(q.lambda, quote_mv_bits(cy - q.mvpy, cx - q.mvpx));
     int yd = 0, xd = 0;
