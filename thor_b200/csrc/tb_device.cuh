@@ -22,7 +22,7 @@
 #define TB_ME_QUAD_SIZE16 1  // also the 8x8 partitions of 16x16 coding blocks (wide-SAD candidate stage)
 #endif
 #ifndef TB_QUAD_HALFPEL_PLANES
-#define TB_QUAD_HALFPEL_PLANES 0  // group form of the half-pel planes inside quad_motion_estimate (untested on hardware: off)
+#define TB_QUAD_HALFPEL_PLANES 0  // group form of the half-pel planes inside quad_motion_estimate: bit-exact, measured slower (cb8 class 6.2 vs 5.3 ms)
 #endif
 #ifndef TB_SAD_V4
 #define TB_SAD_V4 1  // 128-bit loads for block rows of >= 16 bytes
