@@ -432,7 +432,7 @@ int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, in
   LAUNCH((sched_hist_kernel<tb_txfm_item_t, TxClassOf>), sgrid, 256, 0, items, n, cls, meta);
   LAUNCH(sched_scan_kernel, 1, 32, 0, meta);
   LAUNCH((sched_scatter_kernel<tb_txfm_item_t, TxClassOf>), sgrid, 256, 0, items, n, cls, meta, idx);
-  const int grid = std::min((n + 31) / 32, g.sm_count * 5);  // persistent: every CTA resident (launch bounds: 5 per SM)
+  const int grid = std::min((n + 31) / 32, g.sm_count * TB_TX_MINBLOCKS);  // persistent: every CTA resident
   if (sample_bytes == 1) LAUNCH(txfm_chain_kernel<uint8_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
   else LAUNCH(txfm_chain_kernel<uint16_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
   ck(cudaFreeAsync(meta, g.stream), "txfm scratch");

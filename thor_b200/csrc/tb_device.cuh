@@ -47,6 +47,9 @@
 #ifndef TB_SAD_TILE
 #define TB_SAD_TILE 0  // (measured on B200: 0 is faster, 21.7 vs 24.7 ms) 1: issue all loads of a row tile before use; 0: one word at a time
 #endif
+#ifndef TB_TX_MINBLOCKS
+#define TB_TX_MINBLOCKS 6  // __launch_bounds__(128, N) of the transform-chain kernel (measured: 4: 5.84 ms, 5: 5.37, 6: 5.12)
+#endif
 #ifndef TB_ME_MINBLOCKS
 #define TB_ME_MINBLOCKS 6  // __launch_bounds__(128, N) of the motion-search kernel: registers/thread <= 65536 / (128 N)
 #endif

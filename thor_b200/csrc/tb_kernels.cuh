@@ -575,7 +575,7 @@ __device__ __noinline__ void tx_big_chain(const tb_txfm_item_t &q, int bitdepth,
 // (thread_txfm4 in registers, thread_txfm8 in per-thread local arrays; consecutive items are spatial neighbours, so the
 // lanes' loads and stores coalesce).
 template <class S>
-__global__ void __launch_bounds__(CTA_THREADS, 5) txfm_chain_kernel(const tb_txfm_item_t *items, int n, const int *idx, int *meta, int bitdepth, tb_txfm_result_t *out) {
+__global__ void __launch_bounds__(CTA_THREADS, TB_TX_MINBLOCKS) txfm_chain_kernel(const tb_txfm_item_t *items, int n, const int *idx, int *meta, int bitdepth, tb_txfm_result_t *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long red[WARPS_PER_CTA];
   __shared__ int bc, s_next;
