@@ -136,7 +136,7 @@ static void run_txfm(const job_t *j, int lo, int hi) {
     if (q->coeffq) memcpy(q->coeffq, cq, (size_t)qs * qs * 2);
     out[i].ssd = ssd;
     out[i].cbp = cbp;
-    out[i].pad = 0;
+    out[i].bits = 0;
   }
 }
 
