@@ -106,3 +106,12 @@ def test_no_cpu_fallback():
     # the product never links the oracle
     out = subprocess.run(["ldd", t.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "thorref" not in out
+
+
+def test_cpu_bench_driver_compiles_against_the_header():
+    """oracle/cpu_bench.c shares the work-item structs of include/thor_b200.h: a field rename must not leave a stale prebuilt .so behind
+    (build() recompiles it; this is the two-second version of that check)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=gnu99", "-fsyntax-only", "-w", os.path.join(root, "oracle", "cpu_bench.c")], capture_output=True, text=True, cwd=os.path.join(root, "oracle"))
+    assert r.returncode == 0, r.stderr[-800:]
