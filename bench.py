@@ -499,11 +499,12 @@ def run_gpu(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    traffic, ncu_roofs = None, None
     try:  # DRAM bytes of one launch of this kernel from the committed ncu capture (same workload), profiles/r1_ncu_summary.md
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["me_batch_kernel"]
         if tr["items"] == len(me_items):
             traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+            ncu_roofs = {k: tr[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "warps_active_pct") if k in tr}
     except Exception:
         pass
     alg_bytes = float(st[3] + st[4]) * ESZ  # w*h*s per integer candidate (+ one read of the original), ((w+5)(h+5)+w*h)*s per sub-pel probe
@@ -525,7 +526,7 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"kernel": "me_batch_kernel<uint8_t> (a1/a2/a5/a7 fused motion search)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "algorithmic_bytes": int(alg_bytes), "ms_per_launch": round(me_ms, 3), "share_of_step": round(me_ms / (ms / args.steps), 3),
+                     "traffic": traffic, "ncu": ncu_roofs, "algorithmic_bytes": int(alg_bytes), "ms_per_launch": round(me_ms, 3), "share_of_step": round(me_ms / (ms / args.steps), 3),
                      "searches": int(st[0]), "int_block_sads": int(st[1]), "subpel_probes": int(st[2])},
     }
     if not args.no_cpu:
