@@ -57,3 +57,22 @@ def test_two_rank_sharded_encode_equals_monolithic(tmp_path):
     a, b = open(mono, "rb").read(), open(os.path.join(tmp, "sharded.bit"), "rb").read()
     assert len(sg.split_chunks(a)) == n
     assert a == b
+
+
+@needs_ref
+def test_three_rank_six_segments(tmp_path):
+    """several segments per rank, three ranks: the merge must stitch segments within a rank and across ranks"""
+    import torch.multiprocessing as mp
+    tmp = str(tmp_path)
+    w, h, n, period = 64, 64, 49, 8
+    synth_yuv(os.path.join(tmp, "in.yuv"), w, h, n, 8, seed=10)
+    mono = os.path.join(tmp, "mono.bit")
+    r = subprocess.run([THORENC] + HDB + ["-qp", "32", "-f", "30", "-intra_period", str(period), "-if", os.path.join(tmp, "in.yuv"), "-of", mono, "-width", str(w),
+                        "-height", str(h), "-n", str(n)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert [len(p) for p in sg.plan_segments(n, period, 3)] == [2, 2, 2]
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(3, port, tmp, w, h, n, period), nprocs=3, join=True)
+    a, b = open(mono, "rb").read(), open(os.path.join(tmp, "sharded.bit"), "rb").read()
+    assert len(sg.split_chunks(a)) == n
+    assert a == b
