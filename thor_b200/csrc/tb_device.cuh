@@ -38,15 +38,6 @@
 // shrinks L1.  Kept as a measured alternative.
 #define TB_SUBPEL_SHARED 0
 #endif
-#ifndef TB_SUBPEL_RING
-#define TB_SUBPEL_RING 0  // 1: ring-indexed filtered-row window unrolled by six (measured slower on B200: larger code)
-#endif
-#ifndef TB_SUBPEL_RH16
-#define TB_SUBPEL_RH16 0
-#endif
-#ifndef TB_SAD_TILE
-#define TB_SAD_TILE 0  // (measured on B200: 0 is faster, 21.7 vs 24.7 ms) 1: issue all loads of a row tile before use; 0: one word at a time
-#endif
 #ifndef TB_TX_MINBLOCKS
 #define TB_TX_MINBLOCKS 6  // __launch_bounds__(128, N) of the transform-chain kernel (measured: 4: 5.84 ms, 5: 5.37, 6: 5.12)
 #endif
@@ -102,26 +93,6 @@ template <class S> __device__ __forceinline__ int word_px(uint32_t w, int i) {
 // `o` must be 4-byte aligned with an even word pitch (original blocks always are); `r` arbitrary.
 // Lanes sub..sub+nl-1 of a group share the block; returns this lane's partial sum.
 // ---------------------------------------------------------------------------------------------------------------
-// SAD of an NR-row x NW-word tile: all 2*NR*NW + NR loads are issued before the first use (memory-level parallelism;
-// the per-word loop of the first version waited ~one L1 latency per word).
-template <class S, int NW, int NR>
-__device__ __forceinline__ uint32_t sad_tile(const uint32_t *q, int qstep, const uint32_t *a, int astep, unsigned sh) {
-  uint32_t qv[NR][NW + 1], av[NR][NW];
-#pragma unroll
-  for (int r = 0; r < NR; r++) {
-#pragma unroll
-    for (int c = 0; c <= NW; c++) qv[r][c] = __ldg(q + r * qstep + c);  // frames are read-only here: LDG.CONSTANT
-#pragma unroll
-    for (int c = 0; c < NW; c++) av[r][c] = __ldg(a + r * astep + c);
-  }
-  uint32_t acc = 0;
-#pragma unroll
-  for (int r = 0; r < NR; r++)
-#pragma unroll
-    for (int c = 0; c < NW; c++) acc += word_sad<S>(av[r][c], __funnelshift_r(qv[r][c], qv[r][c + 1], sh));
-  return acc;
-}
-
 // Rows of >= 16 bytes with 128-bit loads: one aligned LDG.128 per 16 reference bytes (+1 per row) and one per 16 original
 // bytes instead of eight 32-bit loads — the search is bound by L1 wavefronts (59 % of the l1tex data-pipe peak in ncu), so
 // request count matters more than bytes.  J = word offset of the row inside its first 16-byte chunk (uniform per lane group:
@@ -169,22 +140,6 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   }
 #endif
   uint32_t acc = 0;
-#if TB_SAD_TILE
-  int row = sub;
-  if (ww == 1) {
-    for (; row + 3 * nl < h; row += 4 * nl) acc += sad_tile<S, 1, 4>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
-    for (; row < h; row += nl) acc += sad_tile<S, 1, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
-  } else if (ww == 2) {
-    for (; row + 3 * nl < h; row += 4 * nl) acc += sad_tile<S, 2, 4>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
-    for (; row < h; row += nl) acc += sad_tile<S, 2, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
-  } else if (ww == 4) {
-    for (; row + nl < h; row += 2 * nl) acc += sad_tile<S, 4, 2>(rq + row * rsw, nl * rsw, oq + row * osw, nl * osw, sh);
-    for (; row < h; row += nl) acc += sad_tile<S, 4, 1>(rq + row * rsw, 0, oq + row * osw, 0, sh);
-  } else {
-    for (; row < h; row += nl)
-      for (int c = 0; c < ww; c += 8) acc += sad_tile<S, 8, 1>(rq + row * rsw + c, 0, oq + row * osw + c, 0, sh);
-  }
-#else
   for (int row = sub; row < h; row += nl) {
     const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
     uint32_t prev = __ldg(q);
@@ -194,7 +149,6 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
       prev = nxt;
     }
   }
-#endif
   return acc;
 }
 // whole warp on one block
@@ -487,7 +441,6 @@ __device__ __forceinline__ uint32_t strip_subpel_u8(const uint8_t *o, int os, co
   }
   const int8_t *fh = c_luma_taps[bip ? 1 : 0][xf], *fv = c_luma_taps[bip ? 1 : 0][yf];
   const uint32_t tlo = pack_s8x4(fh[0], fh[1], fh[2], fh[3]), thi = pack_s8x4(fh[4], fh[5], 0, 0);
-#if !TB_SUBPEL_RING
   const int v0 = fv[0], v1 = fv[1], v2 = fv[2], v3 = fv[3], v4 = fv[4], v5 = fv[5];
   int H[6][4];  // filtered rows y-2 .. y+3
 #pragma unroll
@@ -508,39 +461,6 @@ __device__ __forceinline__ uint32_t strip_subpel_u8(const uint8_t *o, int os, co
   }
   return acc;
 }
-#else
-  int fvr[6];
-#pragma unroll
-  for (int m = 0; m < 6; m++) fvr[m] = fv[m];
-  // Ring of the six most recent filtered rows, addressed with compile-time indices: the row loop is unrolled by six so
-  // that no register moves are needed to slide the window.  H[(y - y0 + m) % 6] holds filtered row y - 2 + m.
-  int H[6][4];
-#pragma unroll
-  for (int m = 0; m < 5; m++) hfilt4_u8(ip + (y0 - 2 + m) * rs + x0, tlo, thi, H[m]);
-  const uint8_t *nrow = ip + (y0 + 3) * rs + x0;
-  const uint8_t *orow = o + y0 * os + x0;
-  for (int yb = 0; yb < nrows; yb += 6) {
-#pragma unroll
-    for (int ph = 0; ph < 6; ph++) {
-      if (yb + ph < nrows) {
-        hfilt4_u8(nrow, tlo, thi, H[(ph + 5) % 6]);
-        nrow += rs;
-        uint32_t pk = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          int sum = fvr[0] * H[ph % 6][k] + fvr[1] * H[(ph + 1) % 6][k] + fvr[2] * H[(ph + 2) % 6][k] + fvr[3] * H[(ph + 3) % 6][k] +
-                    fvr[4] * H[(ph + 4) % 6][k] + fvr[5] * H[(ph + 5) % 6][k];
-          pk |= (uint32_t)sat_px((sum + 2048) >> 12, 255) << (8 * k);
-        }
-        if (STORE) *(uint32_t *)const_cast<uint8_t *>(orow) = pk;
-        else acc += __vsadu4(__ldg((const uint32_t *)orow), pk);
-        orow += os;
-      }
-    }
-  }
-  return acc;
-}
-#endif
 
 __device__ __forceinline__ uint32_t strip_sad_subpel_u8(const uint8_t *o, int os, const uint8_t *ip, int rs, int x0, int y0, int nrows, int xf, int yf, int bip) {
   return strip_subpel_u8<false>(o, os, ip, rs, x0, y0, nrows, xf, yf, bip);
@@ -570,11 +490,7 @@ __device__ __noinline__ uint32_t subpel_stage_sads(const S *o, int os, const S *
   if (sizeof(S) == 1) {
     // units of 4 columns x RH rows, dealt round-robin to the probe's four lanes
     // segment height: tall enough to amortise the 5-row filter halo, short enough to give every lane of the probe work
-#if TB_SUBPEL_RH16
-    const int RH = (w >> 2) * (h >> 4) >= 4 ? 16 : (h >= 8 ? 8 : h), nseg = h / RH, units = (w >> 2) * nseg;
-#else
     const int RH = h >= 8 ? 8 : h, nseg = h / RH, units = (w >> 2) * nseg;
-#endif
     for (int u = sub; u < units; u += 4) {
       int strip = u / nseg, seg = u - strip * nseg;
       acc += strip_sad_subpel_u8((const uint8_t *)o, os, (const uint8_t *)ip, rs, strip * 4, seg * RH, RH, xf, yf, bip);
