@@ -478,10 +478,10 @@ def test_motion_estimate(hbd, bd):
     cur = Frame(fw, fh, bd, hbd)
     # current frame = reference shifted by (3,-2) + noise, so the search has a real optimum
     cur.y[...] = np.clip(np.roll(f.y.astype(int), (2, -3), axis=(0, 1)) + rng.integers(-4, 5, f.y.shape), 0, (1 << bd) - 1)
-    for trial in range(120):
+    for trial in range(200):
         size = int(rng.choice([8, 16, 32, 64]))
-        part = int(rng.integers(0, 3))
-        width, height = (size, size) if part == 0 else ((size, size // 2) if part == 1 else (size // 2, size))
+        part = int(rng.integers(0, 4))  # PART_NONE, HOR, VER, QUAD (incl. the 8x8 quarters of 16x16 blocks: wide-SAD candidates on an 8x8 block)
+        width, height = (size, size) if part == 0 else ((size, size // 2) if part == 1 else ((size // 2, size) if part == 2 else (size // 2, size // 2)))
         if min(width, height) < 4: width = height = size
         xpos, ypos = int(rng.integers(0, fw // size)) * size, int(rng.integers(0, fh // size)) * size
         org = aligned((size, size), sdt(hbd))
