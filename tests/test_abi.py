@@ -119,10 +119,11 @@ def test_cpu_bench_driver_compiles_against_the_header():
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/common"), reason="reference headers not on this box")
 def test_binding_example_compiles_against_reference_headers():
-    """examples/frame_filters_binding.c (INTEGRATION.md §2.1 as real C) uses the reference's own types (deblock_data_t, yuv_frame_t)
+    """examples/*.c (INTEGRATION.md §2.1 / §2.2 as real C) use the reference's own types (deblock_data_t, yuv_frame_t)
     and the C ABI header: it must compile, warning-free, for both sample widths"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in ([], ["-DHBD"]):
-        r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I", "/root/reference/common", "-I", "/root/reference/enc", "-I", os.path.join(root, "include")]
-                           + extra + [os.path.join(root, "examples", "frame_filters_binding.c")], capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr[-1200:]
+    for src in ("frame_filters_binding.c", "motion_search_binding.c"):
+        for extra in ([], ["-DHBD"]):
+            r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I", "/root/reference/common", "-I", "/root/reference/enc", "-I", os.path.join(root, "include")]
+                               + extra + [os.path.join(root, "examples", src)], capture_output=True, text=True)
+            assert r.returncode == 0, (src, r.stderr[-1200:])
