@@ -31,7 +31,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, BD, ESZ = 1920, 1080, 8, 1
+W, H, BD, ESZ = 1920, 1080, 8, 1   # --bitdepth 10 switches BD/ESZ/SDT to 10-bit samples in uint16 (the reference's HBD build)
+SDT = np.uint8
 NREF = 4          # -max_num_ref 4  (config_HDB_high_efficiency.txt)
 QP = 35           # -qp 32 + dqpB0 3
 LAMBDA = (1.2 * 158.8437) ** 0.5   # sqrt(lambda_coeffB0 * squared_lambda_QP[35]) as passed to motion_estimate (encode_block.c:1981)
@@ -51,9 +52,10 @@ def synth_frames(rng, n):
     frames = []
     for k in range(n):
         dy, dx = 2 * k, 3 * k
-        y = np.clip(base[dy:dy + H, dx:dx + W] + rng.normal(0, 3, (H, W)), 0, 255).astype(np.uint8)
-        u = np.clip(128 + 30 * np.sin(xx[:H // 2, :W // 2] / 53.0 + k) + rng.normal(0, 2, (H // 2, W // 2)), 0, 255).astype(np.uint8)
-        v = np.clip(128 + 30 * np.cos(yy[:H // 2, :W // 2] / 47.0 - k) + rng.normal(0, 2, (H // 2, W // 2)), 0, 255).astype(np.uint8)
+        sc, mx = 1 << (BD - 8), (1 << BD) - 1
+        y = np.clip((base[dy:dy + H, dx:dx + W] + rng.normal(0, 3, (H, W))) * sc, 0, mx).astype(SDT)
+        u = np.clip((128 + 30 * np.sin(xx[:H // 2, :W // 2] / 53.0 + k) + rng.normal(0, 2, (H // 2, W // 2))) * sc, 0, mx).astype(SDT)
+        v = np.clip((128 + 30 * np.cos(yy[:H // 2, :W // 2] / 47.0 - k) + rng.normal(0, 2, (H // 2, W // 2))) * sc, 0, mx).astype(SDT)
         frames.append((y, u, v))
     return frames
 
@@ -360,7 +362,7 @@ def run_gpu(args):
     h_y, h_u, h_v = [pinned(p)[0] for p in fr[0]]
     h_me, me_bytes = pinned(me_items); h_cand, cand_bytes = pinned(cands)
     h_me_out = L.tb_malloc_host(8 * len(me_items)); h_tx_out = L.tb_malloc_host(16 * len(tx_items))
-    h_rec = [L.tb_malloc_host(W * H), L.tb_malloc_host(W * H // 4), L.tb_malloc_host(W * H // 4)]
+    h_rec = [L.tb_malloc_host(W * H * ESZ), L.tb_malloc_host(W * H // 4 * ESZ), L.tb_malloc_host(W * H // 4 * ESZ)]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     me_ev = []
@@ -502,7 +504,7 @@ def run_gpu(args):
     traffic, ncu_roofs = None, None
     try:  # DRAM bytes of one launch of this kernel from the committed ncu capture (same workload), profiles/r1_ncu_summary.md
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["me_batch_kernel"]
-        if tr["items"] == len(me_items):
+        if tr["items"] == len(me_items) and ESZ == 1:
             traffic = int(tr["dram_bytes_read"] + tr["dram_bytes_write"])
             ncu_roofs = {k: tr[k] for k in ("issue_active_pct", "l1tex_throughput_pct", "warps_active_pct") if k in tr}
     except Exception:
@@ -511,20 +513,20 @@ def run_gpu(args):
     achieved = alg_bytes / (me_ms * 1e-3) / 1e9
     value = world * args.steps * PIXELS / (ms * 1e-3) / 1e6
     e2e_value = world * args.steps * PIXELS / (ems * 1e-3) / 1e6
-    h2d = 3 * W * H // 2 + me_bytes + cand_bytes
-    d2h = 8 * len(me_items) + 16 * len(tx_items) + 3 * W * H // 2
+    h2d = 3 * W * H // 2 * ESZ + me_bytes + cand_bytes
+    d2h = 8 * len(me_items) + 16 * len(tx_items) + 3 * W * H // 2 * ESZ
     line = {
         "metric": "encode hot-path Mpixels/s (1080p HDB_high_efficiency work mix, batched; host RD control flow excluded)",
         "value": round(value, 3), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "1920x1080 8-bit 4:2:0, config_HDB_high_efficiency hot-path batch for ONE inter frame per step: %d motion searches "
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if ESZ == 1 else "u16", "data": "synthetic",
+        "config": {"workload": "1920x1080 " + str(BD) + "-bit 4:2:0, config_HDB_high_efficiency hot-path batch for ONE inter frame per step: %d motion searches "
                                "(blocks 8..128 x 4 refs x 9 PBs, speed 0, bipred taps), %d candidate predictions, %d DCT/quant/recon chains, %d intra predictions, "
                                "deblock+CDEF+CLPF(+detect)+reference pad; dependency-free batching (not a complete encode)" % (len(me_items), len(ip_items), len(tx_items), len(in_items)),
                    "parallelism": "frame-per-GPU x%d, no collective" % world, "l2_policy": "per-step inputs+outputs %.0f MB > 126 MB L2" % (resident_bytes / 1e6)},
         "e2e": {"value": round(e2e_value, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ems / args.steps, 3)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "me_batch_kernel<uint8_t> (a1/a2/a5/a7 fused motion search)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+        "roofline": {"kernel": "me_batch_kernel<%s> (a1/a2/a5/a7 fused motion search)" % ("uint8_t" if ESZ == 1 else "uint16_t"), "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "ncu": ncu_roofs, "algorithmic_bytes": int(alg_bytes), "ms_per_launch": round(me_ms, 3), "share_of_step": round(me_ms / (ms / args.steps), 3),
                      "searches": int(st[0]), "int_block_sads": int(st[1]), "subpel_probes": int(st[2])},
@@ -568,19 +570,19 @@ def cpu_arm(args, brief=False):
     O = oracle()
 
     def hframe(planes):
-        f = HFrame(W, H, BD, 0)
+        f = HFrame(W, H, BD, int(ESZ == 2))
         f.y[...] = planes[0]; f.u[...] = planes[1]; f.v[...] = planes[2]
         for p, (pw, ph, pad) in enumerate(((W, H, 160), (W // 2, H // 2, 80), (W // 2, H // 2, 80))):
-            O.orc_pad_plane_lbd(P(f.full(p), f.origin(p)), f.stride(p), pw, ph, pad, pad)
+            (O.orc_pad_plane_lbd if ESZ == 1 else O.orc_pad_plane_hbd)(P(f.full(p), f.origin(p)), f.stride(p), pw, ph, pad, pad)
         return f
     cur = hframe(fr[0]); refs = [hframe(fr[k + 1]) for k in range(NREF)]; rec = hframe(fr[1]); cand_rec = hframe(fr[1])
     pl = lambda f, p: (f.full(p).ctypes.data + f.origin(p) * ESZ, f.stride(p))
     blocks = block_grid()
     ref_planes = [[pl(r, p) for p in range(3)] for r in refs]
     _, ip_total = build_interp(tb, blocks, ref_planes, 0, np.random.default_rng(1), 1)
-    pred = np.zeros(ip_total + 64, np.uint8)
+    pred = np.zeros(ip_total + 64, SDT)
     _, in_total = build_intra(tb, blocks, 0, pl(rec, 0)[1], 0)
-    ibuf = np.zeros(in_total + 64, np.uint8)
+    ibuf = np.zeros(in_total + 64, SDT)
     tus = tu_list(blocks)
 
     def build(sub_):
@@ -594,10 +596,10 @@ def cpu_arm(args, brief=False):
     def run_once(lists):
         me, cd, tx, ip, it = lists
         me_out = np.zeros(len(me), tb.ME_RESULT); tx_out = np.zeros(len(tx), tb.TXFM_RESULT)
-        t = lib.cpu_bench_run(0, me.ctypes.data, len(me), cd.ctypes.data, me_out.ctypes.data, 0, BD, 0, 1, W, H, cores)
-        t += lib.cpu_bench_run(3, ip.ctypes.data, len(ip), None, None, 0, BD, 0, 1, W, H, cores)
-        t += lib.cpu_bench_run(1, tx.ctypes.data, len(tx), None, tx_out.ctypes.data, 0, BD, 0, 1, W, H, cores)
-        t += lib.cpu_bench_run(2, it.ctypes.data, len(it), None, None, 0, BD, 0, 1, W, H, cores)
+        t = lib.cpu_bench_run(0, me.ctypes.data, len(me), cd.ctypes.data, me_out.ctypes.data, int(ESZ == 2), BD, 0, 1, W, H, cores)
+        t += lib.cpu_bench_run(3, ip.ctypes.data, len(ip), None, None, int(ESZ == 2), BD, 0, 1, W, H, cores)
+        t += lib.cpu_bench_run(1, tx.ctypes.data, len(tx), None, tx_out.ctypes.data, int(ESZ == 2), BD, 0, 1, W, H, cores)
+        t += lib.cpu_bench_run(2, it.ctypes.data, len(it), None, None, int(ESZ == 2), BD, 0, 1, W, H, cores)
         return t
 
     lists = build(sub)
@@ -619,8 +621,8 @@ def cpu_arm(args, brief=False):
         return res
     line = {"impl": "reference", "metric": "encode hot-path Mpixels/s (1080p HDB_high_efficiency work mix, batched; host RD control flow excluded)",
             "value": res["value"], "unit": "Mpixel/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps, "warmup": args.warmup,
-            "ms_per_step": round(1e3 * total / steps * sub, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "same item lists as the GPU arm (1920x1080 8-bit, HDB_high_efficiency hot-path batch), 1/%d sample" % sub},
+            "ms_per_step": round(1e3 * total / steps * sub, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if ESZ == 1 else "u16", "data": "synthetic",
+            "config": {"workload": "same item lists as the GPU arm (1920x1080 " + str(BD) + "-bit, HDB_high_efficiency hot-path batch), 1/%d sample" % sub},
             "cpu_baseline": res, "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -631,10 +633,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bitdepth", type=int, default=8, choices=[8, 10], help="10: the same workload on 10-bit samples in uint16 (config_HDB16_high_efficiency); not the headline metric")
     ap.add_argument("--cpu-subsample", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
     args = ap.parse_args()
+    if args.bitdepth == 10:
+        global BD, ESZ, SDT
+        BD, ESZ, SDT = 10, 2, np.uint16
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) == 0:
             cpu_arm(args)
