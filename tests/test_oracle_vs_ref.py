@@ -301,6 +301,7 @@ def test_deblock(hbd, bd, dims):
     rng = np.random.default_rng(10)
     s = sfx(hbd)
     w, h = dims
+    changed = False
     for qp in (20, 32, 45):
         f = Frame(w, h, bd, hbd, 32, 32)
         f.randomize(rng)
@@ -311,8 +312,9 @@ def test_deblock(hbd, bd, dims):
         before = f.y.copy()
         getattr(O, "orc_deblock_y_" + s)(P(f.Y, f.origin(0)), f.sy, P(bi), w, h, qp, bd)
         getattr(O, "orc_deblock_uv_" + s)(P(f.U, f.origin(1)), P(f.V, f.origin(1)), f.sc, P(bi), w, h, 1, O.orc_chroma_qp(qp), bd)
-        assert (before != f.y).any()
+        changed |= bool((before != f.y).any())  # at low qp a noisy frame may pass every edge unfiltered (seen when fuzzing the seeds)
         assert (f.Y == g.Y).all() and (f.U == g.U).all() and (f.V == g.V).all()
+    assert changed  # the filter did something at some qp: the comparison above is not vacuous
 
 
 @pytest.mark.parametrize("hbd,bd", BD)
