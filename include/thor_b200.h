@@ -100,7 +100,8 @@ int tb_sync(void);
 typedef struct tb_frame tb_frame_t;
 tb_frame_t *tb_frame_create(int width, int height, int pad, int sample_bytes);
 void tb_frame_destroy(tb_frame_t *f);
-/* host <-> device copies of the visible area (planes given with their host pitches in samples) */
+/* copies of the visible area to/from caller memory (planes given with their pitches in samples).  The caller's buffers may be host
+ * memory (pinned or pageable) or device memory (e.g. a buffer an NCCL scatter just filled): the copy kind is inferred (UVA). */
 int tb_frame_upload(tb_frame_t *f, const void *y, int ystride, const void *u, const void *v, int cstride);
 int tb_frame_download(const tb_frame_t *f, void *y, int ystride, void *u, void *v, int cstride);
 /* same, without waiting: the host buffers (pinned) are valid once the current stream has been synchronised */
@@ -248,6 +249,7 @@ int tb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int tb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 /* enqueue only (pinned destination); pair with tb_sync() or an event on the stream given to tb_set_stream() */
 int tb_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes);
+int tb_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes); /* enqueue only, on the library's stream */
 void *tb_malloc_host(size_t bytes); /* pinned */
 void tb_free_host(void *p);
 

@@ -6,8 +6,11 @@
  *                       (SIMD path, use_simd = 1) linked from oracle/_ref/libthorref*.so          ("kind": "reference")
  *   default          -> oracle/libcpubench_port.so     : the plain-C oracle restatement             ("kind": "port")
  * Work items use the structs of include/thor_b200.h with HOST pointers.  The reference is single-threaded; here
- * independent items are spread over `nthreads` pthreads (static partition), which is the most favourable way to
- * use all host cores for it.  Returns wall-clock seconds.
+ * independent items are spread over `nthreads` pthreads by a DYNAMIC queue: an atomic cursor hands out small chunks,
+ * walking the list from its END (bench.py sorts the lists by block size ascending, so the expensive items go first:
+ * longest-processing-time order).  Round 1 used a static contiguous partition, which gave the last threads all the
+ * 128x128 items and inflated the GPU/CPU ratio 7-10x.  cpu_bench_imbalance() returns
+ * max(thread busy time)/mean(thread busy time) of the last run; bench.py asserts it is < 1.3.  Returns wall-clock seconds.
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -50,7 +53,9 @@ static double now(void) {
 }
 
 typedef struct {
-  int kind, tid, nthreads, n, hbd, bitdepth, speed, bip, fw, fh;
+  int kind, tid, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, chunk;
+  long *cursor; /* shared: number of items already handed out (from the end of the list) */
+  double busy;  /* this thread's time inside the run_* loops */
   const void *items;
   const int16_t *cands;
   void *out;
@@ -219,17 +224,24 @@ static void run_interp(const job_t *j, int lo, int hi) {
 }
 
 static void *worker(void *arg) {
-  const job_t *j = (const job_t *)arg;
-  int per = (j->n + j->nthreads - 1) / j->nthreads, lo = j->tid * per, hi = lo + per > j->n ? j->n : lo + per;
-  if (lo >= hi) return NULL;
-  switch (j->kind) {
-    case 0: run_me(j, lo, hi); break;
-    case 1: run_txfm(j, lo, hi); break;
-    case 2: run_intra(j, lo, hi); break;
-    case 3: run_interp(j, lo, hi); break;
+  job_t *j = (job_t *)arg;
+  for (;;) {
+    long taken = __atomic_fetch_add(j->cursor, (long)j->chunk, __ATOMIC_RELAXED);
+    if (taken >= j->n) break;
+    int hi = j->n - (int)taken, lo = hi - j->chunk < 0 ? 0 : hi - j->chunk;
+    double t0 = now();
+    switch (j->kind) {
+      case 0: run_me(j, lo, hi); break;
+      case 1: run_txfm(j, lo, hi); break;
+      case 2: run_intra(j, lo, hi); break;
+      case 3: run_interp(j, lo, hi); break;
+    }
+    j->busy += now() - t0;
   }
   return NULL;
 }
+
+static double last_imbalance = 1.0, last_busy_sum = 0.0;
 
 /* kind: 0 motion search (tb_me_item_t), 1 transform chain (tb_txfm_item_t), 2 intra (tb_intra_item_t), 3 interpolation
  * (tb_interp_item_t).  Returns elapsed wall-clock seconds. */
@@ -240,16 +252,34 @@ double cpu_bench_run(int kind, const void *items, int n, const int16_t *cands, v
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
-  job_t jobs[256];
+  static job_t jobs[256];
+  long cursor = 0;
+  /* chunks small enough that the last one cannot unbalance the run (>= 64 chunks per thread), large enough to keep
+     neighbouring items (which share samples) on one core */
+  int chunk = n / (nthreads * 64);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 256) chunk = 256;
   double t0 = now();
   for (int t = 0; t < nthreads; t++) {
-    job_t j = {kind, t, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, items, cands, out};
+    job_t j = {kind, t, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, chunk, &cursor, 0.0, items, cands, out};
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
   for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-  return now() - t0;
+  double el = now() - t0, mx = 0, sum = 0;
+  for (int t = 0; t < nthreads; t++) {
+    sum += jobs[t].busy;
+    if (jobs[t].busy > mx) mx = jobs[t].busy;
+  }
+  last_imbalance = sum > 0 ? mx / (sum / nthreads) : 1.0;
+  last_busy_sum = sum;
+  return el;
 }
+
+/* max/mean of the per-thread busy times of the last cpu_bench_run (1.0 = perfectly balanced) */
+double cpu_bench_imbalance(void) { return last_imbalance; }
+/* core-seconds of the last cpu_bench_run (sum of the per-thread busy times) */
+double cpu_bench_core_seconds(void) { return last_busy_sum; }
 
 const char *cpu_bench_kind(void) {
 #ifdef CPU_BENCH_REF

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libthor_b200.so")
 SOURCES = ["tb_api.cu"]
-DEPS = ["tb_api.cu", "tb_kernels.cuh", "tb_device.cuh", os.path.join("..", "..", "include", "thor_b200.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "thor_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--use_fast_math=false"]
 
@@ -33,7 +33,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     cmd = [nvcc()] + flags + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
-    with open(os.path.join(HERE, "build.log" if out is None else os.path.basename(out) + ".log"), "w") as f:
+    with open(os.path.join(HERE, "build.log") if out is None else out + ".log", "w") as f:  # A/B builds log next to their output (ab_libs/)
         f.write(" ".join(cmd) + "\n" + log)
     if r.returncode != 0:
         sys.stderr.write(log)

@@ -299,6 +299,12 @@ int tb_memcpy_d2h_async(void *d, const void *s, size_t n) {
   if (e != cudaSuccess) { set_err("D2H", e); return TB_ERR_CUDA; }
   return TB_OK;
 }
+int tb_memcpy_d2d(void *d, const void *s, size_t n) {
+  API_BEGIN();
+  cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g.stream);
+  if (e != cudaSuccess) { set_err("D2D", e); return TB_ERR_CUDA; }
+  return TB_OK;
+}
 void *tb_malloc_host(size_t bytes) {
   if (!ensure_ctx()) return nullptr;
   void *p = nullptr;
@@ -336,7 +342,7 @@ int tb_frame_upload(tb_frame_t *f, const void *y, int ys, const void *u, const v
   for (int p = 0; p < 3; p++) {
     if (!src[p]) continue;
     cudaError_t e = cudaMemcpy2DAsync(f->origin[p], (size_t)f->stride[p] * f->esz, src[p], (size_t)(p ? cs : ys) * f->esz, (size_t)f->pw[p] * f->esz, f->ph[p],
-                                      cudaMemcpyHostToDevice, g.stream);
+                                      cudaMemcpyDefault, g.stream);  // the source may be host (pinned or pageable) or device memory (UVA)
     if (e != cudaSuccess) { set_err("frame upload", e); return TB_ERR_CUDA; }
   }
   return TB_OK;
@@ -350,7 +356,7 @@ static int frame_download(const tb_frame *f, void *y, int ys, void *u, void *v, 
   for (int p = 0; p < 3; p++) {
     if (!dst[p]) continue;
     cudaError_t e = cudaMemcpy2DAsync(dst[p], (size_t)(p ? cs : ys) * f->esz, f->origin[p], (size_t)f->stride[p] * f->esz, (size_t)f->pw[p] * f->esz, f->ph[p],
-                                      cudaMemcpyDeviceToHost, g.stream);
+                                      cudaMemcpyDefault, g.stream);
     if (e != cudaSuccess) { set_err("frame download", e); return TB_ERR_CUDA; }
   }
   cudaError_t e = sync ? cudaStreamSynchronize(g.stream) : cudaSuccess;
