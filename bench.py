@@ -738,6 +738,7 @@ def cpu_arm(args, cfg, brief=False):
     lib.cpu_bench_run.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 7
     lib.cpu_bench_imbalance.restype = C.c_double
     lib.cpu_bench_core_seconds.restype = C.c_double
+    lib.cpu_bench_cpu_seconds.restype = C.c_double
     lib.cpu_bench_kind.restype = C.c_char_p
     kind = lib.cpu_bench_kind().decode()
     cores = len(os.sched_getaffinity(0))
@@ -771,7 +772,7 @@ def cpu_arm(args, cfg, brief=False):
         cd = wl.cands  # candidate lists are addressed through cand_ofs: keep them whole
     me_out = np.zeros(len(me), R.ME_RESULT); tx_out = np.zeros(len(tx), R.TXFM_RESULT)
     hbd = int(ESZ == 2)
-    imb, core_s, by_list = [], [0.0], {}
+    imb, core_s, cpu_s, by_list = [], [0.0], [0.0], {}
 
     def run_once():
         t = 0.0
@@ -779,13 +780,13 @@ def cpu_arm(args, cfg, brief=False):
             dt = lib.cpu_bench_run(kind_, items.ctypes.data, len(items), None if cands_ is None else cands_.ctypes.data, None if out is None else out.ctypes.data,
                                    hbd, BD, cfg.speed, cfg.bipred, W, H, cores)
             t += dt; by_list[name] = by_list.get(name, 0.0) + dt
-            imb.append((dt, lib.cpu_bench_imbalance())); core_s[0] += lib.cpu_bench_core_seconds()
+            imb.append((dt, lib.cpu_bench_imbalance())); core_s[0] += lib.cpu_bench_core_seconds(); cpu_s[0] += lib.cpu_bench_cpu_seconds()
         return t
 
     steps = max(1, args.steps if args.impl == "reference" else 1)
     for _ in range(args.warmup if args.impl == "reference" else 0):
         run_once()
-    imb.clear(); core_s[0] = 0.0; by_list.clear()
+    imb.clear(); core_s[0] = 0.0; cpu_s[0] = 0.0; by_list.clear()
     total = 0.0
     for _ in range(steps):
         total += run_once()
@@ -797,7 +798,12 @@ def cpu_arm(args, cfg, brief=False):
                "reference's own kernels (oracle/_ref, SIMD path, gcc -O3 -march=x86-64-v3; the reference Makefile uses -march=native)" if kind == "reference" else "oracle port",
                cores))
     res = {"value": round(value, 4), "unit": "Mpixel/s", "cores": cores, "physical_cores": phys, "kind": kind, "sample": sample, "seconds": round(total, 2),
-           "core_seconds_per_frame": round(core_s[0] / steps * sub, 2), "seconds_by_list": {k: round(v, 3) for k, v in by_list.items()}, "imbalance_max_over_mean": round(imbalance, 3)}
+           "thread_wall_seconds_per_frame": round(core_s[0] / steps * sub, 2), "cpu_seconds_per_frame": round(cpu_s[0] / steps * sub, 2),
+           "effective_cores": round(cpu_s[0] / total, 1),
+           "ideal_value_all_threads": round(cfg.PIXELS / (cpu_s[0] / steps * sub / cores) / 1e6, 3),
+           "note": "value = measured wall throughput of this host; cpu_seconds_per_frame = CPU time the threads consumed (CLOCK_THREAD_CPUTIME_ID); effective_cores = "
+                   "cpu seconds / wall seconds: when it is far below `cores` the box did not grant the threads that many cores (shared host / SMT); "
+                   "ideal_value_all_threads = pixels / (cpu_seconds_per_frame / cores): what perfect scaling over every hardware thread would give", "seconds_by_list": {k: round(v, 3) for k, v in by_list.items()}, "imbalance_max_over_mean": round(imbalance, 3)}
     assert imbalance < 1.3, "CPU arm is load-imbalanced (max/mean thread time %.2f): its throughput is not a fair baseline" % imbalance
     if brief:
         return res, me_out, tx_out, sub

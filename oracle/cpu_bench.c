@@ -13,6 +13,7 @@
  * max(thread busy time)/mean(thread busy time) of the last run; bench.py asserts it is < 1.3.  Returns wall-clock seconds.
  */
 #define _GNU_SOURCE
+#include <malloc.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -55,7 +56,8 @@ static double now(void) {
 typedef struct {
   int kind, tid, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, chunk;
   long *cursor; /* shared: number of items already handed out (from the end of the list) */
-  double busy;  /* this thread's time inside the run_* loops */
+  double busy;  /* this thread's wall time inside the run_* loops */
+  double cpu;   /* this thread's CPU time (CLOCK_THREAD_CPUTIME_ID): busy >> cpu means the box did not grant the thread a core */
   const void *items;
   const int16_t *cands;
   void *out;
@@ -223,8 +225,15 @@ static void run_interp(const job_t *j, int lo, int hi) {
   }
 }
 
+static double thread_cpu(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t);
+  return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
 static void *worker(void *arg) {
   job_t *j = (job_t *)arg;
+  const double c0 = thread_cpu();
   for (;;) {
     long taken = __atomic_fetch_add(j->cursor, (long)j->chunk, __ATOMIC_RELAXED);
     if (taken >= j->n) break;
@@ -238,10 +247,11 @@ static void *worker(void *arg) {
     }
     j->busy += now() - t0;
   }
+  j->cpu = thread_cpu() - c0;
   return NULL;
 }
 
-static double last_imbalance = 1.0, last_busy_sum = 0.0;
+static double last_imbalance = 1.0, last_busy_sum = 0.0, last_cpu_sum = 0.0;
 
 /* kind: 0 motion search (tb_me_item_t), 1 transform chain (tb_txfm_item_t), 2 intra (tb_intra_item_t), 3 interpolation
  * (tb_interp_item_t).  Returns elapsed wall-clock seconds. */
@@ -249,6 +259,14 @@ double cpu_bench_run(int kind, const void *items, int n, const int16_t *cands, v
 #ifdef CPU_BENCH_REF
   use_simd = 1;
 #endif
+  /* The reference allocates and frees its 32 KB scratch blocks inside every kernel call (thor_alloc).  With glibc's default
+     trim threshold every free of a thread arena's top chunk returns pages to the kernel and the next call faults them back in;
+     across 128 threads that serialises on the process's mmap lock (measured: 16x slower transform chains on the 128-thread
+     GPU host than on 8 threads).  That is an artefact of threading a single-threaded program, not of the reference's kernels:
+     keep freed memory in the arenas. */
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TOP_PAD, 64 << 20);
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
@@ -261,13 +279,15 @@ double cpu_bench_run(int kind, const void *items, int n, const int16_t *cands, v
   if (chunk > 256) chunk = 256;
   double t0 = now();
   for (int t = 0; t < nthreads; t++) {
-    job_t j = {kind, t, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, chunk, &cursor, 0.0, items, cands, out};
+    job_t j = {kind, t, nthreads, n, hbd, bitdepth, speed, bip, fw, fh, chunk, &cursor, 0.0, 0.0, items, cands, out};
     jobs[t] = j;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
   for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   double el = now() - t0, mx = 0, sum = 0;
+  last_cpu_sum = 0;
   for (int t = 0; t < nthreads; t++) {
+    last_cpu_sum += jobs[t].cpu;
     sum += jobs[t].busy;
     if (jobs[t].busy > mx) mx = jobs[t].busy;
   }
@@ -278,6 +298,8 @@ double cpu_bench_run(int kind, const void *items, int n, const int16_t *cands, v
 
 /* max/mean of the per-thread busy times of the last cpu_bench_run (1.0 = perfectly balanced) */
 double cpu_bench_imbalance(void) { return last_imbalance; }
+/* CPU seconds the threads of the last cpu_bench_run actually consumed (CLOCK_THREAD_CPUTIME_ID) */
+double cpu_bench_cpu_seconds(void) { return last_cpu_sum; }
 /* core-seconds of the last cpu_bench_run (sum of the per-thread busy times) */
 double cpu_bench_core_seconds(void) { return last_busy_sum; }
 
