@@ -236,6 +236,67 @@ int tb_scale_down2x2(const tb_frame_t *in, tb_frame_t *out);             /* temp
  * as the reference does.  ref0/ref1 must carry their replicated borders. */
 int tb_interpolate_frames(tb_frame_t *out, const tb_frame_t *ref0, const tb_frame_t *ref1, int ratio, int pos);
 
+
+/* ---- device-resident RD loop.  tb_rdo_encode_frame() runs the reference's process_block() recursion
+ * (enc/encode_block.c:2401-2565: early skip :2231-2399, mode_decision_rdo :1835-2120, encode_block :1340-1514, the bit
+ * counting of write_block enc/write_bits.c:255-600, the MV predictors / skip / merge candidates common/inter_prediction.c:413-836 and
+ * find_block_contexts common/common_block.c:283-303) for EVERY super block of one frame on the GPU, one CTA per super block, super
+ * blocks in a wavefront (left, up-left, up, up-right dependencies), and returns the decisions.  The host then only serialises them
+ * (write_super_mode / write_block of the reference's own bit writer: thor_b200/csrc/tb_rdo_shim.c is that binding).
+ * Supported: 4:2:0, sync = 0, qmtx = 0, interp_ref != 2, max_delta_qp = 0, bitrate = 0 (every BASELINE.json configuration);
+ * anything else returns TB_ERR_ARG and the binding falls back to the reference's host loop over the per-call drop-in kernels. */
+typedef struct { int16_t x, y; } tb_mv_t; /* mv_t, common/types.h:132-136 */
+typedef struct { /* per 4x4 luma block: the part of deblock_data_t (common/types.h:178-187) the RD loop and the in-loop filters read */
+  uint8_t mode, size, tb_split, pb_part;
+  uint8_t cbp_y, cbp_u, cbp_v;
+  int8_t bipred_flag; /* inter_pred.bipred_flag: 0 uni, 2 bi, -1 intra */
+  tb_mv_t mv0, mv1;
+  uint8_t ref_idx0, ref_idx1, pad[2];
+} tb_rdo_blk_t; /* 20 bytes */
+typedef struct { /* one coded block (a leaf of a super block's quad-tree): everything write_block() needs */
+  uint16_t xpos, ypos;
+  uint8_t size, mode, intra_mode, skip_idx;
+  uint8_t pb_part, tb_split, ref_idx0, ref_idx1;
+  int8_t dir;
+  uint8_t cbp_y, cbp_u, cbp_v; /* as coded (one bit per transform block when tb_split) */
+  uint8_t num_skip_vec, num_merge_vec;
+  int8_t ctx_index, ctx_cbp; /* block_context_t.index / .cbp */
+  tb_mv_t mv_arr0[4], mv_arr1[4], mvp;
+  int32_t coeff_ofs; /* first int16 of this block's quantised coefficients inside its super block's coefficient area; -1: none */
+  uint32_t cost;     /* RD cost of the block as process_block() returns it */
+} tb_rdo_leaf_t;     /* 64 bytes */
+#define TB_RDO_MAX_REF 8
+#define TB_RDO_MAX_LEAVES 256    /* 8x8 blocks in a 128x128 super block */
+#define TB_RDO_SB_COEFFS 24576   /* int16 per super block: quantised coefficients never outnumber the samples (128*128*3/2) */
+typedef struct {
+  /* sequence / frame parameters (enc_params, frame_info_t: enc/mainenc.h:35-165) */
+  int32_t width, height, log2_sb_size, bitdepth, sample_bytes;
+  int32_t frame_type; /* 0 I, 1 P, 2 B (frame_type_t) */
+  int32_t qp, num_ref, interp_ref, num_intra_modes;
+  double lambda;      /* frame_info.lambda = lambda_coeff * squared_lambda_QP[qp] */
+  int32_t enable_bipred, enable_tb_split, enable_pb_split, encoder_speed, intra_rdo, use_block_contexts, cfl_intra, cfl_inter;
+  float early_skip_thr;
+  int32_t ref_sign[TB_RDO_MAX_REF];    /* per ref_idx: ref->frame_num >  rec->frame_num (encode_block.c:1975, 1437) */
+  int32_t ref_sign_ge[TB_RDO_MAX_REF]; /* per ref_idx: ref->frame_num >= frame_info.frame_num (early skip, encode_block.c:2282, sic) */
+  /* HOST pointers.  orig / rec: sample (0,0) of each plane; ref: sample (0,0) of padded planes with >= 160 (80) samples of border */
+  const void *orig[3];
+  int32_t orig_stride[2]; /* luma, chroma pitch in samples */
+  const void *ref[TB_RDO_MAX_REF][3];
+  int32_t ref_stride[2], ref_pad; /* ref_pad: luma border (the whole padded plane is uploaded) */
+  void *rec[3];           /* out: reconstruction before the in-loop filters (visible area) */
+  int32_t rec_stride[2];
+  tb_rdo_blk_t *blk;      /* out: (height/4) x (width/4), raster */
+  tb_rdo_leaf_t *leaves;  /* out: TB_RDO_MAX_LEAVES per super block (raster order of super blocks), coding order inside */
+  int32_t *leaf_count;    /* out: per super block */
+  int16_t *coeffs;        /* out: TB_RDO_SB_COEFFS per super block */
+} tb_rdo_frame_t;
+int tb_rdo_encode_frame(const tb_rdo_frame_t *f);
+/* int16 coefficients a leaf stores for one plane: transform blocks packed back to back, each min(tsize,16)^2 in raster order */
+static inline int tb_rdo_coeff_count(int size, int tb_split) {
+  int t = tb_split ? size / 2 : size, q = t < 16 ? t : 16;
+  return (tb_split ? 4 : 1) * q * q;
+}
+
 /* ---- single-block, HOST-buffer forms of host-object functions on the path (staged per call like the drop-in symbols) */
 int tb_quantize(const int16_t *coeff, int16_t *coeffq, int qp, int size, int coeff_block_type); /* quantize(), enc/encode_block.c:84; returns cbp */
 void tb_dequantize(const int16_t *coeffq, int16_t *rcoeff, int qp, int size);                   /* dequantize(), common/common_block.c:45 */
