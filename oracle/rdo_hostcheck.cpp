@@ -52,6 +52,7 @@ template <class S> struct OracleBackend {
   int16_t block[128 * 128], coeff[128 * 128], rcoeff[128 * 128], rblock[128 * 128], tmp[32 * 32];
   S compact[128 * 128], left[2 * 128 + 16], top[2 * 128 + 16];
 
+  tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const { return *p; }
   void clip_mv(Mv &mv, int ypos, int xpos, int fw, int fh, int bw, int bh, int sign) const { orc_clip_mv((orc_mv_t *)&mv, ypos, xpos, fw, fh, bw, bh, sign); }
   void interp_luma(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int bip, int pw, int ph, int xpos, int ypos) const {
     Orc<S>::luma(dst, ref, w, h, rs, ds, (const orc_mv_t *)&mv, sign, bip, pw, ph, xpos, ypos, F->bitdepth);

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libthor_b200.so")
-SOURCES = ["tb_api.cu"]
+SOURCES = ["tb_api.cu", "tb_rdo.cu"]
 DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "thor_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--use_fast_math=false"]

@@ -45,6 +45,16 @@
 #define TB_ME_MINBLOCKS 6  // __launch_bounds__(128, N) of the motion-search kernel: registers/thread <= 65536 / (128 N)
 #endif
 
+// TB_LDG: read-only-path load of data that no thread writes during the kernel (frames, work items).  TB_LDF: load of reconstructed
+// samples that ANOTHER CTA may have written earlier in the same kernel (wavefront RD loop, tb_rdo.cu): that translation unit maps
+// TB_LDG to a plain load (its "original" block can be a scratch block written moments ago) and TB_LDF to an L1-bypassing load.
+#ifndef TB_LDG
+#define TB_LDG(p) __ldg(p)
+#endif
+#ifndef TB_LDF
+#define TB_LDF(p) (*(p))
+#endif
+
 namespace tb {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -102,9 +112,9 @@ __device__ __forceinline__ uint32_t sad_rows_v4(const uint4 *rq, int rsv, const 
   uint32_t acc = 0;
   for (int row = sub; row < h; row += nl) {
     const uint4 *q = rq + row * rsv, *a = oq + row * osv;
-    uint4 P = __ldg(q);
+    uint4 P = TB_LDG(q);
     for (int c = 0; c < nch; c++) {
-      const uint4 N = __ldg(q + c + 1), A = __ldg(a + c);
+      const uint4 N = TB_LDG(q + c + 1), A = TB_LDG(a + c);
       const uint32_t w0 = J == 0 ? P.x : (J == 1 ? P.y : (J == 2 ? P.z : P.w)), w1 = J == 0 ? P.y : (J == 1 ? P.z : (J == 2 ? P.w : N.x)),
                      w2 = J == 0 ? P.z : (J == 1 ? P.w : (J == 2 ? N.x : N.y)), w3 = J == 0 ? P.w : (J == 1 ? N.x : (J == 2 ? N.y : N.z)),
                      w4 = J == 0 ? N.x : (J == 1 ? N.y : (J == 2 ? N.z : N.w));
@@ -142,10 +152,10 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   uint32_t acc = 0;
   for (int row = sub; row < h; row += nl) {
     const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
-    uint32_t prev = __ldg(q);
+    uint32_t prev = TB_LDG(q);
     for (int c = 0; c < ww; c++) {
-      uint32_t nxt = __ldg(q + c + 1);
-      acc += word_sad<S>(__ldg(a + c), __funnelshift_r(prev, nxt, sh));
+      uint32_t nxt = TB_LDG(q + c + 1);
+      acc += word_sad<S>(TB_LDG(a + c), __funnelshift_r(prev, nxt, sh));
       prev = nxt;
     }
   }
@@ -399,7 +409,7 @@ __device__ __forceinline__ void hfilt4_u8(const uint8_t *p, uint32_t tlo, uint32
   uintptr_t a = (uintptr_t)(p - 2);
   const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
   const unsigned sh = (unsigned)(a & 3) * 8;
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  const uint32_t w0 = TB_LDG(w), w1 = TB_LDG(w + 1), w2 = TB_LDG(w + 2), w3 = TB_LDG(w + 3);
   const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -433,7 +443,7 @@ __device__ __forceinline__ uint32_t strip_subpel_u8(const uint8_t *o, int os, co
         pk |= (uint32_t)v << (8 * k);
       }
       if (STORE) *(uint32_t *)(const_cast<uint8_t *>(o) + y * os + x0) = pk;
-      else acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
+      else acc += __vsadu4(TB_LDG((const uint32_t *)(o + y * os + x0)), pk);
 #pragma unroll
       for (int k = 0; k < 4; k++) { h1m[k] = t1[k]; t1[k] = t2[k]; t2[k] = h1p[k]; h2a[k] = h2b[k]; h2b[k] = n2[k]; }
     }
@@ -457,7 +467,7 @@ __device__ __forceinline__ uint32_t strip_subpel_u8(const uint8_t *o, int os, co
       r4[k] = (v0 * H[0][k] + v1 * H[1][k] + v2 * H[2][k] + v3 * H[3][k] + v4 * H[4][k] + v5 * H[5][k] + 2048) >> 12;
     const uint32_t pk = pack_sat_u8x4(r4[0], r4[1], r4[2], r4[3]);
     if (STORE) *(uint32_t *)(const_cast<uint8_t *>(o) + y * os + x0) = pk;
-    else acc += __vsadu4(__ldg((const uint32_t *)(o + y * os + x0)), pk);
+    else acc += __vsadu4(TB_LDG((const uint32_t *)(o + y * os + x0)), pk);
   }
   return acc;
 }
@@ -595,7 +605,7 @@ __device__ __noinline__ uint32_t subpel_stage_sads_shared(const uint8_t *o, int 
         uintptr_t a = (uintptr_t)(p - 2);
         const uint32_t *wq = (const uint32_t *)(a & ~(uintptr_t)3);
         const unsigned shb = (unsigned)(a & 3) * 8;
-        const uint32_t w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 2), w3 = __ldg(wq + 3);
+        const uint32_t w0 = TB_LDG(wq), w1 = TB_LDG(wq + 1), w2 = TB_LDG(wq + 2), w3 = TB_LDG(wq + 3);
         const uint32_t b0 = __funnelshift_r(w0, w1, shb), b1 = __funnelshift_r(w1, w2, shb), b2 = __funnelshift_r(w2, w3, shb);
         if (gd.w & 0x100) {  // the two row filters of the centre kernel: H1 = [0 0 1 1 0 0], H2 = [0 1 2 2 1 0]
           const uint32_t a_lo = 0x01010000u, b_lo = 0x02020100u, b_hi = 0x00000001u;
@@ -634,7 +644,7 @@ __device__ __noinline__ uint32_t subpel_stage_sads_shared(const uint8_t *o, int 
             a3 = __dp2a_hi((int)hw.y, (int)K[m], a3);
           }
           const uint32_t pk = pack_sat_u8x4(a0 >> 12, a1 >> 12, a2 >> 12, a3 >> 12);
-          acc_s += __vsadu4(__ldg((const uint32_t *)(o + (row0 + ty + y) * os + tx + 4 * st)), pk);
+          acc_s += __vsadu4(TB_LDG((const uint32_t *)(o + (row0 + ty + y) * os + tx + 4 * st)), pk);
         }
       }
       // ---- (V) centre-kernel probes: out = (H1[y-1] + H2[y] + H2[y+1] + H1[y+2] + 8) >> 4   (<= 255: no clamp needed)
@@ -647,7 +657,7 @@ __device__ __noinline__ uint32_t subpel_stage_sads_shared(const uint8_t *o, int 
           const uint32_t s01 = ((p0.x + p1.x + p2.x + p3.x + 0x00080008u) >> 4) & 0x0fff0fffu;  // packed u16 pairs, sums <= 4088
           const uint32_t s23 = ((p0.y + p1.y + p2.y + p3.y + 0x00080008u) >> 4) & 0x0fff0fffu;
           const uint32_t pk = __byte_perm(s01, s23, 0x6420);
-          acc_x += __vsadu4(__ldg((const uint32_t *)(o + (row0 + ty + y) * os + tx + 4 * st)), pk);
+          acc_x += __vsadu4(TB_LDG((const uint32_t *)(o + (row0 + ty + y) * os + tx + 4 * st)), pk);
         }
       }
       __syncwarp();
@@ -678,7 +688,7 @@ __device__ __forceinline__ void row12_u8(const uint8_t *p, uint32_t &b0, uint32_
   const uintptr_t a = (uintptr_t)p;
   const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
   const unsigned sh = (unsigned)(a & 3) * 8;
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+  const uint32_t w0 = TB_LDG(w), w1 = TB_LDG(w + 1), w2 = TB_LDG(w + 2), w3 = TB_LDG(w + 3);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
 }
 // NL = 32: the warp works on one search; NL = 8: each group of eight lanes on its own search (quad_motion_estimate)
@@ -715,7 +725,7 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
         const uint32_t lo = k < 4 ? __funnelshift_r(b0, b1, 8 * k) : b1, hi4 = k < 4 ? __funnelshift_r(b1, b2, 8 * k) : b2;
         v[k] = (dp4a_us(lo, tlo, dp4a_us(hi4, thi, 32))) >> 6;
       }
-      const uint32_t ow = __ldg((const uint32_t *)(ob + y * os + 4 * st));
+      const uint32_t ow = TB_LDG((const uint32_t *)(ob + y * os + 4 * st));
       aH0 += __vsadu4(ow, pack_sat_u8x4(v[0], v[1], v[2], v[3]));
       aH1 += __vsadu4(ow, pack_sat_u8x4(v[1], v[2], v[3], v[4]));
     }
@@ -731,7 +741,7 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
       const int rsw = rs >> 2;
       uint32_t W[6];
 #pragma unroll
-      for (int m = 0; m < 6; m++) W[m] = __funnelshift_r(__ldg(wq + m * rsw), __ldg(wq + m * rsw + 1), sh);
+      for (int m = 0; m < 6; m++) W[m] = __funnelshift_r(TB_LDG(wq + m * rsw), TB_LDG(wq + m * rsw + 1), sh);
       int v[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -740,8 +750,8 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
         v[k] = dp4a_us(__byte_perm(t01, t23, 0x5410), tlo, dp4a_us(t45, thi, 32)) >> 6;  // thi has zero taps on the two upper bytes
       }
       const uint32_t pk = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
-      if (r < h) aV0 += __vsadu4(__ldg((const uint32_t *)(ob + r * os + 4 * st)), pk);
-      if (r > 0) aV1 += __vsadu4(__ldg((const uint32_t *)(ob + (r - 1) * os + 4 * st)), pk);
+      if (r < h) aV0 += __vsadu4(TB_LDG((const uint32_t *)(ob + r * os + 4 * st)), pk);
+      if (r > 0) aV1 += __vsadu4(TB_LDG((const uint32_t *)(ob + (r - 1) * os + 4 * st)), pk);
     }
   }
   // ---- C pass: plane rows r = 0 .. h, plane columns 4 s .. 4 s + 4
@@ -769,12 +779,12 @@ __device__ __noinline__ uint32_t halfpel_stage_sads_u8(const uint8_t *o, int os,
       const uint32_t q0 = (uint32_t)(acc[0] >> 4), q1 = (uint32_t)(acc[1] >> 4), q2 = (uint32_t)(acc[2] >> 4), q3 = (uint32_t)(acc[3] >> 4), q4 = (uint32_t)(acc[4] >> 4);
       const uint32_t pk0 = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24), pk1 = q1 | (q2 << 8) | (q3 << 16) | (q4 << 24);
       if (r < h) {
-        const uint32_t ow = __ldg((const uint32_t *)(ob + r * os + 4 * st));
+        const uint32_t ow = TB_LDG((const uint32_t *)(ob + r * os + 4 * st));
         aC00 += __vsadu4(ow, pk0);
         aC01 += __vsadu4(ow, pk1);
       }
       if (r > 0) {
-        const uint32_t ow = __ldg((const uint32_t *)(ob + (r - 1) * os + 4 * st));
+        const uint32_t ow = TB_LDG((const uint32_t *)(ob + (r - 1) * os + 4 * st));
         aC10 += __vsadu4(ow, pk0);
         aC11 += __vsadu4(ow, pk1);
       }
@@ -2092,18 +2102,18 @@ __device__ void warp_make_top_and_left(S *left, S *top, S &top_left, const S *re
     for (int k = lane; k < 2 * size; k += 32) top[k] = mid;
   } else {
     const S *src = (i == 0) ? rec_frame - fstride + j : rblock - rbstride;
-    S val = src[toplen - 1];
-    for (int k = lane; k < 2 * size; k += 32) top[k] = k < toplen ? src[k] : (k >= size ? val : src[k]);
-    if (xpos > 0) tl = (i == 0) ? rec_frame[-fstride + j - 1] : ((j > 0) ? rblock[-rbstride - 1] : rec_frame[(i - 1) * fstride - 1]);
-    else tl = src[0];
+    S val = TB_LDF(src + toplen - 1);
+    for (int k = lane; k < 2 * size; k += 32) top[k] = k < toplen ? TB_LDF(src + k) : (k >= size ? val : TB_LDF(src + k));
+    if (xpos > 0) tl = (i == 0) ? TB_LDF(rec_frame - fstride + j - 1) : ((j > 0) ? TB_LDF(rblock - rbstride - 1) : TB_LDF(rec_frame + (i - 1) * fstride - 1));
+    else tl = TB_LDF(src);
   }
   if (xpos + j == 0) {
     for (int k = lane; k < 2 * size; k += 32) left[k] = mid;
   } else {
     const S *base = (j == 0) ? rec_frame + i * fstride - 1 : rblock - 1;
     const int st = (j == 0) ? fstride : rbstride;
-    S val = base[(leftlen - 1) * st];
-    for (int k = lane; k < 2 * size; k += 32) left[k] = k < leftlen ? base[k * st] : (k >= size ? val : base[k * st]);
+    S val = TB_LDF(base + (leftlen - 1) * st);
+    for (int k = lane; k < 2 * size; k += 32) left[k] = k < leftlen ? TB_LDF(base + k * st) : (k >= size ? val : TB_LDF(base + k * st));
   }
   __syncwarp();
   if (ypos + i == 0) tl = left[0];

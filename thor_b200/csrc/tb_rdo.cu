@@ -1,0 +1,403 @@
+// tb_rdo.cu — SURVEY.md §8f.1: the reference's per-super-block RD loop resident on the GPU.
+//
+// tb_rdo_encode_frame() (include/thor_b200.h) uploads the source frame and the padded reference frames, runs rdo_frame_kernel — one
+// CTA per super-block ROW, super blocks of a row in raster order, rows in a wavefront: row r may start super block c when row r-1 has
+// published c+2 super blocks (left, up-left, up, up-right neighbours: get_mv_pred / intra prediction / block contexts read nothing else)
+// — and downloads the decisions (reconstruction, per-4x4 block state, the leaf list of every super block with its coefficients).
+// The control flow is tb_rdo.h (shared with the CPU host check that pins it against the reference); this file supplies its backend:
+// the warp-cooperative primitives of tb_device.cuh / tb_kernels.cuh, i.e. the same device routines the batched tb_* entry points
+// and the drop-in symbols use (parity-tested against the oracle one by one in tests/test_gpu_parity.py).
+//
+// This is a separate translation unit because two load policies differ from the batched kernels:
+//   TB_LDG -> plain load: the "original" of a search can be a scratch block this CTA wrote a moment ago (bipred target 2*org - pred),
+//             so the read-only (non-coherent) path must not be used;
+//   TB_LDF -> __ldcg: reconstructed samples and block state of the neighbouring super blocks were written by OTHER CTAs during this
+//             launch; L1 is not coherent across SMs and a line can straddle two super blocks, so those loads bypass L1.
+// The device code of this unit lives in its own namespace (the headers define __constant__ tables).
+#define TB_LDG(p) (*(p))
+#define TB_LDF(p) __ldcg(p)
+#define tb tb_rdo_tu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include "tb_kernels.cuh"
+#include "tb_rdo.h"
+
+using namespace tb;
+using namespace tbr;
+
+namespace {
+
+template <class S> struct RdoShared {
+  TxScratch sc;
+  alignas(16) int8_t tab8[TX_TABLE_BYTES];       // int8 DCT matrices (plain, transposed) + 16x16 zig-zag table
+  alignas(16) int16_t tab16[DCT_TAB_SIZE];       // int16 DCT matrices (warp_fwd_transform of the early-skip test)
+  alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual; coefficient scan for the bit count
+  alignas(16) int16_t out16[256];
+  alignas(16) S left[256], top[256], filt[4 * 128 + 4];
+  tb_txfm_result_t res;
+};
+
+template <class S> struct DevBackend {
+  const FrameCtx<S> *F;
+  RdoShared<S> *sh;
+
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+
+  __device__ tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const {
+    // 20 bytes, 4-byte aligned; written by another CTA earlier in this launch -> L2
+    const int *q = (const int *)p;
+    int w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = __ldcg(q + k);
+    tb_rdo_blk_t b;
+    memcpy(&b, w, sizeof(b));
+    return b;
+  }
+  __device__ void clip_mv(Mv &mv, int ypos, int xpos, int fw, int fh, int bw, int bh, int sign) const {
+    int x = mv.x, y = mv.y;
+    tb::clip_mv(x, y, ypos, xpos, fw, fh, bw, bh, sign);
+    mv.x = (int16_t)x; mv.y = (int16_t)y;
+  }
+  // prediction of one block; widths that are not powers of two (rectangular blocks at the right frame edge) take the per-sample form
+  __device__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
+    sync();
+    if (!(w & (w - 1))) warp_interp<S>(dst, ds, ref, rs, w, h, mv.x, mv.y, sign, chroma, bip, pw, ph, xpos, ypos, F->bitdepth);
+    else {
+      int hi, vi, xf, yf;
+      split_mv(mv.x, mv.y, sign, chroma ? 3 : 2, pw, ph, xpos, ypos, w, h, hi, vi, xf, yf);
+      const S *ip = ref + vi * rs + hi;
+      const int maxv = (1 << F->bitdepth) - 1;
+      for (int p = lane(); p < w * h; p += 32) {
+        const int row = p / w, col = p - row * w;
+        const S *q = ip + row * rs + col;
+        int v;
+        if (xf == 0 && yf == 0) v = q[0];
+        else v = chroma ? chroma_sample<S>(q, rs, xf, yf, maxv) : luma_sample<S>(q, rs, xf, yf, bip, maxv);
+        dst[row * ds + col] = (S)v;
+      }
+    }
+    sync();
+  }
+  __device__ void interp_luma(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int bip, int pw, int ph, int xpos, int ypos) const {
+    interp_any(dst, ds, ref, rs, w, h, mv, sign, 0, bip, pw, ph, xpos, ypos);
+  }
+  __device__ void interp_chroma(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int pw, int ph, int xc, int yc) const {
+    interp_any(dst, ds, ref, rs, w, h, mv, sign, 1, 0, pw, ph, xc, yc);
+  }
+  __device__ void avg(S *dst, const S *a, const S *b, int stride, int w, int h) const {
+    sync();
+    for (int p = lane(); p < w * h; p += 32) {
+      const int row = p / w, col = p - row * w, o = row * stride + col;
+      dst[o] = (S)(((int)a[o] + (int)b[o]) >> 1);
+    }
+    sync();
+  }
+  __device__ void sat2ab(S *dst, const S *org, int os, const S *pred, int size) const {
+    const int maxv = (1 << F->bitdepth) - 1, ls = ilog2(size);
+    sync();
+    for (int p = lane(); p < size * size; p += 32) {
+      const int row = p >> ls, col = p & (size - 1);
+      dst[p] = (S)sat_px(2 * (int)org[row * os + col] - (int)pred[p], maxv);
+    }
+    sync();
+  }
+  __device__ void copy(S *dst, int ds, const S *src, int ss, int w, int h) const {
+    sync();
+    for (int p = lane(); p < w * h; p += 32) {
+      const int row = p / w, col = p - row * w;
+      dst[row * ds + col] = src[row * ss + col];
+    }
+    sync();
+  }
+  __device__ void copy_coeff(int16_t *dst, const int16_t *src) const {
+    sync();
+    for (int p = lane(); p < 1024 / 4; p += 32) ((uint2 *)dst)[p] = ((const uint2 *)src)[p];
+    sync();
+  }
+  __device__ void intra_predict(S *dst, int ds, const S *recf, int rfs, const S *rblock, int rbs, int i, int j, int ypos, int xpos, int size, int ur, int dl, int tbs,
+                                int mode) const {
+    sync();
+    S tl;
+    warp_make_top_and_left<S>(sh->left, sh->top, tl, recf, rfs, rblock, rbs, i, j, ypos, xpos, size, ur, dl, tbs, F->bitdepth);
+    sync();
+    if (mode == 10) warp_intra_pred<S>(sh->left, sh->top, tl, 1, 1, size, dst, ds, 0, F->bitdepth, sh->filt);  // DC from (left, top) as gathered
+    else warp_intra_pred<S>(sh->left, sh->top, tl, ypos + i, xpos + j, size, dst, ds, mode, F->bitdepth, sh->filt);
+    sync();
+  }
+  __device__ void cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride) const {
+    sync();
+    warp_cfl<S>(y, u, v, ry, n, cstride, stride, 1, F->bitdepth);
+    sync();
+  }
+  __device__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
+    sync();
+    int cbp;
+    if (size >= 16) {
+      tb_txfm_item_t q;
+      q.orig = orig; q.pred = pred; q.rec = rec; q.coeffq = cq; q.ostride = os; q.pstride = ps; q.rstride = rs;
+      q.size = (uint8_t)size; q.qp = (uint8_t)qp; q.coeff_type = (uint8_t)coeff_type; q.fast = (uint8_t)(fast ? TB_TXFM_FAST : 0);
+      tx_big_chain<S, 1>(q, F->bitdepth, sh->sc, nullptr, sh->tab8, sh->tab8 + DCT_TAB8_SIZE, nullptr, nullptr, &sh->res);
+      sync();
+      cbp = sh->res.cbp;
+    } else {
+      cbp = 0;
+      if (lane() == 0) {
+        uint64_t ssd;
+        int bits;
+        if (size == 4) cbp = thread_txfm4<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, ssd, 0, bits);
+        else cbp = thread_txfm8<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, sh->tab8, sh->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
+      }
+      cbp = __shfl_sync(FULL, cbp, 0);
+    }
+    sync();
+    return cbp;
+  }
+  __device__ int coeff_bits(const int16_t *cq, int size, int type) const {
+    const int qs = min(size, 16), nq = qs * qs, lq = ilog2(qs);
+    sync();
+    for (int p = lane(); p < nq; p += 32) sh->out16[zigzag_index(p >> lq, p & (qs - 1), qs)] = cq[p];
+    sync();
+    const int bits = warp_coeff_bits(sh->out16, nq, size, type);
+    sync();
+    return bits;
+  }
+  __device__ uint64_t ssd(const S *a, int as, const S *b, int bs, int w, int h) const {
+    sync();
+    if (!(w & (w - 1))) return warp_ssd<S>(a, as, b, bs, w, h);
+    uint64_t acc = 0;
+    for (int p = lane(); p < w * h; p += 32) {
+      const int row = p / w, col = p - row * w, d = (int)a[row * as + col] - (int)b[row * bs + col];
+      acc += (uint64_t)(uint32_t)(d * d);
+    }
+    return warp_sum64(acc);
+  }
+  __device__ unsigned sad(const S *a, int as, const S *b, int bs, int w, int h) const {
+    sync();
+    return warp_sad<S>(a, as, b, bs, w, h);
+  }
+  __device__ int me(const S *org, int os, const S *ref, int rs, int size, int w, int h, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
+                    int ncand) const {
+    sync();
+    MeCtx c;
+    c.size = size; c.width = w; c.height = h; c.sign = sign; c.s = sign ? -1 : 1; c.xpos = xpos; c.ypos = ypos; c.fw = F->width; c.fh = F->height;
+    c.bitdepth = F->bitdepth; c.speed = F->speed; c.bip = F->enable_bipred; c.mvpx = mvp.x; c.mvpy = mvp.y; c.lambda = lambda; c.n_int = 0; c.n_sub = 0; c.sps = nullptr;
+    MeTeam<1> tm;
+    tm.xch = nullptr; tm.warp = 0; tm.phase = 0;
+    int mx, my;
+    uint32_t cost;
+    warp_motion_estimate<S, 1>(org, os, ref, rs, c, mvc.x, mvc.y, (const int16_t *)cand, ncand, mx, my, cost, tm);
+    mx = __shfl_sync(FULL, mx, 0); my = __shfl_sync(FULL, my, 0); cost = __shfl_sync(FULL, cost, 0);
+    mv->x = (int16_t)mx; mv->y = (int16_t)my;
+    sync();
+    return (int)cost;
+  }
+  __device__ int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
+                       int ncand) const {
+    sync();
+    int mx, my;
+    uint32_t cost;
+    warp_motion_estimate_bi<S>(org, os, ref0, ref1, rs, size, sign, xpos, ypos, F->width, F->height, F->bitdepth, 1, lambda, mvc.x, mvc.y, mvp.x, mvp.y, (const int16_t *)cand,
+                               ncand, mx, my, cost);
+    mx = __shfl_sync(FULL, mx, 0); my = __shfl_sync(FULL, my, 0); cost = __shfl_sync(FULL, cost, 0);
+    mv->x = (int16_t)mx; mv->y = (int16_t)my;
+    sync();
+    return (int)cost;
+  }
+  // check_early_skip_sub_block (enc/encode_block.c:2147-2180): 2x2 average of the residual, (size/2)-point transform, any |c| > threshold
+  __device__ int es_luma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+    const int s2 = size / 2, l2 = ilog2(s2);
+    sync();
+    for (int p = lane(); p < s2 * s2; p += 32) {
+      const int i = p >> l2, j = p & (s2 - 1);
+      int sum = 2;
+#pragma unroll
+      for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int n = 0; n < 2; n++) sum += (int)(int16_t)((int)orig[(2 * i + m) * os + 2 * j + n] - (int)pred[(2 * i + m) * ps + 2 * j + n]);
+      sh->blk16[p] = (int16_t)(sum >> 2);
+    }
+    sync();
+    warp_fwd_transform(sh->blk16, s2, s2, 0, F->bitdepth, sh->sc, sh->out16, sh->tab16);
+    int hit = 0;
+    for (int p = lane(); p < s2 * s2; p += 32) hit |= iabs((int)sh->out16[p]) > threshold;
+    hit = __any_sync(FULL, hit);
+    sync();
+    return hit;
+  }
+  // check_early_skip_sub_blockC :2214-2229 with calc_cbp_simd
+  __device__ int es_chroma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+    const int ls = ilog2(size);
+    sync();
+    for (int p = lane(); p < size * size; p += 32) {
+      const int i = p >> ls, j = p & (size - 1);
+      sh->blk16[p] = (int16_t)((int)orig[i * os + j] - (int)pred[i * ps + j]);
+    }
+    sync();
+    const int r = warp_calc_cbp(sh->blk16, size, threshold);
+    sync();
+    return r;
+  }
+  __device__ void store_blk(tb_rdo_blk_t *blk, int stride, int by, int bx, int nbw, int nbh, int div, tb_rdo_blk_t v, const Mv *mv0, const Mv *mv1) const {
+    sync();
+    for (int p = lane(); p < nbw * nbh; p += 32) {
+      const int m = p / nbw, n = p - m * nbw;
+      const int m0 = div > 0 ? m / div : 0, n0 = div > 0 ? n / div : 0, index = 2 * m0 + n0;
+      tb_rdo_blk_t w = v;
+      w.mv0 = mv0[index]; w.mv1 = mv1[index];
+      blk[(by + m) * stride + bx + n] = w;
+    }
+    sync();
+  }
+  __device__ void pack_coeff(int16_t *dst, const int16_t *q, int size, int tb_split, int nonzero) const {
+    const int t = tb_split ? size / 2 : size, qs = t < 16 ? t : 16, n = tb_split ? 4 : 1, nq = qs * qs;
+    sync();
+    for (int p = lane(); p < n * nq; p += 32) {
+      const int k = p / nq, i = p - k * nq;
+      dst[p] = nonzero ? q[k * 256 + i] : (int16_t)0;
+    }
+    sync();
+  }
+  __device__ void store_leaf(tb_rdo_leaf_t *p, const tb_rdo_leaf_t &L) const {
+    if (lane() == 0) *p = L;
+    sync();
+  }
+  __device__ void store_count(int *p, int n) const {
+    if (lane() == 0) *p = n;
+    sync();
+  }
+};
+
+template <class S>
+__global__ void __launch_bounds__(32) rdo_frame_kernel(FrameCtx<S> ctx, Work<S> *works, int *progress, int nsbx) {
+  __shared__ RdoShared<S> sh;
+  dct_tab8_fill(sh.tab8, sh.tab8 + DCT_TAB8_SIZE);
+  dct_tab_fill(sh.tab16);
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) ((uint8_t *)(sh.tab8 + 2 * DCT_TAB8_SIZE))[t] = (uint8_t)zigzag_index(t >> 4, t & 15, 16);
+  __syncthreads();
+  const int row = blockIdx.x;
+  DevBackend<S> be;
+  be.F = &ctx; be.sh = &sh;
+  volatile int *prog = progress;
+  for (int sbx = 0; sbx < nsbx; sbx++) {
+    if (row > 0) {
+      const int need = min(sbx + 2, nsbx);
+      if ((threadIdx.x & 31) == 0)
+        while (prog[row - 1] < need) __nanosleep(200);
+      __syncwarp();
+      __threadfence();
+    }
+    Rdo<S, DevBackend<S>> R(ctx, works[row], be);
+    R.process_sb(sbx, row);
+    __syncwarp();
+    __threadfence();  // every writing lane orders its stores before the flag
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) prog[row] = sbx + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------------------------
+struct DevState {
+  int w = 0, h = 0, esz = 0, sb = 0, pad = 0, nref = 0, sy = 0, sc = 0;
+  void *org[3] = {nullptr, nullptr, nullptr}, *rec[3] = {nullptr, nullptr, nullptr};
+  void *ref[TB_RDO_MAX_REF][3] = {};
+  tb_rdo_blk_t *blk = nullptr;
+  tb_rdo_leaf_t *leaves = nullptr;
+  int *leaf_count = nullptr, *progress = nullptr;
+  int16_t *coeffs = nullptr;
+  void *works = nullptr;
+  char err[256] = {0};
+} D;
+
+void free_state() {
+  for (int p = 0; p < 3; p++) { cudaFree(D.org[p]); cudaFree(D.rec[p]); D.org[p] = D.rec[p] = nullptr; }
+  for (int r = 0; r < TB_RDO_MAX_REF; r++)
+    for (int p = 0; p < 3; p++) { cudaFree(D.ref[r][p]); D.ref[r][p] = nullptr; }
+  cudaFree(D.blk); cudaFree(D.leaves); cudaFree(D.leaf_count); cudaFree(D.progress); cudaFree(D.coeffs); cudaFree(D.works);
+  D.blk = nullptr; D.leaves = nullptr; D.leaf_count = D.progress = nullptr; D.coeffs = nullptr; D.works = nullptr;
+  D.w = 0;
+}
+
+#define CK(x)                                                                                     \
+  do {                                                                                            \
+    cudaError_t e__ = (x);                                                                        \
+    if (e__ != cudaSuccess) { snprintf(D.err, sizeof(D.err), "%s: %s", #x, cudaGetErrorString(e__)); return TB_ERR_CUDA; } \
+  } while (0)
+
+template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
+  const int w = f->width, h = f->height, sb = 1 << f->log2_sb_size, esz = (int)sizeof(S), pad = f->ref_pad;
+  const int nsbx = (w + sb - 1) / sb, nsby = (h + sb - 1) / sb, nsb = nsbx * nsby;
+  const int sy = f->ref_stride[0], sc = f->ref_stride[1], padc = pad >> 1;
+  const size_t ref_y_bytes = (size_t)(h + 2 * pad) * sy * esz, ref_c_bytes = (size_t)((h >> 1) + 2 * padc) * sc * esz;
+  if (D.w != w || D.h != h || D.esz != esz || D.sb != sb || D.pad != pad || D.sy != sy || D.sc != sc || D.nref < f->num_ref) {
+    free_state();
+    // source and reconstruction use the padded geometry of the reference frames (only their visible area is touched)
+    for (int p = 0; p < 3; p++) { CK(cudaMalloc(&D.org[p], (p ? ref_c_bytes : ref_y_bytes) + 256)); CK(cudaMalloc(&D.rec[p], (p ? ref_c_bytes : ref_y_bytes) + 256)); }
+    for (int r = 0; r < f->num_ref || r < 5; r++)
+      for (int p = 0; p < 3; p++) CK(cudaMalloc(&D.ref[r][p], (p ? ref_c_bytes : ref_y_bytes) + 256));
+    CK(cudaMalloc(&D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4)));
+    CK(cudaMalloc(&D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES));
+    CK(cudaMalloc(&D.leaf_count, sizeof(int) * nsb));
+    CK(cudaMalloc(&D.progress, sizeof(int) * nsby));
+    CK(cudaMalloc(&D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS));
+    CK(cudaMalloc(&D.works, sizeof(Work<S>) * (size_t)nsby));
+    D.w = w; D.h = h; D.esz = esz; D.sb = sb; D.pad = pad; D.sy = sy; D.sc = sc; D.nref = f->num_ref > 5 ? f->num_ref : 5;
+  }
+  FrameCtx<S> C;
+  static const int8_t chroma_qp_mid[13] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37};  // common/common_tables.c:67-72
+  C.width = w; C.height = h; C.sb_size = sb; C.bitdepth = f->bitdepth; C.frame_type = f->frame_type; C.qp = f->qp;
+  C.qpc = f->qp < 30 ? f->qp : (f->qp >= 43 ? f->qp - 6 : chroma_qp_mid[f->qp - 30]);
+  C.num_ref = f->num_ref; C.interp_ref = f->interp_ref; C.num_intra_modes = f->num_intra_modes; C.lambda = f->lambda; C.sqrt_lambda = sqrt(f->lambda);
+  C.enable_bipred = f->enable_bipred; C.enable_tb_split = f->enable_tb_split; C.enable_pb_split = f->enable_pb_split; C.speed = f->encoder_speed; C.intra_rdo = f->intra_rdo;
+  C.use_block_contexts = f->use_block_contexts; C.cfl_intra = f->cfl_intra; C.cfl_inter = f->cfl_inter; C.early_skip_thr = f->early_skip_thr;
+  const size_t oy = ((size_t)pad * sy + pad) * esz, oc = ((size_t)padc * sc + padc) * esz;
+  for (int r = 0; r < TB_RDO_MAX_REF; r++) {
+    C.ref_sign[r] = f->ref_sign[r]; C.ref_sign_ge[r] = f->ref_sign_ge[r];
+    for (int p = 0; p < 3; p++) C.ref[r][p] = r < f->num_ref ? (const S *)((char *)D.ref[r][p] + (p ? oc : oy)) : nullptr;
+  }
+  for (int p = 0; p < 3; p++) { C.org[p] = (const S *)((char *)D.org[p] + (p ? oc : oy)); C.rec[p] = (S *)((char *)D.rec[p] + (p ? oc : oy)); }
+  C.org_stride[0] = sy; C.org_stride[1] = sc; C.ref_stride[0] = sy; C.ref_stride[1] = sc; C.rec_stride[0] = sy; C.rec_stride[1] = sc;
+  C.blk = D.blk; C.blk_stride = w / 4; C.leaves = D.leaves; C.leaf_count = D.leaf_count; C.coeffs = D.coeffs;
+  // uploads: source (visible area), references (whole padded planes: one contiguous copy each)
+  for (int p = 0; p < 3; p++)
+    CK(cudaMemcpy2DAsync((void *)C.org[p], (size_t)(p ? sc : sy) * esz, f->orig[p], (size_t)f->orig_stride[p ? 1 : 0] * esz, (size_t)(p ? w >> 1 : w) * esz, p ? h >> 1 : h,
+                         cudaMemcpyHostToDevice, st));
+  for (int r = 0; r < f->num_ref; r++)
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(D.progress, 0, sizeof(int) * nsby, st));
+  rdo_frame_kernel<S><<<nsby, 32, 0, st>>>(C, (Work<S> *)D.works, D.progress, nsbx);
+  CK(cudaGetLastError());
+  for (int p = 0; p < 3; p++)
+    CK(cudaMemcpy2DAsync(f->rec[p], (size_t)f->rec_stride[p ? 1 : 0] * esz, C.rec[p], (size_t)(p ? sc : sy) * esz, (size_t)(p ? w >> 1 : w) * esz, p ? h >> 1 : h,
+                         cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->blk, D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+const char *tb_rdo_last_error(void) { return D.err; }
+static uint64_t g_rdo_launches = 0;
+uint64_t tb_rdo_launch_count(void) { return g_rdo_launches; }
+
+int tb_rdo_encode_frame(const tb_rdo_frame_t *f) {
+  if (!f || f->num_ref > TB_RDO_MAX_REF || f->num_ref < 0 || f->log2_sb_size > 7 || f->log2_sb_size < 4 || (f->sample_bytes != 1 && f->sample_bytes != 2) || f->width <= 0 ||
+      f->height <= 0 || (f->width & 7) || (f->height & 7) || f->interp_ref == 2 || f->qp < 0 || f->qp > 51 || !f->blk || !f->leaves || !f->leaf_count || !f->coeffs ||
+      (f->num_ref > 0 && f->ref_pad < 16))
+    return TB_ERR_ARG;
+  if (tb_init(-1) != TB_OK) return TB_ERR_CUDA;  // no CPU path: without a CUDA device the call fails
+  cudaStream_t st = (cudaStream_t)tb_stream();
+  g_rdo_launches++;
+  return f->sample_bytes == 1 ? run_frame<uint8_t>(f, st) : run_frame<uint16_t>(f, st);
+}
+}

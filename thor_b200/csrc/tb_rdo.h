@@ -18,7 +18,7 @@
 #include "../../include/thor_b200.h"
 
 #ifdef __CUDACC__
-#define TBR_HD __host__ __device__
+#define TBR_HD __device__  // under nvcc the header is only instantiated for the device backend
 #else
 #define TBR_HD
 #endif
@@ -38,6 +38,8 @@ struct Ctx3 { int split, cbp, index; };                               // block_c
 TBR_HD inline int imin(int a, int b) { return a < b ? a : b; }
 TBR_HD inline int imax(int a, int b) { return a > b ? a : b; }
 TBR_HD inline int iabs_(int a) { return a < 0 ? -a : a; }
+// tb_rdo_coeff_count of thor_b200.h for both builds
+TBR_HD inline int coeff_count(int size, int tb_split) { const int t = tb_split ? size / 2 : size, q = t < 16 ? t : 16; return (tb_split ? 4 : 1) * q * q; }
 TBR_HD inline int ilog2_(unsigned x) { int r = 0; while (x >>= 1) r++; return r; }
 
 // lambda * n + 0.5 without FMA contraction (the reference is ISO C on x86-64: separate multiply and add)
@@ -161,7 +163,7 @@ template <class S, class B> struct Rdo {
   // neighbour state
   // ---------------------------------------------------------------------------------------------------------------
   TBR_HD IPred ipred_at(int index) const {
-    const tb_rdo_blk_t &b = F.blk[index];
+    const tb_rdo_blk_t b = be.ld_blk(F.blk + index);  // another CTA may have written it: the device backend bypasses L1
     IPred p; p.mv0 = b.mv0; p.mv1 = b.mv1; p.ref_idx0 = b.ref_idx0; p.ref_idx1 = b.ref_idx1; p.bipred_flag = b.bipred_flag;
     return p;
   }
@@ -185,7 +187,7 @@ template <class S, class B> struct Rdo {
     else if (U == 1 && UR == 0 && L == 1 && DL == 1) { a = up2; b = l0; c = dl; }
     else if (U == 1 && UR == 1 && L == 1 && DL == 1) { a = up0; b = ur; c = l0; }
     Mv z; z.x = z.y = 0;
-    const Mv mva = a >= 0 ? F.blk[a].mv0 : z, mvb = b >= 0 ? F.blk[b].mv0 : z, mvc = c >= 0 ? F.blk[c].mv0 : z;
+    const Mv mva = a >= 0 ? be.ld_blk(F.blk + a).mv0 : z, mvb = b >= 0 ? be.ld_blk(F.blk + b).mv0 : z, mvc = c >= 0 ? be.ld_blk(F.blk + c).mv0 : z;
     Mv p;
     p.x = (int16_t)(mva.x < mvb.x ? imin(mvb.x, imax(mva.x, mvc.x)) : imin(mva.x, imax(mvb.x, mvc.x)));
     p.y = (int16_t)(mva.y < mvb.y ? imin(mvb.y, imax(mva.y, mvc.y)) : imin(mva.y, imax(mvb.y, mvc.y)));
@@ -214,7 +216,7 @@ template <class S, class B> struct Rdo {
     Ctx3 c;
     if (ypos >= MIN_BLOCK && xpos >= MIN_BLOCK && ypos + size < F.height && xpos + size < F.width && F.use_block_contexts && size <= MAX_TR) {
       const int bs = F.blk_stride, bi = (ypos / MIN_PB) * bs + xpos / MIN_PB;
-      const tb_rdo_blk_t &u = F.blk[bi - bs], &l = F.blk[bi - 1];
+      const tb_rdo_blk_t u = be.ld_blk(F.blk + bi - bs), l = be.ld_blk(F.blk + bi - 1);
       c.split = (u.size < size) + (l.size < size);
       c.cbp = (u.cbp_y > 0) + (l.cbp_y > 0);
       c.index = 3 * c.split + ((u.cbp_y > 0 || u.cbp_u > 0 || u.cbp_v > 0) + (l.cbp_y > 0 || l.cbp_u > 0 || l.cbp_v > 0));
@@ -837,7 +839,7 @@ template <class S, class B> struct Rdo {
     L.mvp = bi.mvp; L.cost = cost; L.coeff_ofs = -1;
     if (b.mode != MODE_SKIP && (b.cbp_y || b.cbp_u || b.cbp_v)) {
       const int tbc = b.tb_split && sc > 4;
-      const int ny = tb_rdo_coeff_count(size, b.tb_split), nc = tb_rdo_coeff_count(sc, tbc);
+      const int ny = coeff_count(size, b.tb_split), nc = coeff_count(sc, tbc);
       int16_t *dst = F.coeffs + (size_t)sb_index * TB_RDO_SB_COEFFS + coeff_used;
       L.coeff_ofs = coeff_used;
       be.pack_coeff(dst, qy, size, b.tb_split, b.cbp_y != 0);
