@@ -284,9 +284,20 @@ __global__ void __launch_bounds__(32) rdo_frame_kernel(FrameCtx<S> ctx, Work<S> 
   for (int sbx = 0; sbx < nsbx; sbx++) {
     if (row > 0) {
       const int need = min(sbx + 2, nsbx);
-      if ((threadIdx.x & 31) == 0)
-        while (prog[row - 1] < need) __nanosleep(200);
-      __syncwarp();
+      int give_up = 0;
+      if ((threadIdx.x & 31) == 0) {
+        const long long t0 = clock64();
+        while (prog[row - 1] < need) {
+          __nanosleep(200);
+          // a row that never publishes (it faulted) must not hang the launch: ~30 s of SM clocks, far beyond any super block
+          if (clock64() - t0 > 60000000000ll || prog[gridDim.x] != 0) { give_up = 1; break; }
+        }
+      }
+      give_up = __shfl_sync(FULL, give_up, 0);
+      if (give_up) {
+        if ((threadIdx.x & 31) == 0) prog[gridDim.x] = 1;  // error flag behind the per-row counters
+        return;
+      }
       __threadfence();
     }
     Rdo<S, DevBackend<S>> R(ctx, works[row], be);
@@ -329,9 +340,12 @@ void free_state() {
   } while (0)
 
 template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
-  const int w = f->width, h = f->height, sb = 1 << f->log2_sb_size, esz = (int)sizeof(S), pad = f->ref_pad;
+  const int w = f->width, h = f->height, sb = 1 << f->log2_sb_size, esz = (int)sizeof(S);
   const int nsbx = (w + sb - 1) / sb, nsby = (h + sb - 1) / sb, nsb = nsbx * nsby;
-  const int sy = f->ref_stride[0], sc = f->ref_stride[1], padc = pad >> 1;
+  // device planes use the padded geometry of the caller's reference frames; a frame without references (intra) may leave it unset:
+  // then the reference's own geometry (common/common_frame.c:435-452 with PADDING_Y = 160)
+  const int pad = f->ref_stride[0] > 0 ? f->ref_pad : 160, padc = pad >> 1;
+  const int sy = f->ref_stride[0] > 0 ? f->ref_stride[0] : ((w + 2 * pad + 15) & ~15), sc = f->ref_stride[0] > 0 ? f->ref_stride[1] : (((w >> 1) + 2 * padc + 15) & ~15);
   const size_t ref_y_bytes = (size_t)(h + 2 * pad) * sy * esz, ref_c_bytes = (size_t)((h >> 1) + 2 * padc) * sc * esz;
   if (D.w != w || D.h != h || D.esz != esz || D.sb != sb || D.pad != pad || D.sy != sy || D.sc != sc || D.nref < f->num_ref) {
     free_state();
@@ -342,7 +356,7 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
     CK(cudaMalloc(&D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4)));
     CK(cudaMalloc(&D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES));
     CK(cudaMalloc(&D.leaf_count, sizeof(int) * nsb));
-    CK(cudaMalloc(&D.progress, sizeof(int) * nsby));
+    CK(cudaMalloc(&D.progress, sizeof(int) * (nsby + 1)));
     CK(cudaMalloc(&D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS));
     CK(cudaMalloc(&D.works, sizeof(Work<S>) * (size_t)nsby));
     D.w = w; D.h = h; D.esz = esz; D.sb = sb; D.pad = pad; D.sy = sy; D.sc = sc; D.nref = f->num_ref > 5 ? f->num_ref : 5;
@@ -369,7 +383,7 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
   for (int r = 0; r < f->num_ref; r++)
     for (int p = 0; p < 3; p++)
       CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(D.progress, 0, sizeof(int) * nsby, st));
+  CK(cudaMemsetAsync(D.progress, 0, sizeof(int) * (nsby + 1), st));
   rdo_frame_kernel<S><<<nsby, 32, 0, st>>>(C, (Work<S> *)D.works, D.progress, nsbx);
   CK(cudaGetLastError());
   for (int p = 0; p < 3; p++)
@@ -379,7 +393,10 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
   CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDeviceToHost, st));
+  int wedged = 0;
+  CK(cudaMemcpyAsync(&wedged, D.progress + nsby, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (wedged) { snprintf(D.err, sizeof(D.err), "rdo_frame_kernel: a super-block row stopped publishing progress"); return TB_ERR_CUDA; }
   return TB_OK;
 }
 
@@ -393,9 +410,12 @@ uint64_t tb_rdo_launch_count(void) { return g_rdo_launches; }
 int tb_rdo_encode_frame(const tb_rdo_frame_t *f) {
   if (!f || f->num_ref > TB_RDO_MAX_REF || f->num_ref < 0 || f->log2_sb_size > 7 || f->log2_sb_size < 4 || (f->sample_bytes != 1 && f->sample_bytes != 2) || f->width <= 0 ||
       f->height <= 0 || (f->width & 7) || (f->height & 7) || f->interp_ref == 2 || f->qp < 0 || f->qp > 51 || !f->blk || !f->leaves || !f->leaf_count || !f->coeffs ||
-      (f->num_ref > 0 && f->ref_pad < 16))
+      (f->num_ref > 0 && (f->ref_pad < 16 || f->ref_stride[0] < f->width + 2 * f->ref_pad))) {
+    snprintf(D.err, sizeof(D.err), "unsupported frame description (%dx%d, %d refs, sb %d, interp_ref %d, qp %d, pad %d)", f ? f->width : 0, f ? f->height : 0,
+             f ? f->num_ref : 0, f ? f->log2_sb_size : 0, f ? f->interp_ref : 0, f ? f->qp : 0, f ? f->ref_pad : 0);
     return TB_ERR_ARG;
-  if (tb_init(-1) != TB_OK) return TB_ERR_CUDA;  // no CPU path: without a CUDA device the call fails
+  }
+  if (tb_init(-1) != TB_OK) { snprintf(D.err, sizeof(D.err), "no CUDA device: %s", tb_last_error()); return TB_ERR_CUDA; }  // no CPU path
   cudaStream_t st = (cudaStream_t)tb_stream();
   g_rdo_launches++;
   return f->sample_bytes == 1 ? run_frame<uint8_t>(f, st) : run_frame<uint16_t>(f, st);

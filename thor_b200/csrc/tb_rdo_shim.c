@@ -35,6 +35,7 @@ void find_block_contexts_lbd(int ypos, int xpos, int height, int width, int size
 void find_block_contexts_hbd(int ypos, int xpos, int height, int width, int size, deblock_data_t *deblock_data, block_context_t *block_context, int enable);
 /* optional (weak): only oracle/librdo_hostcheck.so has it */
 int tb_rdo_encode_sb(const tb_rdo_frame_t *f, int sbx, int sby) __attribute__((weak));
+const char *tb_rdo_last_error(void) __attribute__((weak));
 
 static struct {
   int w, h, nsb, valid, frame_ok, verify, inited;
@@ -88,6 +89,8 @@ static void fill_desc(tb_rdo_frame_t *f, encoder_info_t *e, int esz) {
   f->enable_bipred = p->enable_bipred; f->enable_tb_split = p->enable_tb_split; f->enable_pb_split = p->enable_pb_split; f->encoder_speed = p->encoder_speed;
   f->intra_rdo = p->intra_rdo; f->use_block_contexts = p->use_block_contexts; f->cfl_intra = p->cfl_intra; f->cfl_inter = p->cfl_inter;
   f->early_skip_thr = p->early_skip_thr;
+  /* every padded frame of the encoder has the same geometry (enc/mainenc.c:181-186); intra frames have no reference but still need it */
+  f->ref_stride[0] = e->ref[0]->stride_y; f->ref_stride[1] = e->ref[0]->stride_c; f->ref_pad = e->ref[0]->pad_hor_y;
   for (int r = 0; r < fi->num_ref; r++) {
     const int ra = fi->ref_array[r];
     yuv_frame_t *ref = ra >= 0 ? e->ref[ra] : e->interp_frames[0];
@@ -254,8 +257,12 @@ static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, i
   }
 
   if (xpos == 0 && ypos == 0) {
-    G.frame_ok = tb_rdo_encode_frame(&f) == TB_OK;
+    const int rc = tb_rdo_encode_frame(&f);
+    G.frame_ok = rc == TB_OK;
     if (G.frame_ok) G.frames_dev++; else G.frames_host++;
+    if (!G.frame_ok)
+      fprintf(stderr, "[tb_rdo_shim] frame %d (type %d, %d refs): tb_rdo_encode_frame returned %d (%s) -> the reference's host loop takes this frame\n", e->frame_info.frame_num,
+              e->frame_info.frame_type, e->frame_info.num_ref, rc, tb_rdo_last_error ? tb_rdo_last_error() : "");
   }
   if (!G.frame_ok) return real(e, size, ypos, xpos, qp, sub);
   /* tb_rdo_encode_frame wrote the whole reconstruction into e->rec; here: this super block's deblock_data + bits */
