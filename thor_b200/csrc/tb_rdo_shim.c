@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "global.h"
 #include "mainenc.h"
 #include "encode_block.h"
@@ -44,13 +45,17 @@ static struct {
   int32_t *leaf_count;
   int16_t *coeffs;
   long sb_total, sb_bad, frames_dev, frames_host;
+  double t_rdo, t_emit;
 } G;
+
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 static void shim_report(void) {
   if (G.verify)
     fprintf(stderr, "[tb_rdo_shim] verify: %ld super blocks compared with the reference's process_block, %ld differ\n", G.sb_total, G.sb_bad);
   if (getenv("TB_RDO_STATS"))
-    fprintf(stderr, "[tb_rdo_shim] frames decided by tb_rdo_encode_frame: %ld, by the reference's host loop: %ld\n", G.frames_dev, G.frames_host);
+    fprintf(stderr, "[tb_rdo_shim] frames decided by tb_rdo_encode_frame: %ld, by the reference's host loop: %ld; seconds in tb_rdo_encode_frame %.3f, in serialisation %.3f\n",
+            G.frames_dev, G.frames_host, G.t_rdo, G.t_emit);
 }
 
 static int supported(const encoder_info_t *e, int qp, int sub, int hbd) {
@@ -257,7 +262,10 @@ static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, i
   }
 
   if (xpos == 0 && ypos == 0) {
+    const double t0 = now_s();
     const int rc = tb_rdo_encode_frame(&f);
+    G.t_rdo += now_s() - t0;
+    if (getenv("TB_RDO_TRACE")) fprintf(stderr, "[tb_rdo_shim] frame %d type %d refs %d qp %d: tb_rdo_encode_frame %.1f ms\n", e->frame_info.frame_num, e->frame_info.frame_type, e->frame_info.num_ref, (int)e->frame_info.qp, 1e3 * (now_s() - t0));
     G.frame_ok = rc == TB_OK;
     if (G.frame_ok) G.frames_dev++; else G.frames_host++;
     if (!G.frame_ok)
@@ -266,9 +274,11 @@ static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, i
   }
   if (!G.frame_ok) return real(e, size, ypos, xpos, qp, sub);
   /* tb_rdo_encode_frame wrote the whole reconstruction into e->rec; here: this super block's deblock_data + bits */
+  const double t1 = now_s();
   blk_to_deblock(e, xpos, ypos, x1, y1);
   walk_t w = {e, G.leaves + (size_t)sbi * TB_RDO_MAX_LEAVES, G.coeffs + (size_t)sbi * TB_RDO_SB_COEFFS, G.leaf_count[sbi], 0, hbd};
   emit_node(&w, xpos, ypos, sb);
+  G.t_emit += now_s() - t1;
   uint32_t cost = 0;
   for (int i = 0; i < w.n; i++) cost += w.leaves[i].cost;
   return (int)cost;
