@@ -11,6 +11,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include "../thor_b200/csrc/tb_rdo.h"
 #include "thor_oracle.h"
 
@@ -46,8 +50,76 @@ template <class S> struct Orc;
 ORC_FWD(uint8_t, lbd)
 ORC_FWD(uint16_t, hbd)
 
+// "warps" simulated by host threads (TBR_HOST_WARPS=N): the exchange area and the barrier of one simulated CTA
+struct Exchange {
+  int nw = 1;
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0, phase = 0;
+  uint32_t cost[16];
+  int idx[16];
+  uint32_t rng[16][2];
+  int flag[16];
+  Mv mv[TB_RDO_MAX_REF][16];
+  uint32_t sad[TB_RDO_MAX_REF];
+  unsigned char buf[256];
+  // The oracle's functions keep static scratch buffers (not re-entrant), so the simulated warps never run at the same time: a thread
+  // holds `run` while it executes and gives it up only while it waits at a barrier.  The interleaving is arbitrary, the semantics are
+  // those of warps that only communicate at CTA barriers.
+  std::mutex run;
+  void barrier() {
+    if (nw == 1) return;
+    run.unlock();
+    {
+      std::unique_lock<std::mutex> lk(m);
+      const int ph = phase;
+      if (++waiting == nw) { waiting = 0; phase++; cv.notify_all(); }
+      else cv.wait(lk, [&] { return phase != ph; });
+    }
+    run.lock();
+  }
+};
+
 template <class S> struct OracleBackend {
   const FrameCtx<S> *F;
+  Exchange *X = nullptr;
+  int wid = 0;
+  // ---- SPMD over simulated warps (see tb_rdo.h)
+  int warp() const { return wid; }
+  bool mine(int k) const { return (k % X->nw) == wid; }
+  void cta_sync() const { X->barrier(); }
+  void put_me(int ref, const Mv *mv16, uint32_t sad) const { memcpy(X->mv[ref], mv16, 16 * sizeof(Mv)); X->sad[ref] = sad; }
+  void get_me(int ref, Mv *mv16, uint32_t *sad) const { memcpy(mv16, X->mv[ref], 16 * sizeof(Mv)); *sad = X->sad[ref]; }
+  int reduce_best(uint32_t *cost, int *idx) const {
+    X->cost[wid] = *cost; X->idx[wid] = *idx;
+    X->barrier();
+    int w = 0;
+    for (int k = 1; k < X->nw; k++)
+      if (X->cost[k] < X->cost[w] || (X->cost[k] == X->cost[w] && X->idx[k] < X->idx[w])) w = k;
+    *cost = X->cost[w]; *idx = X->idx[w];
+    X->barrier();
+    return w;
+  }
+  void bcast(void *p, int nbytes, int owner) const {
+    if (wid == owner) memcpy(X->buf, p, nbytes);
+    X->barrier();
+    if (wid != owner) memcpy(p, X->buf, nbytes);
+    X->barrier();
+  }
+  void reduce_range(uint32_t *worst, uint32_t *best) const {
+    X->rng[wid][0] = *worst; X->rng[wid][1] = *best;
+    X->barrier();
+    for (int k = 0; k < X->nw; k++) { if (X->rng[k][0] > *worst) *worst = X->rng[k][0]; if (X->rng[k][1] < *best) *best = X->rng[k][1]; }
+    X->barrier();
+  }
+  int reduce_or(int f) const {
+    X->flag[wid] = f;
+    X->barrier();
+    int r = 0;
+    for (int k = 0; k < X->nw; k++) r |= X->flag[k];
+    X->barrier();
+    return r;
+  }
   // scratch
   int16_t block[128 * 128], coeff[128 * 128], rcoeff[128 * 128], rblock[128 * 128], tmp[32 * 32];
   S compact[128 * 128], left[2 * 128 + 16], top[2 * 128 + 16];
@@ -164,15 +236,31 @@ template <class S> static void make_ctx(FrameCtx<S> &C, const tb_rdo_frame_t *f)
 
 template <class S> static int run(const tb_rdo_frame_t *f, int sbx0, int sby0, int one) {
   static FrameCtx<S> C;
-  static Work<S> W;
-  static OracleBackend<S> be;
+  const char *e = getenv("TBR_HOST_WARPS");
+  const int nw = e ? atoi(e) : 1;
+  if (nw < 1 || nw > 16) return TB_ERR_ARG;
+  static std::vector<Work<S>> W;
+  static std::vector<OracleBackend<S>> be;
+  static Exchange X;
+  if ((int)W.size() != nw) { W.resize(nw); be.resize(nw); }
   make_ctx(C, f);
-  be.F = &C;
+  X.nw = nw;
+  for (int k = 0; k < nw; k++) { be[k].F = &C; be[k].X = &X; be[k].wid = k; }
   const int nsbx = (C.width + C.sb_size - 1) / C.sb_size, nsby = (C.height + C.sb_size - 1) / C.sb_size;
   for (int sby = one ? sby0 : 0; sby < (one ? sby0 + 1 : nsby); sby++)
     for (int sbx = one ? sbx0 : 0; sbx < (one ? sbx0 + 1 : nsbx); sbx++) {
-      Rdo<S, OracleBackend<S>> R(C, W, be);
-      R.process_sb(sbx, sby);
+      auto body = [&](int k) {
+        if (nw > 1) X.run.lock();
+        Rdo<S, OracleBackend<S>> R(C, W[k], W[0], be[k]);
+        R.process_sb(sbx, sby);
+        if (nw > 1) X.run.unlock();
+      };
+      if (nw == 1) body(0);
+      else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nw; k++) th.emplace_back(body, k);
+        for (auto &t : th) t.join();
+      }
     }
   return TB_OK;
 }

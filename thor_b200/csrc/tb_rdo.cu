@@ -29,21 +29,99 @@ using namespace tbr;
 
 namespace {
 
-template <class S> struct RdoShared {
-  TxScratch sc;
+// per-primitive cycle counters (TB_RDO_PROF=1): which part of the RD loop the warp spends its time in
+enum { PF_INTERP, PF_ME, PF_MEBI, PF_TX, PF_BITS, PF_SSD, PF_INTRA, PF_COPY, PF_ES, PF_WAIT, PF_TOTAL, PF_N };
+struct Prof {
+  long long *acc;
+  int k;
+  long long t0;
+#ifdef __CUDA_ARCH__
+  __device__ __forceinline__ Prof(long long *a, int kk) : acc(a), k(kk), t0(clock64()) {}
+  __device__ __forceinline__ ~Prof() { acc[k] += clock64() - t0; }
+#else
+  Prof(long long *a, int kk) : acc(a), k(kk), t0(0) {}
+#endif
+};
+
+constexpr int RDO_MAX_WARPS = 16;
+// per-CTA: tables and the exchange area of the SPMD control flow (tb_rdo.h)
+struct RdoCta {
   alignas(16) int8_t tab8[TX_TABLE_BYTES];       // int8 DCT matrices (plain, transposed) + 16x16 zig-zag table
   alignas(16) int16_t tab16[DCT_TAB_SIZE];       // int16 DCT matrices (warp_fwd_transform of the early-skip test)
-  alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual; coefficient scan for the bit count
-  alignas(16) int16_t out16[256];
+  uint32_t x_cost[RDO_MAX_WARPS];
+  int x_idx[RDO_MAX_WARPS];
+  uint32_t x_rng[RDO_MAX_WARPS][2];
+  int x_flag[RDO_MAX_WARPS];
+  tb_mv_t x_mv[TB_RDO_MAX_REF][16];
+  uint32_t x_sad[TB_RDO_MAX_REF];
+  alignas(16) int x_buf[32];
+  int give_up;
+};
+// per-warp scratch
+template <class S> struct RdoShared {
+  long long prof[PF_N];
+  TxScratch sc;
+  alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual
+  alignas(16) int16_t out16[256];                // transform output of the early-skip test; coefficient scan for the bit count
   alignas(16) S left[256], top[256], filt[4 * 128 + 4];
   tb_txfm_result_t res;
 };
 
 template <class S> struct DevBackend {
   const FrameCtx<S> *F;
-  RdoShared<S> *sh;
+  RdoShared<S> *sh;  // this warp's scratch
+  RdoCta *cta;
+  int nw, wid;
+
+  // ---- SPMD over the warps of the CTA (tb_rdo.h): every warp reaches every CTA barrier (the control flow is replicated)
+  __device__ __forceinline__ int warp() const { return wid; }
+  __device__ __forceinline__ bool mine(int k) const { return (k % nw) == wid; }
+  __device__ void cta_sync() const { __threadfence(); __syncthreads(); }
+  __device__ void put_me(int ref, const Mv *mv16, uint32_t sad) const {
+    if ((threadIdx.x & 31) < 16) cta->x_mv[ref][threadIdx.x & 31] = mv16[threadIdx.x & 31];
+    if ((threadIdx.x & 31) == 0) cta->x_sad[ref] = sad;
+  }
+  __device__ void get_me(int ref, Mv *mv16, uint32_t *sad) const {  // every lane fills its own (replicated) copy
+#pragma unroll
+    for (int k = 0; k < 16; k++) mv16[k] = cta->x_mv[ref][k];
+    *sad = cta->x_sad[ref];
+  }
+  __device__ int reduce_best(uint32_t *cost, int *idx) const {
+    if ((threadIdx.x & 31) == 0) { cta->x_cost[wid] = *cost; cta->x_idx[wid] = *idx; }
+    __syncthreads();
+    int w = 0;
+    for (int k = 1; k < nw; k++)
+      if (cta->x_cost[k] < cta->x_cost[w] || (cta->x_cost[k] == cta->x_cost[w] && cta->x_idx[k] < cta->x_idx[w])) w = k;
+    *cost = cta->x_cost[w]; *idx = cta->x_idx[w];
+    __syncthreads();
+    return w;
+  }
+  __device__ void bcast(void *p, int nbytes, int owner) const {  // p: per-thread (replicated) object, multiple of 4 bytes, <= 128
+    int *q = (int *)p;
+    if (wid == owner && (threadIdx.x & 31) == 0)
+      for (int k = 0; k < nbytes / 4; k++) cta->x_buf[k] = q[k];
+    __syncthreads();
+    if (wid != owner)
+      for (int k = 0; k < nbytes / 4; k++) q[k] = cta->x_buf[k];
+    __syncthreads();
+  }
+  __device__ void reduce_range(uint32_t *worst, uint32_t *best) const {
+    if ((threadIdx.x & 31) == 0) { cta->x_rng[wid][0] = *worst; cta->x_rng[wid][1] = *best; }
+    __syncthreads();
+    for (int k = 0; k < nw; k++) { *worst = max(*worst, cta->x_rng[k][0]); *best = min(*best, cta->x_rng[k][1]); }
+    __syncthreads();
+  }
+  __device__ int reduce_or(int f) const {
+    if ((threadIdx.x & 31) == 0) cta->x_flag[wid] = f;
+    __syncthreads();
+    int r = 0;
+    for (int k = 0; k < nw; k++) r |= cta->x_flag[k];
+    __syncthreads();
+    return r;
+  }
 
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+#define PROF(k) Prof prof__(sh->prof, k)
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 
   __device__ tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const {
@@ -63,6 +141,7 @@ template <class S> struct DevBackend {
   }
   // prediction of one block; widths that are not powers of two (rectangular blocks at the right frame edge) take the per-sample form
   __device__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
+    PROF(PF_INTERP);
     sync();
     if (!(w & (w - 1))) warp_interp<S>(dst, ds, ref, rs, w, h, mv.x, mv.y, sign, chroma, bip, pw, ph, xpos, ypos, F->bitdepth);
     else {
@@ -88,6 +167,7 @@ template <class S> struct DevBackend {
     interp_any(dst, ds, ref, rs, w, h, mv, sign, 1, 0, pw, ph, xc, yc);
   }
   __device__ void avg(S *dst, const S *a, const S *b, int stride, int w, int h) const {
+    PROF(PF_COPY);
     sync();
     for (int p = lane(); p < w * h; p += 32) {
       const int row = p / w, col = p - row * w, o = row * stride + col;
@@ -96,6 +176,7 @@ template <class S> struct DevBackend {
     sync();
   }
   __device__ void sat2ab(S *dst, const S *org, int os, const S *pred, int size) const {
+    PROF(PF_COPY);
     const int maxv = (1 << F->bitdepth) - 1, ls = ilog2(size);
     sync();
     for (int p = lane(); p < size * size; p += 32) {
@@ -105,6 +186,7 @@ template <class S> struct DevBackend {
     sync();
   }
   __device__ void copy(S *dst, int ds, const S *src, int ss, int w, int h) const {
+    PROF(PF_COPY);
     sync();
     for (int p = lane(); p < w * h; p += 32) {
       const int row = p / w, col = p - row * w;
@@ -113,12 +195,14 @@ template <class S> struct DevBackend {
     sync();
   }
   __device__ void copy_coeff(int16_t *dst, const int16_t *src) const {
+    PROF(PF_COPY);
     sync();
     for (int p = lane(); p < 1024 / 4; p += 32) ((uint2 *)dst)[p] = ((const uint2 *)src)[p];
     sync();
   }
   __device__ void intra_predict(S *dst, int ds, const S *recf, int rfs, const S *rblock, int rbs, int i, int j, int ypos, int xpos, int size, int ur, int dl, int tbs,
                                 int mode) const {
+    PROF(PF_INTRA);
     sync();
     S tl;
     warp_make_top_and_left<S>(sh->left, sh->top, tl, recf, rfs, rblock, rbs, i, j, ypos, xpos, size, ur, dl, tbs, F->bitdepth);
@@ -128,18 +212,20 @@ template <class S> struct DevBackend {
     sync();
   }
   __device__ void cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride) const {
+    PROF(PF_INTRA);
     sync();
     warp_cfl<S>(y, u, v, ry, n, cstride, stride, 1, F->bitdepth);
     sync();
   }
   __device__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
+    PROF(PF_TX);
     sync();
     int cbp;
     if (size >= 16) {
       tb_txfm_item_t q;
       q.orig = orig; q.pred = pred; q.rec = rec; q.coeffq = cq; q.ostride = os; q.pstride = ps; q.rstride = rs;
       q.size = (uint8_t)size; q.qp = (uint8_t)qp; q.coeff_type = (uint8_t)coeff_type; q.fast = (uint8_t)(fast ? TB_TXFM_FAST : 0);
-      tx_big_chain<S, 1>(q, F->bitdepth, sh->sc, nullptr, sh->tab8, sh->tab8 + DCT_TAB8_SIZE, nullptr, nullptr, &sh->res);
+      tx_big_chain<S, 1>(q, F->bitdepth, sh->sc, nullptr, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, nullptr, nullptr, &sh->res);
       sync();
       cbp = sh->res.cbp;
     } else {
@@ -148,7 +234,7 @@ template <class S> struct DevBackend {
         uint64_t ssd;
         int bits;
         if (size == 4) cbp = thread_txfm4<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, ssd, 0, bits);
-        else cbp = thread_txfm8<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, sh->tab8, sh->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
+        else cbp = thread_txfm8<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
       }
       cbp = __shfl_sync(FULL, cbp, 0);
     }
@@ -156,6 +242,7 @@ template <class S> struct DevBackend {
     return cbp;
   }
   __device__ int coeff_bits(const int16_t *cq, int size, int type) const {
+    PROF(PF_BITS);
     const int qs = min(size, 16), nq = qs * qs, lq = ilog2(qs);
     sync();
     for (int p = lane(); p < nq; p += 32) sh->out16[zigzag_index(p >> lq, p & (qs - 1), qs)] = cq[p];
@@ -165,6 +252,7 @@ template <class S> struct DevBackend {
     return bits;
   }
   __device__ uint64_t ssd(const S *a, int as, const S *b, int bs, int w, int h) const {
+    PROF(PF_SSD);
     sync();
     if (!(w & (w - 1))) return warp_ssd<S>(a, as, b, bs, w, h);
     uint64_t acc = 0;
@@ -175,11 +263,13 @@ template <class S> struct DevBackend {
     return warp_sum64(acc);
   }
   __device__ unsigned sad(const S *a, int as, const S *b, int bs, int w, int h) const {
+    PROF(PF_SSD);
     sync();
     return warp_sad<S>(a, as, b, bs, w, h);
   }
   __device__ int me(const S *org, int os, const S *ref, int rs, int size, int w, int h, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
                     int ncand) const {
+    PROF(PF_ME);
     sync();
     MeCtx c;
     c.size = size; c.width = w; c.height = h; c.sign = sign; c.s = sign ? -1 : 1; c.xpos = xpos; c.ypos = ypos; c.fw = F->width; c.fh = F->height;
@@ -196,6 +286,7 @@ template <class S> struct DevBackend {
   }
   __device__ int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
                        int ncand) const {
+    PROF(PF_MEBI);
     sync();
     int mx, my;
     uint32_t cost;
@@ -208,6 +299,7 @@ template <class S> struct DevBackend {
   }
   // check_early_skip_sub_block (enc/encode_block.c:2147-2180): 2x2 average of the residual, (size/2)-point transform, any |c| > threshold
   __device__ int es_luma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+    PROF(PF_ES);
     const int s2 = size / 2, l2 = ilog2(s2);
     sync();
     for (int p = lane(); p < s2 * s2; p += 32) {
@@ -220,7 +312,7 @@ template <class S> struct DevBackend {
       sh->blk16[p] = (int16_t)(sum >> 2);
     }
     sync();
-    warp_fwd_transform(sh->blk16, s2, s2, 0, F->bitdepth, sh->sc, sh->out16, sh->tab16);
+    warp_fwd_transform(sh->blk16, s2, s2, 0, F->bitdepth, sh->sc, sh->out16, cta->tab16);
     int hit = 0;
     for (int p = lane(); p < s2 * s2; p += 32) hit |= iabs((int)sh->out16[p]) > threshold;
     hit = __any_sync(FULL, hit);
@@ -229,6 +321,7 @@ template <class S> struct DevBackend {
   }
   // check_early_skip_sub_blockC :2214-2229 with calc_cbp_simd
   __device__ int es_chroma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+    PROF(PF_ES);
     const int ls = ilog2(size);
     sync();
     for (int p = lane(); p < size * size; p += 32) {
@@ -270,42 +363,54 @@ template <class S> struct DevBackend {
   }
 };
 
+constexpr int RDO_WARPS = 8;  // warps per CTA: 8 x 32 threads x 255 registers = the whole register file of an SM
+
 template <class S>
-__global__ void __launch_bounds__(32) rdo_frame_kernel(FrameCtx<S> ctx, Work<S> *works, int *progress, int nsbx) {
-  __shared__ RdoShared<S> sh;
-  dct_tab8_fill(sh.tab8, sh.tab8 + DCT_TAB8_SIZE);
-  dct_tab_fill(sh.tab16);
-  for (int t = threadIdx.x; t < 256; t += blockDim.x) ((uint8_t *)(sh.tab8 + 2 * DCT_TAB8_SIZE))[t] = (uint8_t)zigzag_index(t >> 4, t & 15, 16);
+__global__ void __launch_bounds__(32 * RDO_WARPS, 1) rdo_frame_kernel(FrameCtx<S> ctx, Work<S> *works, int *progress, int nsbx, unsigned long long *prof_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RdoCta &cta = *(RdoCta *)smem_raw;
+  RdoShared<S> *shs = (RdoShared<S> *)(smem_raw + ((sizeof(RdoCta) + 15) & ~(size_t)15));
+  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RdoShared<S> &sh = shs[wid];
+  for (int k = lane; k < PF_N; k += 32) sh.prof[k] = 0;
+  const long long t_start = clock64();
+  dct_tab8_fill(cta.tab8, cta.tab8 + DCT_TAB8_SIZE);
+  dct_tab_fill(cta.tab16);
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) ((uint8_t *)(cta.tab8 + 2 * DCT_TAB8_SIZE))[t] = (uint8_t)zigzag_index(t >> 4, t & 15, 16);
+  if (threadIdx.x == 0) cta.give_up = 0;
   __syncthreads();
   const int row = blockIdx.x;
   DevBackend<S> be;
-  be.F = &ctx; be.sh = &sh;
+  be.F = &ctx; be.sh = &sh; be.cta = &cta; be.nw = nw; be.wid = wid;
   volatile int *prog = progress;
   for (int sbx = 0; sbx < nsbx; sbx++) {
     if (row > 0) {
+      Prof pw(sh.prof, PF_WAIT);
       const int need = min(sbx + 2, nsbx);
-      int give_up = 0;
-      if ((threadIdx.x & 31) == 0) {
+      if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (prog[row - 1] < need) {
           __nanosleep(200);
           // a row that never publishes (it faulted) must not hang the launch: ~30 s of SM clocks, far beyond any super block
-          if (clock64() - t0 > 60000000000ll || prog[gridDim.x] != 0) { give_up = 1; break; }
+          if (clock64() - t0 > 60000000000ll || prog[gridDim.x] != 0) { cta.give_up = 1; break; }
         }
       }
-      give_up = __shfl_sync(FULL, give_up, 0);
-      if (give_up) {
-        if ((threadIdx.x & 31) == 0) prog[gridDim.x] = 1;  // error flag behind the per-row counters
+      __syncthreads();
+      if (cta.give_up) {
+        if (threadIdx.x == 0) prog[gridDim.x] = 1;  // error flag behind the per-row counters
         return;
       }
       __threadfence();
     }
-    Rdo<S, DevBackend<S>> R(ctx, works[row], be);
+    Rdo<S, DevBackend<S>> R(ctx, works[row * nw + wid], works[row * nw], be);
     R.process_sb(sbx, row);
-    __syncwarp();
-    __threadfence();  // every writing lane orders its stores before the flag
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) prog[row] = sbx + 1;
+    __threadfence();  // every writing thread orders its stores before the flag
+    __syncthreads();
+    if (threadIdx.x == 0) prog[row] = sbx + 1;
+  }
+  if (prof_out && lane == 0) {
+    sh.prof[PF_TOTAL] = clock64() - t_start;
+    for (int k = 0; k < PF_N; k++) atomicAdd(&prof_out[k], (unsigned long long)sh.prof[k]);
   }
 }
 
@@ -321,6 +426,7 @@ struct DevState {
   int *leaf_count = nullptr, *progress = nullptr;
   int16_t *coeffs = nullptr;
   void *works = nullptr;
+  unsigned long long *prof = nullptr;
   char err[256] = {0};
 } D;
 
@@ -328,7 +434,7 @@ void free_state() {
   for (int p = 0; p < 3; p++) { cudaFree(D.org[p]); cudaFree(D.rec[p]); D.org[p] = D.rec[p] = nullptr; }
   for (int r = 0; r < TB_RDO_MAX_REF; r++)
     for (int p = 0; p < 3; p++) { cudaFree(D.ref[r][p]); D.ref[r][p] = nullptr; }
-  cudaFree(D.blk); cudaFree(D.leaves); cudaFree(D.leaf_count); cudaFree(D.progress); cudaFree(D.coeffs); cudaFree(D.works);
+  cudaFree(D.blk); cudaFree(D.leaves); cudaFree(D.leaf_count); cudaFree(D.progress); cudaFree(D.coeffs); cudaFree(D.works); cudaFree(D.prof); D.prof = nullptr;
   D.blk = nullptr; D.leaves = nullptr; D.leaf_count = D.progress = nullptr; D.coeffs = nullptr; D.works = nullptr;
   D.w = 0;
 }
@@ -358,7 +464,8 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
     CK(cudaMalloc(&D.leaf_count, sizeof(int) * nsb));
     CK(cudaMalloc(&D.progress, sizeof(int) * (nsby + 1)));
     CK(cudaMalloc(&D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS));
-    CK(cudaMalloc(&D.works, sizeof(Work<S>) * (size_t)nsby));
+    CK(cudaMalloc(&D.works, sizeof(Work<S>) * (size_t)nsby * RDO_WARPS));
+    CK(cudaMalloc(&D.prof, sizeof(unsigned long long) * PF_N));
     D.w = w; D.h = h; D.esz = esz; D.sb = sb; D.pad = pad; D.sy = sy; D.sc = sc; D.nref = f->num_ref > 5 ? f->num_ref : 5;
   }
   FrameCtx<S> C;
@@ -384,7 +491,12 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
     for (int p = 0; p < 3; p++)
       CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(D.progress, 0, sizeof(int) * (nsby + 1), st));
-  rdo_frame_kernel<S><<<nsby, 32, 0, st>>>(C, (Work<S> *)D.works, D.progress, nsbx);
+  const bool want_prof = getenv("TB_RDO_PROF") != nullptr;
+  if (want_prof) CK(cudaMemsetAsync(D.prof, 0, sizeof(unsigned long long) * PF_N, st));
+  const size_t smem = ((sizeof(RdoCta) + 15) & ~(size_t)15) + sizeof(RdoShared<S>) * RDO_WARPS;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[esz]) { CK(cudaFuncSetAttribute(rdo_frame_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set[esz] = true; }
+  rdo_frame_kernel<S><<<nsby, 32 * RDO_WARPS, smem, st>>>(C, (Work<S> *)D.works, D.progress, nsbx, want_prof ? D.prof : nullptr);
   CK(cudaGetLastError());
   for (int p = 0; p < 3; p++)
     CK(cudaMemcpy2DAsync(f->rec[p], (size_t)f->rec_stride[p ? 1 : 0] * esz, C.rec[p], (size_t)(p ? sc : sy) * esz, (size_t)(p ? w >> 1 : w) * esz, p ? h >> 1 : h,
@@ -396,6 +508,14 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
   int wedged = 0;
   CK(cudaMemcpyAsync(&wedged, D.progress + nsby, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (want_prof) {
+    unsigned long long pr[PF_N];
+    CK(cudaMemcpy(pr, D.prof, sizeof(pr), cudaMemcpyDeviceToHost));
+    static const char *names[PF_N] = {"interp", "me", "me_bi", "tx_chain", "coeff_bits", "ssd_sad", "intra", "copy_avg", "early_skip", "wavefront_wait", "total"};
+    fprintf(stderr, "[tb_rdo prof] %d rows x %d warps:", nsby, RDO_WARPS);
+    for (int k = 0; k < PF_N; k++) fprintf(stderr, " %s %.1f%%", names[k], 100.0 * (double)pr[k] / (double)(pr[PF_TOTAL] ? pr[PF_TOTAL] : 1));
+    fprintf(stderr, "\n");
+  }
   if (wedged) { snprintf(D.err, sizeof(D.err), "rdo_frame_kernel: a super-block row stopped publishing progress"); return TB_ERR_CUDA; }
   return TB_OK;
 }

@@ -2,8 +2,14 @@
 //   * nvcc, device backend (tb_rdo_dev.cuh): the product — one CTA per super block inside rdo_frame_kernel;
 //   * g++,  oracle backend (oracle/rdo_hostcheck.cpp): TEST INFRASTRUCTURE — the same control flow over the plain-C oracle's
 //     primitives, used here (no GPU in the build container) to pin the control flow against the compiled reference SB by SB.
-// The control flow is scalar and warp-uniform: on the device every lane of the CTA's first warp executes it redundantly and
-// the backend's primitives are the warp-cooperative routines of tb_device.cuh.  Nothing in this file touches samples directly.
+// The control flow is scalar and warp-uniform, and it is SPMD over the NW warps of a CTA (NW = 1 on the host unless the host check
+// simulates warps with threads): every warp executes the whole control flow on its own scratch blocks (Work), so sequential sections
+// (neighbour derivation, the bipred refinement, the recursion itself) are simply replicated and stay consistent without communication.
+// Two kinds of sections are DISTRIBUTED: the motion searches of the reference frames (one reference per warp; results exchanged through
+// the backend and the candidate lists replayed by the other warps) and the RD candidates of a block (candidate k is evaluated by warp
+// k mod NW).  The reference keeps the first candidate with the strictly smallest cost; that is the minimum of (cost, k), which the
+// backend's reduction returns together with the warp that holds the winning reconstruction; that warp alone commits the block.
+// The backend's primitives are the warp-cooperative routines of tb_device.cuh.  Nothing in this file touches samples directly.
 //
 // What is restated (reference file:line at each function): process_block enc/encode_block.c:2401-2565, early skip :2123-2399,
 // mode_decision_rdo :1835-2120, search_{intra,inter,bipred}_prediction_params :928-1098, 1679-1833, encode_block :1340-1514 with
@@ -151,13 +157,18 @@ template <class S> struct Work {
 
 template <class S, class B> struct Rdo {
   FrameCtx<S> &F;
-  Work<S> &W;
+  Work<S> &W;    // this warp's scratch
+  Work<S> &W0;   // warp 0's scratch: holds the CTA-shared top-down save area
   B &be;
   int best_ref;      // frame_info->best_ref (per super block)
   int sb_index;
   int n_leaves, coeff_used;
+  // distributed candidate evaluation: running candidate index and this warp's best so far
+  int cidx, loc_idx;
+  uint32_t loc_cost, loc_worst, loc_bestc;
 
-  TBR_HD Rdo(FrameCtx<S> &f, Work<S> &w, B &b) : F(f), W(w), be(b), best_ref(-1), sb_index(0), n_leaves(0), coeff_used(0) {}
+  TBR_HD Rdo(FrameCtx<S> &f, Work<S> &w, Work<S> &w0, B &b)
+      : F(f), W(w), W0(w0), be(b), best_ref(-1), sb_index(0), n_leaves(0), coeff_used(0), cidx(0), loc_idx(0), loc_cost(MAX_U32), loc_worst(0), loc_bestc(MAX_U32) {}
 
   // ---------------------------------------------------------------------------------------------------------------
   // neighbour state
@@ -631,22 +642,35 @@ template <class S, class B> struct Rdo {
   // ---------------------------------------------------------------------------------------------------------------
   // mode_decision_rdo :1835-2120
   // ---------------------------------------------------------------------------------------------------------------
-  TBR_HD void try_cand(BlockInfo &bi, Cand &c, int w, int h, uint32_t &min_cost, uint32_t *out_cost = nullptr) {
+  TBR_HD void cand_group_begin() { cidx = 0; loc_idx = 0x7fffffff; loc_cost = MAX_U32; loc_worst = 0; loc_bestc = MAX_U32; }
+  // candidate number cidx of the current group: evaluated by the warp that owns it; track_range: also the worst / best cost (:1998-1999)
+  TBR_HD void try_cand(BlockInfo &bi, Cand &c, int w, int h, bool track_range = false) {
+    const int my = cidx++;
+    if (!be.mine(my)) return;
     const int nbits = encode_block(bi, c);
     const uint32_t cost = cost_calc(bi, w, h, nbits);
-    if (out_cost) *out_cost = cost;
-    if (cost < min_cost) { min_cost = cost; copy_best(bi, c); }
+    if (track_range) { loc_worst = loc_worst > cost ? loc_worst : cost; loc_bestc = loc_bestc < cost ? loc_bestc : cost; }
+    if (cost < loc_cost) { loc_cost = cost; loc_idx = my; copy_best(bi, c); }
+  }
+  // end of a group: the winner over all warps = min (cost, index); every warp receives its cost and parameters, `owner` holds its blocks
+  TBR_HD uint32_t cand_group_end(BlockInfo &bi, int *owner) {
+    uint32_t cost = loc_cost;
+    int idx = loc_idx;
+    *owner = be.reduce_best(&cost, &idx);
+    be.bcast(&bi.best, (int)sizeof(Cand), *owner);
+    return cost;
   }
   TBR_HD static void set_from_ipred(Cand &c, const IPred &p, int idx) {
     c.skip_idx = idx; c.ref_idx0 = p.ref_idx0; c.ref_idx1 = p.ref_idx1; c.mv0[0] = p.mv0; c.mv1[0] = p.mv1; c.dir = p.bipred_flag;
   }
 
-  TBR_HD uint32_t mode_decision_rdo(BlockInfo &bi) {
+  TBR_HD uint32_t mode_decision_rdo(BlockInfo &bi, int *owner) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos;
     const int rectangular = bi.bwidth != size || bi.bheight != size;
     const int intra_inter_sad = F.speed > 0;
-    uint32_t min_cost = MAX_U32, sad_intra = MAX_U32, sad_inter = MAX_U32;
+    uint32_t sad_intra = MAX_U32;
     int do_inter = 1, do_intra = 1;
+    cand_group_begin();
     Cand t;
     t.mode = MODE_SKIP; t.intra_mode = 0; t.skip_idx = 0; t.pb_part = PART_NONE; t.ref_idx0 = t.ref_idx1 = 0; t.dir = 0; t.cbp_y = t.cbp_u = t.cbp_v = 0; t.tb_param = 0; t.tb_split = 0;
     for (int i = 0; i < 4; i++) { t.mv0[i].x = t.mv0[i].y = t.mv1[i].x = t.mv1[i].y = 0; }
@@ -657,7 +681,7 @@ template <class S, class B> struct Rdo {
       for (int k = 0; k < bi.num_skip; k++) {
         set_from_ipred(t, bi.skip_cand[k], k);
         t.mode = MODE_SKIP;
-        try_cand(bi, t, bi.bwidth, bi.bheight, min_cost);
+        try_cand(bi, t, bi.bwidth, bi.bheight);
       }
     }
     if ((size < 128 || F.speed == 0) && !rectangular && size <= MAX_TR) {
@@ -666,7 +690,7 @@ template <class S, class B> struct Rdo {
         for (int k = 0; k < bi.num_merge; k++) {
           set_from_ipred(t, bi.merge_cand[k], k);
           t.mode = MODE_MERGE;
-          for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; try_cand(bi, t, size, size, min_cost); }
+          for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; try_cand(bi, t, size, size); }
         }
         if (intra_inter_sad) {
           sad_intra = (uint32_t)search_intra(bi, &intra_mode);
@@ -677,45 +701,63 @@ template <class S, class B> struct Rdo {
         if (best_ref < 0 || F.speed < 2 || F.enable_bipred) { min_idx = 0; max_idx = F.num_ref - 1; }
         else min_idx = max_idx = best_ref;
         if (F.frame_type == B_FRAME && F.interp_ref > 2) min_idx = 1;
-        uint32_t worst_cost = 0, best_cost = MAX_U32;
-        Mv mv_all[4][4], mv_center[TB_RDO_MAX_REF], mvp;
-        mvp.x = mvp.y = 0;
+        Mv mv_all[TB_RDO_MAX_REF][4][4], mv_center[TB_RDO_MAX_REF], mvp;
+        uint32_t sad_inter_r[TB_RDO_MAX_REF];
         const S *oy = F.org[0] + ypos * F.org_stride[0] + xpos;
+        mvp = get_mv_pred(ypos, xpos, size, size);  // the same for every reference (its ref_idx argument is unused, inter_prediction.c:413)
+        bi.mvp = mvp;
+        // (1) the searches: reference ref_idx on warp (ref_idx - min_idx) mod NW.  A reference's searches only read and extend ITS candidate list
         for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
-          t.ref_idx0 = t.ref_idx1 = ref_idx;
-          mvp = get_mv_pred(ypos, xpos, size, size);
+          if (!be.mine(ref_idx - min_idx)) continue;
           add_mvcandidate(mvp, ref_idx);
-          bi.mvp = mvp;
           const int sign = F.ref_sign[ref_idx];
           mv_center[ref_idx] = mvp;
-          sad_inter = MAX_U32;
+          uint32_t sad_inter = MAX_U32;
           for (int part = 0; part < bi.max_pb; part++) {
-            const uint32_t sad = (uint32_t)search_inter(oy, F.org_stride[0], ref_idx, bi, mv_center[ref_idx], mvp, mv_all[part], part, sign, ref_idx);
-            for (int i = 0; i < 4; i++) add_mvcandidate(mv_all[part][i], ref_idx);
-            mv_center[ref_idx] = mv_all[0][0];
+            const uint32_t sad = (uint32_t)search_inter(oy, F.org_stride[0], ref_idx, bi, mv_center[ref_idx], mvp, mv_all[ref_idx][part], part, sign, ref_idx);
+            for (int i = 0; i < 4; i++) add_mvcandidate(mv_all[ref_idx][part][i], ref_idx);
+            mv_center[ref_idx] = mv_all[ref_idx][0][0];
             sad_inter = sad_inter < sad ? sad_inter : sad;
           }
+          sad_inter_r[ref_idx] = sad_inter;
+          be.put_me(ref_idx, &mv_all[ref_idx][0][0], sad_inter);
+        }
+        be.cta_sync();
+        // (2) every warp learns the other references' vectors and replays their effect on its replica of the candidate lists
+        for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
+          if (be.mine(ref_idx - min_idx)) continue;
+          be.get_me(ref_idx, &mv_all[ref_idx][0][0], &sad_inter_r[ref_idx]);
+          add_mvcandidate(mvp, ref_idx);
+          for (int part = 0; part < bi.max_pb; part++)
+            for (int i = 0; i < 4; i++) add_mvcandidate(mv_all[ref_idx][part][i], ref_idx);
+          mv_center[ref_idx] = mv_all[ref_idx][0][0];
+        }
+        be.cta_sync();
+        // (3) the RD candidates of every reference
+        for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
+          t.ref_idx0 = t.ref_idx1 = ref_idx;
           if (intra_inter_sad) {
-            do_inter = sad_inter < sad_intra;
-            if (sad_inter < sad_intra) do_intra = 0;
+            do_inter = sad_inter_r[ref_idx] < sad_intra;
+            if (sad_inter_r[ref_idx] < sad_intra) do_intra = 0;
           }
           if (do_inter) {
             for (int part = 0; part < bi.max_pb; part++) {
               t.pb_part = part;
-              for (int i = 0; i < 4; i++) t.mv0[i] = t.mv1[i] = mv_all[part][i];
+              for (int i = 0; i < 4; i++) t.mv0[i] = t.mv1[i] = mv_all[ref_idx][part][i];
               const int min_tb = F.speed < 1 ? -1 : 0;
               t.mode = MODE_INTER; t.dir = 0;
               for (int tb = min_tb; tb <= bi.max_tb - 1; tb++) {
                 t.tb_param = tb;
-                uint32_t cost;
-                try_cand(bi, t, size, size, min_cost, &cost);
-                worst_cost = worst_cost > cost ? worst_cost : cost;
-                best_cost = best_cost < cost ? best_cost : cost;
+                try_cand(bi, t, size, size, true);
               }
             }
           }
         }
-        if (worst_cost && (uint64_t)worst_cost * 3 > (uint64_t)best_cost * 4) best_ref = 0;  // best_ref_idx is never updated in the reference (:1868, :2019)
+        {
+          uint32_t worst_cost = loc_worst, best_cost = loc_bestc;
+          be.reduce_range(&worst_cost, &best_cost);
+          if (worst_cost && (uint64_t)worst_cost * 3 > (uint64_t)best_cost * 4) best_ref = 0;  // best_ref_idx is never updated in the reference (:1868, :2019)
+        }
 
         if (F.num_ref > 1 && F.enable_bipred && do_inter) {
           int r0, r1;
@@ -725,38 +767,41 @@ template <class S, class B> struct Rdo {
           t.pb_part = 0; t.ref_idx0 = r0; t.ref_idx1 = r1;
           for (int i = 0; i < 4; i++) { t.mv0[i] = a0[i]; t.mv1[i] = a1[i]; }
           t.mode = MODE_BIPRED;
-          for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; try_cand(bi, t, size, size, min_cost); }
+          for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; try_cand(bi, t, size, size); }
           if (F.frame_type == B_FRAME && F.speed == 0) {
             search_bipred(bi, 1, mv_center, mvp, &r0, &r1, a0, a1, 1);
             t.pb_part = PART_NONE; t.ref_idx0 = r0; t.ref_idx1 = r1;
             for (int i = 0; i < 4; i++) { t.mv0[i] = a0[i]; t.mv1[i] = a1[i]; }
             t.tb_param = 0; t.mode = MODE_BIPRED;
-            try_cand(bi, t, size, size, min_cost);
+            try_cand(bi, t, size, size);
           }
         }
       }
       if (do_intra) {
         t.mode = MODE_INTRA;
         if (F.intra_rdo) {
+          // choice of the intra mode by RD cost (:2080-2097): its own distributed group, no copy_best
           uint32_t min_intra_cost = MAX_U32;
-          int best_intra_mode = 0;
+          int best_k = 0x7fffffff, k = 0;
           for (int m = 0; m < F.num_intra_modes; m++) {
             t.intra_mode = m;
-            for (int tb = 0; tb <= bi.max_tb - 1; tb++) {
+            for (int tb = 0; tb <= bi.max_tb - 1; tb++, k++) {
+              if (!be.mine(k)) continue;
               t.tb_param = tb; t.mode = MODE_INTRA;
               const int nbits = encode_block(bi, t);
               const uint32_t cost = cost_calc(bi, size, size, nbits);
-              if (cost < min_intra_cost) { min_intra_cost = cost; best_intra_mode = m; }
+              if (cost < min_intra_cost) { min_intra_cost = cost; best_k = k; }
             }
           }
-          intra_mode = best_intra_mode;
+          be.reduce_best(&min_intra_cost, &best_k);
+          intra_mode = min_intra_cost == MAX_U32 ? 0 : best_k / bi.max_tb;
         } else
           search_intra(bi, &intra_mode);
         t.intra_mode = intra_mode;
-        for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; t.mode = MODE_INTRA; try_cand(bi, t, size, size, min_cost); }
+        for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; t.mode = MODE_INTRA; try_cand(bi, t, size, size); }
       }
     }
-    return min_cost;
+    return cand_group_end(bi, owner);
   }
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -795,30 +840,45 @@ template <class S, class B> struct Rdo {
       }
     return !significant;
   }
-  TBR_HD int search_early_skip(BlockInfo &bi) {  // :2352-2392
-    uint32_t min_cost = MAX_U32;
+  // :2352-2392.  Skip candidate k (its early-skip test and, if it passes, its RD cost) on warp k mod NW
+  TBR_HD int search_early_skip(BlockInfo &bi, uint32_t *cost, int *owner) {
     int flag = 0;
     Cand t;
     t.intra_mode = 0; t.pb_part = PART_NONE; t.cbp_y = t.cbp_u = t.cbp_v = 0; t.tb_split = 0;
     for (int i = 0; i < 4; i++) { t.mv0[i].x = t.mv0[i].y = t.mv1[i].x = t.mv1[i].y = 0; }
+    cand_group_begin();
     for (int k = 0; k < bi.num_skip; k++) {
       t.tb_param = 0;
       set_from_ipred(t, bi.skip_cand[k], k);
       t.mode = MODE_SKIP;
-      if (check_early_skip_block(bi, t)) {
-        flag = 1;
-        try_cand(bi, t, bi.size, bi.size, min_cost);
-      }
+      if (be.mine(cidx)) {
+        if (check_early_skip_block(bi, t)) { flag = 1; try_cand(bi, t, bi.size, bi.size); }
+        else cidx++;
+      } else cidx++;
     }
+    flag = be.reduce_or(flag);
+    // the reference encodes the chosen candidate once more (final_encode = 3) and returns that cost: same bits, same reconstruction, same cost
+    *cost = cand_group_end(bi, owner);
     return flag;
   }
 
   // ---------------------------------------------------------------------------------------------------------------
   // commit: copy_block_to_frame :1516 + copy_deblock_data :1568 + the leaf record (what the final write_block needs)
   // ---------------------------------------------------------------------------------------------------------------
-  TBR_HD void commit_block(const BlockInfo &bi, uint32_t cost, const S *by, const S *bu, const S *bv, const int16_t *qy, const int16_t *qu, const int16_t *qv) {
+  // Only warp `owner` (the one whose scratch holds the winning blocks) stores; every warp advances the leaf / coefficient counters; the CTA
+  // barrier at the end publishes the block to the other warps (and, through the row's progress counter, to the other CTAs).
+  TBR_HD void commit_block(const BlockInfo &bi, uint32_t cost, int owner, const S *by, const S *bu, const S *bv, const int16_t *qy, const int16_t *qu, const int16_t *qv) {
     const int size = bi.size, sc = size >> 1, bw = bi.bwidth, bh = bi.bheight;
     const Cand &b = bi.best;
+    const bool has_coeff = b.mode != MODE_SKIP && (b.cbp_y || b.cbp_u || b.cbp_v);
+    const int tbc_ = b.tb_split && sc > 4;
+    const int ny_ = coeff_count(size, b.tb_split), nc_ = coeff_count(sc, tbc_);
+    if (be.warp() != owner) {
+      if (has_coeff) coeff_used += ny_ + 2 * nc_;
+      n_leaves++;
+      be.cta_sync();
+      return;
+    }
     be.copy(F.rec[0] + bi.ypos * F.rec_stride[0] + bi.xpos, F.rec_stride[0], by, size, bw, bh);
     be.copy(F.rec[1] + (bi.ypos >> 1) * F.rec_stride[1] + (bi.xpos >> 1), F.rec_stride[1], bu, sc, bw >> 1, bh >> 1);
     be.copy(F.rec[2] + (bi.ypos >> 1) * F.rec_stride[1] + (bi.xpos >> 1), F.rec_stride[1], bv, sc, bw >> 1, bh >> 1);
@@ -849,13 +909,14 @@ template <class S, class B> struct Rdo {
     }
     be.store_leaf(F.leaves + (size_t)sb_index * TB_RDO_MAX_LEAVES + n_leaves, L);
     n_leaves++;
+    be.cta_sync();
   }
 
   // ---------------------------------------------------------------------------------------------------------------
   // process_block :2401-2565, iteratively (depth <= 5: 128 -> 8)
   // ---------------------------------------------------------------------------------------------------------------
   struct Frame_ {
-    int size, ypos, xpos, stage, child, leaf_start, coeff_start, encode_this, encode_rect, top_down;
+    int size, ypos, xpos, stage, child, leaf_start, coeff_start, encode_this, encode_rect, top_down, owner;
     uint32_t cost, cost_small;
     BlockInfo bi;
   };
@@ -881,7 +942,7 @@ template <class S, class B> struct Rdo {
         f.encode_this = ypos + size <= F.height && xpos + size <= F.width;
         f.encode_rect = !f.encode_this && F.frame_type != I_FRAME;
         f.top_down = size == 2 * MIN_BLOCK && f.encode_this && F.frame_type != I_FRAME && F.speed > 0;
-        f.cost_small = 1u << 28; f.cost = 1u << 28; f.child = 0;
+        f.cost_small = 1u << 28; f.cost = 1u << 28; f.child = 0; f.owner = 0;
         f.leaf_start = n_leaves; f.coeff_start = coeff_used;
         BlockInfo &bi = f.bi;
         bi.size = size; bi.ypos = ypos; bi.xpos = xpos; bi.bwidth = imin(size, F.width - xpos); bi.bheight = imin(size, F.height - ypos);
@@ -894,14 +955,10 @@ template <class S, class B> struct Rdo {
           bi.num_merge = get_mv_skip_merge(ypos, xpos, size, size, bi.merge_cand);
         }
         if (f.encode_this && F.frame_type != I_FRAME && F.early_skip_thr > 0.0f) {
-          if (search_early_skip(bi)) {
-            // final_encode = 3: the chosen skip candidate is encoded again (deterministic: same result as the stored best)
-            Cand fin = bi.best;
-            const int nbit = block_bits(bi, fin, W.bq_y, W.bq_u, W.bq_v);
-            const int sc = size >> 1;
-            be.copy(W.rec_y, size, W.best_y, size, size, size); be.copy(W.rec_u, sc, W.best_u, sc, sc, sc); be.copy(W.rec_v, sc, W.best_v, sc, sc, sc);
-            const uint32_t cost = cost_calc(bi, size, size, nbit);
-            commit_block(bi, cost, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
+          uint32_t cost;
+          int owner;
+          if (search_early_skip(bi, &cost, &owner)) {
+            commit_block(bi, cost, owner, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
             ret = cost; have_ret = true; sp--; continue;
           }
         }
@@ -921,13 +978,16 @@ template <class S, class B> struct Rdo {
       }
       if (f.stage == 2) {
         if (f.encode_this || f.encode_rect) {
-          f.cost = mode_decision_rdo(f.bi);
+          f.cost = mode_decision_rdo(f.bi, &f.owner);
           const uint32_t thr = (uint32_t)(size * size * iq_8x8[F.qp] / 8);
           if (f.top_down && f.cost > thr) {
-            // the children reuse the scratch blocks: keep this block's best aside (16x16 only)
-            const int sc = size >> 1;
-            be.copy(W.td_y, size, W.best_y, size, size, size); be.copy(W.td_u, sc, W.best_u, sc, sc, sc); be.copy(W.td_v, sc, W.best_v, sc, sc, sc);
-            be.copy_coeff(W.tdq_y, W.bq_y); be.copy_coeff(W.tdq_u, W.bq_u); be.copy_coeff(W.tdq_v, W.bq_v);
+            // the children reuse the scratch blocks: the owner keeps this block's best aside in the CTA-shared save area (16x16 only)
+            if (be.warp() == f.owner) {
+              const int sc = size >> 1;
+              be.copy(W0.td_y, size, W.best_y, size, size, size); be.copy(W0.td_u, sc, W.best_u, sc, sc, sc); be.copy(W0.td_v, sc, W.best_v, sc, sc, sc);
+              be.copy_coeff(W0.tdq_y, W.bq_y); be.copy_coeff(W0.tdq_u, W.bq_u); be.copy_coeff(W0.tdq_v, W.bq_v);
+            }
+            be.cta_sync();
             f.cost_small = 0; f.stage = 3; f.child = 0;
             continue;
           }
@@ -939,12 +999,13 @@ template <class S, class B> struct Rdo {
       if ((f.encode_this || f.encode_rect) && f.cost <= f.cost_small) {
         n_leaves = f.leaf_start; coeff_used = f.coeff_start;  // the children's blocks are replaced
         const bool from_td = f.top_down && f.child == 4;      // the children ran after this block's decision
-        if (from_td) commit_block(f.bi, f.cost, W.td_y, W.td_u, W.td_v, W.tdq_y, W.tdq_u, W.tdq_v);
-        else commit_block(f.bi, f.cost, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
+        if (from_td) commit_block(f.bi, f.cost, 0, W0.td_y, W0.td_u, W0.td_v, W0.tdq_y, W0.tdq_u, W0.tdq_v);
+        else commit_block(f.bi, f.cost, f.owner, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
       }
       ret = f.cost < f.cost_small ? f.cost : f.cost_small; have_ret = true; sp--;
     }
-    be.store_count(F.leaf_count + sb_index, n_leaves);
+    if (be.warp() == 0) be.store_count(F.leaf_count + sb_index, n_leaves);
+    be.cta_sync();
     return ret;
   }
 };
