@@ -291,6 +291,28 @@ typedef struct {
   int16_t *coeffs;        /* out: TB_RDO_SB_COEFFS per super block */
 } tb_rdo_frame_t;
 int tb_rdo_encode_frame(const tb_rdo_frame_t *f);
+/* n INDEPENDENT frames (the B frames of one hierarchy level, frames of several sequences or intra-period segments) in ONE launch: persistent CTAs
+ * draw ready super blocks from all of them, so the GPU is filled although one frame's wavefront is only a few super blocks wide.  All frames must
+ * have the same sample size; geometry and parameters may differ.  Same outputs per frame as tb_rdo_encode_frame(). */
+int tb_rdo_encode_frames(const tb_rdo_frame_t *f, int n);
+/* The same in steps, for callers that keep frames resident or overlap the copies: every call only ENQUEUES on the library's stream
+ * (tb_stream()); host buffers must stay valid until tb_rdo_batch_sync() (pinned buffers make the copies truly asynchronous). */
+typedef struct tb_rdo_batch tb_rdo_batch_t;
+tb_rdo_batch_t *tb_rdo_batch_create(int n_slots, int sample_bytes);                         /* NULL: tb_rdo_last_error() */
+int tb_rdo_batch_upload(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f);              /* parameters + source + references -> HBM */
+int tb_rdo_batch_run(tb_rdo_batch_t *b, int n_active);                                      /* one launch over slots [0, n_active) */
+int tb_rdo_batch_download(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f);            /* decisions of a slot -> f's output buffers (rec[] may be NULL) */
+int tb_rdo_batch_sync(tb_rdo_batch_t *b);                                                   /* waits; TB_ERR_CUDA if the launch did not finish every super block */
+int tb_rdo_batch_grid(const tb_rdo_batch_t *b);                                             /* CTAs of the last launch */
+/* counters of the last synchronised launch, summed over all warps: [0..10] SM cycles per primitive class (interp, search, bipred search, transform
+ * chain, coefficient bits, SSD/SAD, intra, copies, early skip, idle, total); [11..22] work actually executed (the RD loop is data dependent):
+ * searches, integer block SADs, sub-pel probes, search samples ((n_int+1) w h + n_sub ((w+5)(h+5) + w h)), predictions, prediction samples,
+ * transform chains, chain samples (3 N^2), intra predictions, intra samples (4N + N^2), SSD/SAD samples (2 w h), super blocks */
+#define TB_RDO_NSTATS 23
+int tb_rdo_batch_stats(const tb_rdo_batch_t *b, uint64_t *out, int n);
+void tb_rdo_batch_destroy(tb_rdo_batch_t *b);
+const char *tb_rdo_last_error(void);
+uint64_t tb_rdo_launch_count(void);
 /* int16 coefficients a leaf stores for one plane: transform blocks packed back to back, each min(tsize,16)^2 in raster order */
 static inline int tb_rdo_coeff_count(int size, int tb_split) {
   int t = tb_split ? size / 2 : size, q = t < 16 ? t : 16;

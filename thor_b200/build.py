@@ -26,18 +26,41 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+def _compile(src, obj, flags):
+    cmd = [nvcc()] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, " ".join(cmd) + "\n" + r.stdout + r.stderr
+
+
 def build(force=False, verbose=False, defines=(), out=None):
+    """one object per translation unit (compiled in parallel, kept under thor_b200/build/ and reused while its sources are older), then one link"""
     if not force and not stale() and out is None:
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
-    cmd = [nvcc()] + flags + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math") and f != "-shared"] + ["-D" + d for d in defines]
+    objdir = os.path.join(HERE, "build", "default" if out is None else os.path.basename(out))
+    os.makedirs(objdir, exist_ok=True)
+    newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)
+    jobs = []
+    for s in SOURCES:
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+            jobs.append((s, obj))
+    log = ""
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        for rc, text in ex.map(lambda j: _compile(j[0], j[1], flags), jobs):
+            log += text
+            if rc != 0:
+                sys.stderr.write(text)
+                raise RuntimeError("nvcc failed building libthor_b200.so")
+    cmd = [nvcc(), "-shared", "-o", out or LIB] + [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = r.stdout + r.stderr
+    log += " ".join(cmd) + "\n" + r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log") if out is None else out + ".log", "w") as f:  # A/B builds log next to their output (ab_libs/)
-        f.write(" ".join(cmd) + "\n" + log)
+        f.write(log)
     if r.returncode != 0:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libthor_b200.so")
+        raise RuntimeError("nvcc failed linking libthor_b200.so")
     if verbose:
         print(log)
     return out or LIB

@@ -1,9 +1,9 @@
 // tb_rdo.cu — SURVEY.md §8f.1: the reference's per-super-block RD loop resident on the GPU.
 //
-// tb_rdo_encode_frame() (include/thor_b200.h) uploads the source frame and the padded reference frames, runs rdo_frame_kernel — one
-// CTA per super-block ROW, super blocks of a row in raster order, rows in a wavefront: row r may start super block c when row r-1 has
-// published c+2 super blocks (left, up-left, up, up-right neighbours: get_mv_pred / intra prediction / block contexts read nothing else)
-// — and downloads the decisions (reconstruction, per-4x4 block state, the leaf list of every super block with its coefficients).
+// tb_rdo_encode_frames() (include/thor_b200.h) uploads the source frames and their padded reference frames, runs rdo_batch_kernel —
+// persistent CTAs that draw READY super blocks from the rows of every frame of the batch (row r may process super block c when row r-1
+// has published c+2 super blocks: left, up-left, up, up-right neighbours; frames are independent) — and downloads the decisions
+// (reconstruction, per-4x4 block state, the leaf list of every super block with its coefficients).
 // The control flow is tb_rdo.h (shared with the CPU host check that pins it against the reference); this file supplies its backend:
 // the warp-cooperative primitives of tb_device.cuh / tb_kernels.cuh, i.e. the same device routines the batched tb_* entry points
 // and the drop-in symbols use (parity-tested against the oracle one by one in tests/test_gpu_parity.py).
@@ -31,6 +31,10 @@ namespace {
 
 // per-primitive cycle counters (TB_RDO_PROF=1): which part of the RD loop the warp spends its time in
 enum { PF_INTERP, PF_ME, PF_MEBI, PF_TX, PF_BITS, PF_SSD, PF_INTRA, PF_COPY, PF_ES, PF_WAIT, PF_TOTAL, PF_N };
+// always-on work counters (SURVEY.md §8d algorithmic samples of what the RD loop actually executed: the loop is data dependent) behind the cycle counters:
+// searches, integer block SADs, sub-pel probes, search samples, predictions, prediction samples, transform chains, chain samples, intra predictions, intra samples,
+// SSD/SAD samples, super blocks
+enum { ST_ME = PF_N, ST_ME_INT, ST_ME_SUB, ST_ME_SAMPLES, ST_IP, ST_IP_SAMPLES, ST_TX, ST_TX_SAMPLES, ST_INTRA, ST_INTRA_SAMPLES, ST_SSD_SAMPLES, ST_SB, ST_END };
 struct Prof {
   long long *acc;
   int k;
@@ -43,6 +47,7 @@ struct Prof {
 #endif
 };
 
+static_assert(ST_END == TB_RDO_NSTATS, "tb_rdo_batch_stats layout");
 constexpr int RDO_MAX_WARPS = 16;
 // per-CTA: tables and the exchange area of the SPMD control flow (tb_rdo.h)
 struct RdoCta {
@@ -55,11 +60,11 @@ struct RdoCta {
   tb_mv_t x_mv[TB_RDO_MAX_REF][16];
   uint32_t x_sad[TB_RDO_MAX_REF];
   alignas(16) int x_buf[32];
-  int give_up;
+  int sel;
 };
 // per-warp scratch
 template <class S> struct RdoShared {
-  long long prof[PF_N];
+  long long prof[ST_END];
   TxScratch sc;
   alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual
   alignas(16) int16_t out16[256];                // transform output of the early-skip test; coefficient scan for the bit count
@@ -142,6 +147,7 @@ template <class S> struct DevBackend {
   // prediction of one block; widths that are not powers of two (rectangular blocks at the right frame edge) take the per-sample form
   __device__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
     PROF(PF_INTERP);
+    if (lane() == 0) { sh->prof[ST_IP] += 1; sh->prof[ST_IP_SAMPLES] += (xf_any(mv, chroma) ? (w + 5) * (h + 5) : w * h) + w * h; }
     sync();
     if (!(w & (w - 1))) warp_interp<S>(dst, ds, ref, rs, w, h, mv.x, mv.y, sign, chroma, bip, pw, ph, xpos, ypos, F->bitdepth);
     else {
@@ -160,6 +166,7 @@ template <class S> struct DevBackend {
     }
     sync();
   }
+  __device__ __forceinline__ static int xf_any(Mv mv, int chroma) { return chroma ? ((mv.x | mv.y) & 7) : ((mv.x | mv.y) & 3); }
   __device__ void interp_luma(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int bip, int pw, int ph, int xpos, int ypos) const {
     interp_any(dst, ds, ref, rs, w, h, mv, sign, 0, bip, pw, ph, xpos, ypos);
   }
@@ -203,6 +210,7 @@ template <class S> struct DevBackend {
   __device__ void intra_predict(S *dst, int ds, const S *recf, int rfs, const S *rblock, int rbs, int i, int j, int ypos, int xpos, int size, int ur, int dl, int tbs,
                                 int mode) const {
     PROF(PF_INTRA);
+    if (lane() == 0) { sh->prof[ST_INTRA] += 1; sh->prof[ST_INTRA_SAMPLES] += 4 * size + size * size; }
     sync();
     S tl;
     warp_make_top_and_left<S>(sh->left, sh->top, tl, recf, rfs, rblock, rbs, i, j, ypos, xpos, size, ur, dl, tbs, F->bitdepth);
@@ -219,6 +227,7 @@ template <class S> struct DevBackend {
   }
   __device__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
     PROF(PF_TX);
+    if (lane() == 0) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * size * size; }
     sync();
     int cbp;
     if (size >= 16) {
@@ -253,6 +262,7 @@ template <class S> struct DevBackend {
   }
   __device__ uint64_t ssd(const S *a, int as, const S *b, int bs, int w, int h) const {
     PROF(PF_SSD);
+    if (lane() == 0) sh->prof[ST_SSD_SAMPLES] += 2 * w * h;
     sync();
     if (!(w & (w - 1))) return warp_ssd<S>(a, as, b, bs, w, h);
     uint64_t acc = 0;
@@ -264,6 +274,7 @@ template <class S> struct DevBackend {
   }
   __device__ unsigned sad(const S *a, int as, const S *b, int bs, int w, int h) const {
     PROF(PF_SSD);
+    if (lane() == 0) sh->prof[ST_SSD_SAMPLES] += 2 * w * h;
     sync();
     return warp_sad<S>(a, as, b, bs, w, h);
   }
@@ -281,6 +292,10 @@ template <class S> struct DevBackend {
     warp_motion_estimate<S, 1>(org, os, ref, rs, c, mvc.x, mvc.y, (const int16_t *)cand, ncand, mx, my, cost, tm);
     mx = __shfl_sync(FULL, mx, 0); my = __shfl_sync(FULL, my, 0); cost = __shfl_sync(FULL, cost, 0);
     mv->x = (int16_t)mx; mv->y = (int16_t)my;
+    if (lane() == 0) {
+      sh->prof[ST_ME] += 1; sh->prof[ST_ME_INT] += c.n_int; sh->prof[ST_ME_SUB] += c.n_sub;
+      sh->prof[ST_ME_SAMPLES] += (long long)(c.n_int + 1) * w * h + (long long)c.n_sub * ((w + 5) * (h + 5) + w * h);
+    }
     sync();
     return (int)cost;
   }
@@ -365,96 +380,179 @@ template <class S> struct DevBackend {
 
 constexpr int RDO_WARPS = 8;  // warps per CTA: 8 x 32 threads x 255 registers = the whole register file of an SM
 
+// One row of super blocks of one frame of the batch.  Rows are the unit a CTA claims; super blocks inside a row are sequential.
+struct RowDesc { int frame, row, nsbx, pad; };
+// scheduler words behind the per-row arrays
+enum { CTL_REMAINING = 0, CTL_ERROR = 1, CTL_N = 4 };
+
+// Persistent CTAs draw READY super blocks from the rows of every frame of the batch (dataflow scheduling): row r of a frame may process
+// super block c when row r-1 has published min(c+2, nsbx) super blocks (left, up-left, up, up-right neighbours: get_mv_pred / intra
+// prediction / block contexts read nothing else); frames are independent of each other.  A CTA claims a ready row (lowest index first:
+// the top rows of the earliest frames unblock the most work), processes super blocks while the next one is ready, then releases the row,
+// so a CTA never holds an SM while it waits for a neighbour: a row migrates between CTAs at super-block boundaries (all per-super-block
+// state is re-initialised by process_sb; data of other super blocks is read through L2, see TB_LDF above).
 template <class S>
-__global__ void __launch_bounds__(32 * RDO_WARPS, 1) rdo_frame_kernel(FrameCtx<S> ctx, Work<S> *works, int *progress, int nsbx, unsigned long long *prof_out) {
+__global__ void __launch_bounds__(32 * RDO_WARPS, 1)
+    rdo_batch_kernel(const FrameCtx<S> *ctxs, const RowDesc *rows, int nrows, Work<S> *works, int *prog, int *claimed, int *ctl, unsigned long long *prof_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RdoCta &cta = *(RdoCta *)smem_raw;
-  RdoShared<S> *shs = (RdoShared<S> *)(smem_raw + ((sizeof(RdoCta) + 15) & ~(size_t)15));
+  FrameCtx<S> &fctx = *(FrameCtx<S> *)(smem_raw + ((sizeof(RdoCta) + 15) & ~(size_t)15));
+  RdoShared<S> *shs = (RdoShared<S> *)(smem_raw + ((sizeof(RdoCta) + 15) & ~(size_t)15) + ((sizeof(FrameCtx<S>) + 15) & ~(size_t)15));
   const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RdoShared<S> &sh = shs[wid];
-  for (int k = lane; k < PF_N; k += 32) sh.prof[k] = 0;
+  for (int k = lane; k < ST_END; k += 32) sh.prof[k] = 0;
   const long long t_start = clock64();
   dct_tab8_fill(cta.tab8, cta.tab8 + DCT_TAB8_SIZE);
   dct_tab_fill(cta.tab16);
   for (int t = threadIdx.x; t < 256; t += blockDim.x) ((uint8_t *)(cta.tab8 + 2 * DCT_TAB8_SIZE))[t] = (uint8_t)zigzag_index(t >> 4, t & 15, 16);
-  if (threadIdx.x == 0) cta.give_up = 0;
   __syncthreads();
-  const int row = blockIdx.x;
   DevBackend<S> be;
-  be.F = &ctx; be.sh = &sh; be.cta = &cta; be.nw = nw; be.wid = wid;
-  volatile int *prog = progress;
-  for (int sbx = 0; sbx < nsbx; sbx++) {
-    if (row > 0) {
+  be.F = &fctx; be.sh = &sh; be.cta = &cta; be.nw = nw; be.wid = wid;
+  volatile int *vprog = prog, *vclaimed = claimed, *vctl = ctl;
+  long long idle_since = clock64();
+  int cur_frame = -1;
+  while (true) {
+    // ---- claim a ready row
+    int sel;
+    {
       Prof pw(sh.prof, PF_WAIT);
-      const int need = min(sbx + 2, nsbx);
-      if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        while (prog[row - 1] < need) {
-          __nanosleep(200);
-          // a row that never publishes (it faulted) must not hang the launch: ~30 s of SM clocks, far beyond any super block
-          if (clock64() - t0 > 60000000000ll || prog[gridDim.x] != 0) { cta.give_up = 1; break; }
+      if (threadIdx.x == 0) cta.sel = 0x7fffffff;
+      __syncthreads();
+      int mine = 0x7fffffff;
+      for (int g = threadIdx.x; g < nrows; g += blockDim.x) {
+        if (vclaimed[g]) continue;
+        const RowDesc rd = rows[g];
+        const int p = vprog[g];
+        if (p < rd.nsbx && (rd.row == 0 || vprog[g - 1] >= min(p + 2, rd.nsbx))) { mine = g; break; }
+      }
+      if (mine != 0x7fffffff) atomicMin(&cta.sel, mine);
+      __syncthreads();
+      sel = cta.sel;
+      if (sel == 0x7fffffff) {  // nothing ready: finished, failed, or wait for the running super blocks
+        if (threadIdx.x == 0) {
+          int f = 0;
+          if (vctl[CTL_REMAINING] <= 0) f = 1;
+          // ~30 s of SM clocks without any work for this CTA while work remains: a row stopped publishing (it faulted): do not hang the launch
+          else if (vctl[CTL_ERROR] != 0 || clock64() - idle_since > 60000000000ll) { vctl[CTL_ERROR] = 1; f = 1; }
+          else __nanosleep(1000);
+          cta.x_flag[0] = f;
         }
+        __syncthreads();
+        if (cta.x_flag[0]) break;
+        continue;
+      }
+      if (threadIdx.x == 0) {
+        int got = atomicCAS(&claimed[sel], 0, 1) == 0;
+        if (got) {  // the row is ours: its position cannot change any more; re-evaluate readiness at that position
+          const RowDesc rd = rows[sel];
+          const int p = vprog[sel];
+          if (!(p < rd.nsbx && (rd.row == 0 || vprog[sel - 1] >= min(p + 2, rd.nsbx)))) { atomicExch(&claimed[sel], 0); got = 0; }
+          cta.x_idx[0] = p;
+        }
+        cta.x_flag[0] = got;
       }
       __syncthreads();
-      if (cta.give_up) {
-        if (threadIdx.x == 0) prog[gridDim.x] = 1;  // error flag behind the per-row counters
-        return;
-      }
-      __threadfence();
+      if (!cta.x_flag[0]) continue;
     }
-    Rdo<S, DevBackend<S>> R(ctx, works[row * nw + wid], works[row * nw], be);
-    R.process_sb(sbx, row);
-    __threadfence();  // every writing thread orders its stores before the flag
+    __threadfence();
+    const RowDesc rd = rows[sel];
+    if (rd.frame != cur_frame) {  // frame parameters into shared memory
+      const int *src = (const int *)(ctxs + rd.frame);
+      int *dst = (int *)&fctx;
+      __syncthreads();
+      for (int k = threadIdx.x; k < (int)(sizeof(FrameCtx<S>) / 4); k += blockDim.x) dst[k] = src[k];
+      cur_frame = rd.frame;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) prog[row] = sbx + 1;
+    int sbx = cta.x_idx[0];
+    while (true) {
+      Rdo<S, DevBackend<S>> R(fctx, works[blockIdx.x * nw + wid], works[blockIdx.x * nw], be);
+      R.process_sb(sbx, rd.row);
+      __threadfence();  // every writing thread orders its stores before the flag
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        sh.prof[ST_SB] += 1;
+        vprog[sel] = sbx + 1;
+        atomicSub(&ctl[CTL_REMAINING], 1);
+        const int nx = sbx + 1;
+        const int cont = nx < rd.nsbx && (rd.row == 0 || vprog[sel - 1] >= min(nx + 2, rd.nsbx));
+        if (!cont) { __threadfence(); atomicExch(&claimed[sel], 0); }
+        cta.x_flag[0] = cont;
+      }
+      __syncthreads();
+      if (!cta.x_flag[0]) break;
+      __threadfence();
+      sbx++;
+    }
+    idle_since = clock64();
   }
-  if (prof_out && lane == 0) {
+  if (lane == 0) {
     sh.prof[PF_TOTAL] = clock64() - t_start;
-    for (int k = 0; k < PF_N; k++) atomicAdd(&prof_out[k], (unsigned long long)sh.prof[k]);
+    for (int k = 0; k < ST_END; k++)
+      if (sh.prof[k]) atomicAdd(&prof_out[k], (unsigned long long)sh.prof[k]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------------------------
-struct DevState {
-  int w = 0, h = 0, esz = 0, sb = 0, pad = 0, nref = 0, sy = 0, sc = 0;
+char g_err[256] = {0};
+#define CK(x)                                                                                     \
+  do {                                                                                            \
+    cudaError_t e__ = (x);                                                                        \
+    if (e__ != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s: %s", #x, cudaGetErrorString(e__)); return TB_ERR_CUDA; } \
+  } while (0)
+
+// device-resident state of one frame of a batch
+struct Slot {
+  int w = 0, h = 0, esz = 0, sb = 0, pad = 0, nref = 0, sy = 0, sc = 0, used = 0;
   void *org[3] = {nullptr, nullptr, nullptr}, *rec[3] = {nullptr, nullptr, nullptr};
   void *ref[TB_RDO_MAX_REF][3] = {};
   tb_rdo_blk_t *blk = nullptr;
   tb_rdo_leaf_t *leaves = nullptr;
-  int *leaf_count = nullptr, *progress = nullptr;
+  int *leaf_count = nullptr;
   int16_t *coeffs = nullptr;
+  int nsbx = 0, nsby = 0;
+  void release() {
+    for (int p = 0; p < 3; p++) { cudaFree(org[p]); cudaFree(rec[p]); org[p] = rec[p] = nullptr; }
+    for (int r = 0; r < TB_RDO_MAX_REF; r++)
+      for (int p = 0; p < 3; p++) { cudaFree(ref[r][p]); ref[r][p] = nullptr; }
+    cudaFree(blk); cudaFree(leaves); cudaFree(leaf_count); cudaFree(coeffs);
+    blk = nullptr; leaves = nullptr; leaf_count = nullptr; coeffs = nullptr; w = 0; nref = 0; used = 0;
+  }
+};
+}  // namespace
+
+struct tb_rdo_batch {
+  int nslots = 0, esz = 0, grid = 0, nrows = 0, nrows_cap = 0, grid_cap = 0;
+  Slot *slots = nullptr;
+  void *ctx_host = nullptr, *ctx_dev = nullptr;  // FrameCtx<S>[nslots] (pinned staging, device copy)
+  RowDesc *rows_host = nullptr, *rows_dev = nullptr;
+  int *sched_dev = nullptr;                      // prog[nrows] | claimed[nrows] | ctl[CTL_N]
+  int *ctl_host = nullptr;                       // pinned: ctl words read back after the launch
   void *works = nullptr;
   unsigned long long *prof = nullptr;
-  char err[256] = {0};
-} D;
+  unsigned long long stats[ST_END] = {};
+  int sms = 0;
+};
 
-void free_state() {
-  for (int p = 0; p < 3; p++) { cudaFree(D.org[p]); cudaFree(D.rec[p]); D.org[p] = D.rec[p] = nullptr; }
-  for (int r = 0; r < TB_RDO_MAX_REF; r++)
-    for (int p = 0; p < 3; p++) { cudaFree(D.ref[r][p]); D.ref[r][p] = nullptr; }
-  cudaFree(D.blk); cudaFree(D.leaves); cudaFree(D.leaf_count); cudaFree(D.progress); cudaFree(D.coeffs); cudaFree(D.works); cudaFree(D.prof); D.prof = nullptr;
-  D.blk = nullptr; D.leaves = nullptr; D.leaf_count = D.progress = nullptr; D.coeffs = nullptr; D.works = nullptr;
-  D.w = 0;
+namespace {
+
+template <class S> size_t smem_bytes() {
+  return ((sizeof(RdoCta) + 15) & ~(size_t)15) + ((sizeof(FrameCtx<S>) + 15) & ~(size_t)15) + sizeof(RdoShared<S>) * RDO_WARPS;
 }
 
-#define CK(x)                                                                                     \
-  do {                                                                                            \
-    cudaError_t e__ = (x);                                                                        \
-    if (e__ != cudaSuccess) { snprintf(D.err, sizeof(D.err), "%s: %s", #x, cudaGetErrorString(e__)); return TB_ERR_CUDA; } \
-  } while (0)
-
-template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
-  const int w = f->width, h = f->height, sb = 1 << f->log2_sb_size, esz = (int)sizeof(S);
-  const int nsbx = (w + sb - 1) / sb, nsby = (h + sb - 1) / sb, nsb = nsbx * nsby;
+int slot_prepare(Slot &D, const tb_rdo_frame_t *f) {
+  const int w = f->width, h = f->height, sb = 1 << f->log2_sb_size, esz = f->sample_bytes;
   // device planes use the padded geometry of the caller's reference frames; a frame without references (intra) may leave it unset:
   // then the reference's own geometry (common/common_frame.c:435-452 with PADDING_Y = 160)
   const int pad = f->ref_stride[0] > 0 ? f->ref_pad : 160, padc = pad >> 1;
   const int sy = f->ref_stride[0] > 0 ? f->ref_stride[0] : ((w + 2 * pad + 15) & ~15), sc = f->ref_stride[0] > 0 ? f->ref_stride[1] : (((w >> 1) + 2 * padc + 15) & ~15);
   const size_t ref_y_bytes = (size_t)(h + 2 * pad) * sy * esz, ref_c_bytes = (size_t)((h >> 1) + 2 * padc) * sc * esz;
   if (D.w != w || D.h != h || D.esz != esz || D.sb != sb || D.pad != pad || D.sy != sy || D.sc != sc || D.nref < f->num_ref) {
-    free_state();
+    D.release();
+    D.nsbx = (w + sb - 1) / sb; D.nsby = (h + sb - 1) / sb;
+    const int nsb = D.nsbx * D.nsby;
     // source and reconstruction use the padded geometry of the reference frames (only their visible area is touched)
     for (int p = 0; p < 3; p++) { CK(cudaMalloc(&D.org[p], (p ? ref_c_bytes : ref_y_bytes) + 256)); CK(cudaMalloc(&D.rec[p], (p ? ref_c_bytes : ref_y_bytes) + 256)); }
     for (int r = 0; r < f->num_ref || r < 5; r++)
@@ -462,15 +560,17 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
     CK(cudaMalloc(&D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4)));
     CK(cudaMalloc(&D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES));
     CK(cudaMalloc(&D.leaf_count, sizeof(int) * nsb));
-    CK(cudaMalloc(&D.progress, sizeof(int) * (nsby + 1)));
     CK(cudaMalloc(&D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS));
-    CK(cudaMalloc(&D.works, sizeof(Work<S>) * (size_t)nsby * RDO_WARPS));
-    CK(cudaMalloc(&D.prof, sizeof(unsigned long long) * PF_N));
     D.w = w; D.h = h; D.esz = esz; D.sb = sb; D.pad = pad; D.sy = sy; D.sc = sc; D.nref = f->num_ref > 5 ? f->num_ref : 5;
   }
-  FrameCtx<S> C;
+  return TB_OK;
+}
+
+template <class S> void fill_ctx(FrameCtx<S> &C, const Slot &D, const tb_rdo_frame_t *f) {
   static const int8_t chroma_qp_mid[13] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37};  // common/common_tables.c:67-72
-  C.width = w; C.height = h; C.sb_size = sb; C.bitdepth = f->bitdepth; C.frame_type = f->frame_type; C.qp = f->qp;
+  const int w = D.w, h = D.h, esz = D.esz, pad = D.pad, padc = pad >> 1, sy = D.sy, sc = D.sc;
+  memset(&C, 0, sizeof(C));
+  C.width = w; C.height = h; C.sb_size = D.sb; C.bitdepth = f->bitdepth; C.frame_type = f->frame_type; C.qp = f->qp;
   C.qpc = f->qp < 30 ? f->qp : (f->qp >= 43 ? f->qp - 6 : chroma_qp_mid[f->qp - 30]);
   C.num_ref = f->num_ref; C.interp_ref = f->interp_ref; C.num_intra_modes = f->num_intra_modes; C.lambda = f->lambda; C.sqrt_lambda = sqrt(f->lambda);
   C.enable_bipred = f->enable_bipred; C.enable_tb_split = f->enable_tb_split; C.enable_pb_split = f->enable_pb_split; C.speed = f->encoder_speed; C.intra_rdo = f->intra_rdo;
@@ -483,61 +583,203 @@ template <class S> int run_frame(const tb_rdo_frame_t *f, cudaStream_t st) {
   for (int p = 0; p < 3; p++) { C.org[p] = (const S *)((char *)D.org[p] + (p ? oc : oy)); C.rec[p] = (S *)((char *)D.rec[p] + (p ? oc : oy)); }
   C.org_stride[0] = sy; C.org_stride[1] = sc; C.ref_stride[0] = sy; C.ref_stride[1] = sc; C.rec_stride[0] = sy; C.rec_stride[1] = sc;
   C.blk = D.blk; C.blk_stride = w / 4; C.leaves = D.leaves; C.leaf_count = D.leaf_count; C.coeffs = D.coeffs;
-  // uploads: source (visible area), references (whole padded planes: one contiguous copy each)
-  for (int p = 0; p < 3; p++)
-    CK(cudaMemcpy2DAsync((void *)C.org[p], (size_t)(p ? sc : sy) * esz, f->orig[p], (size_t)f->orig_stride[p ? 1 : 0] * esz, (size_t)(p ? w >> 1 : w) * esz, p ? h >> 1 : h,
-                         cudaMemcpyHostToDevice, st));
-  for (int r = 0; r < f->num_ref; r++)
-    for (int p = 0; p < 3; p++)
-      CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(D.progress, 0, sizeof(int) * (nsby + 1), st));
-  const bool want_prof = getenv("TB_RDO_PROF") != nullptr;
-  if (want_prof) CK(cudaMemsetAsync(D.prof, 0, sizeof(unsigned long long) * PF_N, st));
-  const size_t smem = ((sizeof(RdoCta) + 15) & ~(size_t)15) + sizeof(RdoShared<S>) * RDO_WARPS;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[esz]) { CK(cudaFuncSetAttribute(rdo_frame_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set[esz] = true; }
-  rdo_frame_kernel<S><<<nsby, 32 * RDO_WARPS, smem, st>>>(C, (Work<S> *)D.works, D.progress, nsbx, want_prof ? D.prof : nullptr);
-  CK(cudaGetLastError());
-  for (int p = 0; p < 3; p++)
-    CK(cudaMemcpy2DAsync(f->rec[p], (size_t)f->rec_stride[p ? 1 : 0] * esz, C.rec[p], (size_t)(p ? sc : sy) * esz, (size_t)(p ? w >> 1 : w) * esz, p ? h >> 1 : h,
-                         cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->blk, D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDeviceToHost, st));
-  int wedged = 0;
-  CK(cudaMemcpyAsync(&wedged, D.progress + nsby, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (want_prof) {
-    unsigned long long pr[PF_N];
-    CK(cudaMemcpy(pr, D.prof, sizeof(pr), cudaMemcpyDeviceToHost));
-    static const char *names[PF_N] = {"interp", "me", "me_bi", "tx_chain", "coeff_bits", "ssd_sad", "intra", "copy_avg", "early_skip", "wavefront_wait", "total"};
-    fprintf(stderr, "[tb_rdo prof] %d rows x %d warps:", nsby, RDO_WARPS);
-    for (int k = 0; k < PF_N; k++) fprintf(stderr, " %s %.1f%%", names[k], 100.0 * (double)pr[k] / (double)(pr[PF_TOTAL] ? pr[PF_TOTAL] : 1));
-    fprintf(stderr, "\n");
+}
+
+int check_desc(const tb_rdo_frame_t *f) {
+  if (!f || f->num_ref > TB_RDO_MAX_REF || f->num_ref < 0 || f->log2_sb_size > 7 || f->log2_sb_size < 4 || (f->sample_bytes != 1 && f->sample_bytes != 2) || f->width <= 0 ||
+      f->height <= 0 || (f->width & 7) || (f->height & 7) || f->interp_ref == 2 || f->qp < 0 || f->qp > 51 ||
+      (f->num_ref > 0 && (f->ref_pad < 16 || f->ref_stride[0] < f->width + 2 * f->ref_pad))) {
+    snprintf(g_err, sizeof(g_err), "unsupported frame description (%dx%d, %d refs, sb %d, interp_ref %d, qp %d, pad %d)", f ? f->width : 0, f ? f->height : 0,
+             f ? f->num_ref : 0, f ? f->log2_sb_size : 0, f ? f->interp_ref : 0, f ? f->qp : 0, f ? f->ref_pad : 0);
+    return TB_ERR_ARG;
   }
-  if (wedged) { snprintf(D.err, sizeof(D.err), "rdo_frame_kernel: a super-block row stopped publishing progress"); return TB_ERR_CUDA; }
+  return TB_OK;
+}
+
+template <class S> int batch_launch(tb_rdo_batch *b, int n_active, cudaStream_t st) {
+  // rows of the active slots, frame-major: the lowest index is the most urgent row
+  int nrows = 0, nsb_total = 0;
+  for (int s = 0; s < n_active; s++) { nrows += b->slots[s].nsby; nsb_total += b->slots[s].nsby * b->slots[s].nsbx; }
+  if (nrows > b->nrows_cap) {
+    cudaFreeHost(b->rows_host); cudaFree(b->rows_dev); cudaFree(b->sched_dev);
+    b->rows_host = nullptr; b->rows_dev = nullptr; b->sched_dev = nullptr; b->nrows_cap = 0;
+    CK(cudaMallocHost((void **)&b->rows_host, sizeof(RowDesc) * nrows));
+    CK(cudaMalloc((void **)&b->rows_dev, sizeof(RowDesc) * nrows));
+    CK(cudaMalloc((void **)&b->sched_dev, sizeof(int) * (2 * (size_t)nrows + CTL_N)));
+    b->nrows_cap = nrows;
+  }
+  if (!b->ctl_host) CK(cudaMallocHost((void **)&b->ctl_host, sizeof(int) * CTL_N));
+  int g = 0;
+  for (int s = 0; s < n_active; s++)
+    for (int r = 0; r < b->slots[s].nsby; r++) { b->rows_host[g].frame = s; b->rows_host[g].row = r; b->rows_host[g].nsbx = b->slots[s].nsbx; b->rows_host[g].pad = 0; g++; }
+  b->nrows = nrows;
+  const size_t smem = smem_bytes<S>();
+  static bool attr_set[3] = {false, false, false};
+  static int per_sm[3] = {0, 0, 0};
+  if (!attr_set[sizeof(S)]) {
+    CK(cudaFuncSetAttribute(rdo_batch_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[sizeof(S)], rdo_batch_kernel<S>, 32 * RDO_WARPS, smem));
+    attr_set[sizeof(S)] = true;
+  }
+  if (!b->sms) { int dev = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, dev)); }
+  // persistent grid: every CTA is resident (a CTA may spin until a neighbour publishes), never more CTAs than rows
+  int grid = b->sms * (per_sm[sizeof(S)] > 0 ? per_sm[sizeof(S)] : 1);
+  if (const char *e = getenv("TB_RDO_GRID")) { const int v = atoi(e); if (v > 0 && v < grid) grid = v; }
+  if (grid > nrows) grid = nrows;
+  if (grid > b->grid_cap) {
+    cudaFree(b->works); b->works = nullptr; b->grid_cap = 0;
+    CK(cudaMalloc(&b->works, sizeof(Work<S>) * (size_t)grid * RDO_WARPS));
+    b->grid_cap = grid;
+  }
+  b->grid = grid;
+  if (!b->prof) CK(cudaMalloc((void **)&b->prof, sizeof(unsigned long long) * ST_END));
+  CK(cudaMemcpyAsync(b->rows_dev, b->rows_host, sizeof(RowDesc) * nrows, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(b->ctx_dev, b->ctx_host, sizeof(FrameCtx<S>) * n_active, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(b->sched_dev, 0, sizeof(int) * (2 * (size_t)nrows + CTL_N), st));
+  b->ctl_host[CTL_REMAINING] = nsb_total; b->ctl_host[CTL_ERROR] = 0; b->ctl_host[2] = b->ctl_host[3] = 0;
+  CK(cudaMemcpyAsync(b->sched_dev + 2 * (size_t)nrows, b->ctl_host, sizeof(int) * CTL_N, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(b->prof, 0, sizeof(unsigned long long) * ST_END, st));
+  rdo_batch_kernel<S><<<grid, 32 * RDO_WARPS, smem, st>>>((const FrameCtx<S> *)b->ctx_dev, b->rows_dev, nrows, (Work<S> *)b->works, b->sched_dev, b->sched_dev + nrows,
+                                                         b->sched_dev + 2 * (size_t)nrows, b->prof);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->ctl_host, b->sched_dev + 2 * (size_t)nrows, sizeof(int) * CTL_N, cudaMemcpyDeviceToHost, st));
   return TB_OK;
 }
 
 }  // namespace
 
 extern "C" {
-const char *tb_rdo_last_error(void) { return D.err; }
+const char *tb_rdo_last_error(void) { return g_err; }
 static uint64_t g_rdo_launches = 0;
 uint64_t tb_rdo_launch_count(void) { return g_rdo_launches; }
 
-int tb_rdo_encode_frame(const tb_rdo_frame_t *f) {
-  if (!f || f->num_ref > TB_RDO_MAX_REF || f->num_ref < 0 || f->log2_sb_size > 7 || f->log2_sb_size < 4 || (f->sample_bytes != 1 && f->sample_bytes != 2) || f->width <= 0 ||
-      f->height <= 0 || (f->width & 7) || (f->height & 7) || f->interp_ref == 2 || f->qp < 0 || f->qp > 51 || !f->blk || !f->leaves || !f->leaf_count || !f->coeffs ||
-      (f->num_ref > 0 && (f->ref_pad < 16 || f->ref_stride[0] < f->width + 2 * f->ref_pad))) {
-    snprintf(D.err, sizeof(D.err), "unsupported frame description (%dx%d, %d refs, sb %d, interp_ref %d, qp %d, pad %d)", f ? f->width : 0, f ? f->height : 0,
-             f ? f->num_ref : 0, f ? f->log2_sb_size : 0, f ? f->interp_ref : 0, f ? f->qp : 0, f ? f->ref_pad : 0);
-    return TB_ERR_ARG;
+tb_rdo_batch_t *tb_rdo_batch_create(int n_slots, int sample_bytes) {
+  if (n_slots <= 0 || (sample_bytes != 1 && sample_bytes != 2)) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_create: bad arguments"); return nullptr; }
+  if (tb_init(-1) != TB_OK) { snprintf(g_err, sizeof(g_err), "no CUDA device: %s", tb_last_error()); return nullptr; }  // no CPU path
+  tb_rdo_batch *b = new tb_rdo_batch();
+  b->nslots = n_slots; b->esz = sample_bytes;
+  b->slots = new Slot[n_slots];
+  const size_t cb = (sample_bytes == 1 ? sizeof(FrameCtx<uint8_t>) : sizeof(FrameCtx<uint16_t>)) * (size_t)n_slots;
+  if (cudaMallocHost(&b->ctx_host, cb) != cudaSuccess || cudaMalloc(&b->ctx_dev, cb) != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "tb_rdo_batch_create: out of memory");
+    tb_rdo_batch_destroy(b);
+    return nullptr;
   }
-  if (tb_init(-1) != TB_OK) { snprintf(D.err, sizeof(D.err), "no CUDA device: %s", tb_last_error()); return TB_ERR_CUDA; }  // no CPU path
+  return b;
+}
+
+void tb_rdo_batch_destroy(tb_rdo_batch_t *b) {
+  if (!b) return;
+  cudaDeviceSynchronize();
+  for (int s = 0; s < b->nslots; s++) b->slots[s].release();
+  delete[] b->slots;
+  cudaFreeHost(b->ctx_host); cudaFree(b->ctx_dev); cudaFreeHost(b->rows_host); cudaFree(b->rows_dev); cudaFree(b->sched_dev); cudaFreeHost(b->ctl_host);
+  cudaFree(b->works); cudaFree(b->prof);
+  delete b;
+}
+
+int tb_rdo_batch_upload(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f) {
+  if (!b || slot < 0 || slot >= b->nslots) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_upload: bad slot"); return TB_ERR_ARG; }
+  if (check_desc(f) != TB_OK) return TB_ERR_ARG;
+  if (f->sample_bytes != b->esz) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_upload: sample size differs from the batch's"); return TB_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)tb_stream();
+  Slot &D = b->slots[slot];
+  if (slot_prepare(D, f) != TB_OK) return TB_ERR_CUDA;
+  const int esz = D.esz, w = D.w, h = D.h, padc = D.pad >> 1;
+  const size_t oy = ((size_t)D.pad * D.sy + D.pad) * esz, oc = ((size_t)padc * D.sc + padc) * esz;
+  const size_t ref_y_bytes = (size_t)(h + 2 * D.pad) * D.sy * esz, ref_c_bytes = (size_t)((h >> 1) + 2 * padc) * D.sc * esz;
+  if (esz == 1) fill_ctx(((FrameCtx<uint8_t> *)b->ctx_host)[slot], D, f);
+  else fill_ctx(((FrameCtx<uint16_t> *)b->ctx_host)[slot], D, f);
+  // uploads: source (visible area), references (whole padded planes: one contiguous copy each)
+  for (int p = 0; p < 3; p++)
+    CK(cudaMemcpy2DAsync((char *)D.org[p] + (p ? oc : oy), (size_t)(p ? D.sc : D.sy) * esz, f->orig[p], (size_t)f->orig_stride[p ? 1 : 0] * esz, (size_t)(p ? w >> 1 : w) * esz,
+                         p ? h >> 1 : h, cudaMemcpyHostToDevice, st));
+  for (int r = 0; r < f->num_ref; r++)
+    for (int p = 0; p < 3; p++)
+      CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
+  D.used = 1;
+  return TB_OK;
+}
+
+int tb_rdo_batch_run(tb_rdo_batch_t *b, int n_active) {
+  if (!b || n_active <= 0 || n_active > b->nslots) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_run: bad frame count"); return TB_ERR_ARG; }
+  for (int s = 0; s < n_active; s++)
+    if (!b->slots[s].used) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_run: slot %d was never uploaded", s); return TB_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)tb_stream();
   g_rdo_launches++;
-  return f->sample_bytes == 1 ? run_frame<uint8_t>(f, st) : run_frame<uint16_t>(f, st);
+  return b->esz == 1 ? batch_launch<uint8_t>(b, n_active, st) : batch_launch<uint16_t>(b, n_active, st);
 }
+
+int tb_rdo_batch_download(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f) {
+  if (!b || slot < 0 || slot >= b->nslots || !b->slots[slot].used || !f || !f->blk || !f->leaves || !f->leaf_count || !f->coeffs) {
+    snprintf(g_err, sizeof(g_err), "tb_rdo_batch_download: bad arguments");
+    return TB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)tb_stream();
+  const Slot &D = b->slots[slot];
+  const int esz = D.esz, w = D.w, h = D.h, padc = D.pad >> 1, nsb = D.nsbx * D.nsby;
+  if (f->width != w || f->height != h || f->sample_bytes != esz) { snprintf(g_err, sizeof(g_err), "tb_rdo_batch_download: geometry differs from the uploaded frame"); return TB_ERR_ARG; }
+  const size_t oy = ((size_t)D.pad * D.sy + D.pad) * esz, oc = ((size_t)padc * D.sc + padc) * esz;
+  for (int p = 0; p < 3; p++)
+    if (f->rec[p])
+      CK(cudaMemcpy2DAsync(f->rec[p], (size_t)f->rec_stride[p ? 1 : 0] * esz, (const char *)D.rec[p] + (p ? oc : oy), (size_t)(p ? D.sc : D.sy) * esz, (size_t)(p ? w >> 1 : w) * esz,
+                           p ? h >> 1 : h, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->blk, D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDeviceToHost, st));
+  return TB_OK;
+}
+
+int tb_rdo_batch_sync(tb_rdo_batch_t *b) {
+  if (!b) return TB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)tb_stream();
+  CK(cudaStreamSynchronize(st));
+  if (b->prof) CK(cudaMemcpy(b->stats, b->prof, sizeof(b->stats), cudaMemcpyDeviceToHost));
+  if (getenv("TB_RDO_PROF") && b->prof) {
+    const unsigned long long *pr = b->stats;
+    static const char *names[PF_N] = {"interp", "me", "me_bi", "tx_chain", "coeff_bits", "ssd_sad", "intra", "copy_avg", "early_skip", "idle", "total"};
+    fprintf(stderr, "[tb_rdo prof] %d rows on %d CTAs x %d warps:", b->nrows, b->grid, RDO_WARPS);
+    for (int k = 0; k < PF_N; k++) fprintf(stderr, " %s %.1f%%", names[k], 100.0 * (double)pr[k] / (double)(pr[PF_TOTAL] ? pr[PF_TOTAL] : 1));
+    fprintf(stderr, "\n");
+  }
+  if (b->ctl_host && (b->ctl_host[CTL_ERROR] || b->ctl_host[CTL_REMAINING] != 0)) {
+    snprintf(g_err, sizeof(g_err), "rdo_batch_kernel: a super-block row stopped publishing progress (%d super blocks left)", b->ctl_host[CTL_REMAINING]);
+    return TB_ERR_CUDA;
+  }
+  return TB_OK;
+}
+
+int tb_rdo_batch_grid(const tb_rdo_batch_t *b) { return b ? b->grid : 0; }
+int tb_rdo_batch_stats(const tb_rdo_batch_t *b, uint64_t *out, int n) {
+  if (!b || !out) return 0;
+  const int m = n < TB_RDO_NSTATS ? n : TB_RDO_NSTATS;
+  for (int k = 0; k < m; k++) out[k] = b->stats[k];
+  return m;
+}
+
+int tb_rdo_encode_frames(const tb_rdo_frame_t *f, int n) {
+  static tb_rdo_batch *B[3] = {nullptr, nullptr, nullptr};  // one internal batch per sample size, grown on demand
+  if (!f || n <= 0) { snprintf(g_err, sizeof(g_err), "tb_rdo_encode_frames: bad arguments"); return TB_ERR_ARG; }
+  for (int i = 0; i < n; i++) {
+    if (check_desc(&f[i]) != TB_OK) return TB_ERR_ARG;
+    if (f[i].sample_bytes != f[0].sample_bytes) { snprintf(g_err, sizeof(g_err), "tb_rdo_encode_frames: mixed sample sizes"); return TB_ERR_ARG; }
+    if (!f[i].blk || !f[i].leaves || !f[i].leaf_count || !f[i].coeffs) { snprintf(g_err, sizeof(g_err), "tb_rdo_encode_frames: missing output buffers"); return TB_ERR_ARG; }
+  }
+  const int esz = f[0].sample_bytes;
+  if (!B[esz] || B[esz]->nslots < n) {
+    tb_rdo_batch_destroy(B[esz]);
+    B[esz] = tb_rdo_batch_create(n, esz);
+    if (!B[esz]) return TB_ERR_CUDA;
+  }
+  int rc;
+  for (int i = 0; i < n; i++)
+    if ((rc = tb_rdo_batch_upload(B[esz], i, &f[i])) != TB_OK) return rc;
+  if ((rc = tb_rdo_batch_run(B[esz], n)) != TB_OK) return rc;
+  for (int i = 0; i < n; i++)
+    if ((rc = tb_rdo_batch_download(B[esz], i, &f[i])) != TB_OK) return rc;
+  return tb_rdo_batch_sync(B[esz]);
+}
+
+int tb_rdo_encode_frame(const tb_rdo_frame_t *f) { return tb_rdo_encode_frames(f, 1); }
 }

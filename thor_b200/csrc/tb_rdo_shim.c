@@ -13,6 +13,12 @@
  * Configurations the device loop does not cover (see thor_b200.h) fall through to __real_process_block_*(), i.e. the reference's
  * host loop over the per-call drop-in kernels of libthor_b200.so.
  *
+ * Linked WITHOUT libthor_b200.so (oracle/_ref/Thorenc_capture: the all-reference CPU encoder + this file) tb_rdo_encode_frame is an unresolved
+ * weak symbol and every super block is decided by the reference's own process_block(); the shim then only observes: it times the RD loop
+ * (TB_RDO_STATS=1) and, with TB_RDO_DUMP=<dir>, writes every frame's RD-loop JOB (the tb_rdo_frame_t description, source planes, padded
+ * reference planes) together with the reference's RESULT (reconstruction before the in-loop filters, per-4x4 block state, process_block's
+ * return value per super block) to <dir>/frame_NNN.job — the workload and the expected answers of bench.py and tests/test_gpu_rdo_batch.py.
+ *
  * TB_RDO_VERIFY=1 (needs the per-super-block entry of oracle/librdo_hostcheck.so, TEST INFRASTRUCTURE): every super block is decided by
  * tb_rdo_encode_sb() AND by the reference's own process_block() on the same state; bits, reconstruction and deblock_data are compared
  * and the reference's result is kept.  That is how the control flow of tb_rdo.h is pinned against the reference in this container.
@@ -36,6 +42,7 @@ void find_block_contexts_lbd(int ypos, int xpos, int height, int width, int size
 void find_block_contexts_hbd(int ypos, int xpos, int height, int width, int size, deblock_data_t *deblock_data, block_context_t *block_context, int enable);
 /* optional (weak): only oracle/librdo_hostcheck.so has it */
 int tb_rdo_encode_sb(const tb_rdo_frame_t *f, int sbx, int sby) __attribute__((weak));
+int tb_rdo_encode_frame(const tb_rdo_frame_t *f) __attribute__((weak)); /* absent in the capture link (no libthor_b200.so) */
 const char *tb_rdo_last_error(void) __attribute__((weak));
 
 static struct {
@@ -45,7 +52,9 @@ static struct {
   int32_t *leaf_count;
   int16_t *coeffs;
   long sb_total, sb_bad, frames_dev, frames_host;
-  double t_rdo, t_emit;
+  double t_rdo, t_emit, t_ref;
+  int32_t *sb_cost; /* capture: process_block's return value per super block */
+  FILE *dump;
 } G;
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
@@ -54,8 +63,8 @@ static void shim_report(void) {
   if (G.verify)
     fprintf(stderr, "[tb_rdo_shim] verify: %ld super blocks compared with the reference's process_block, %ld differ\n", G.sb_total, G.sb_bad);
   if (getenv("TB_RDO_STATS"))
-    fprintf(stderr, "[tb_rdo_shim] frames decided by tb_rdo_encode_frame: %ld, by the reference's host loop: %ld; seconds in tb_rdo_encode_frame %.3f, in serialisation %.3f\n",
-            G.frames_dev, G.frames_host, G.t_rdo, G.t_emit);
+    fprintf(stderr, "[tb_rdo_shim] frames decided by tb_rdo_encode_frame: %ld, by the reference's host loop: %ld; seconds in tb_rdo_encode_frame %.3f, in serialisation %.3f, "
+            "in the reference's process_block %.3f\n", G.frames_dev, G.frames_host, G.t_rdo, G.t_emit, G.t_ref);
 }
 
 static int supported(const encoder_info_t *e, int qp, int sub, int hbd) {
@@ -70,7 +79,8 @@ static int supported(const encoder_info_t *e, int qp, int sub, int hbd) {
 static void ensure_buffers(int w, int h, int log2sb) {
   const int sb = 1 << log2sb, nsb = ((w + sb - 1) / sb) * ((h + sb - 1) / sb);
   if (G.w == w && G.h == h && G.nsb == nsb) return;
-  free(G.blk); free(G.leaves); free(G.leaf_count); free(G.coeffs);
+  free(G.blk); free(G.leaves); free(G.leaf_count); free(G.coeffs); free(G.sb_cost);
+  G.sb_cost = calloc((size_t)nsb, sizeof(int32_t));
   G.w = w; G.h = h; G.nsb = nsb;
   G.blk = calloc((size_t)(h / 4) * (w / 4), sizeof(tb_rdo_blk_t));
   G.leaves = calloc((size_t)nsb * TB_RDO_MAX_LEAVES, sizeof(tb_rdo_leaf_t));
@@ -191,6 +201,43 @@ static void copy_region(void *dst, const void *src, int stride, int x0, int y0, 
   for (int y = y0; y < y1; y++) memcpy((char *)dst + ((size_t)y * stride + x0) * esz, (const char *)src + ((size_t)y * stride + x0) * esz, (size_t)(x1 - x0) * esz);
 }
 
+/* ---- capture (reference mode): one file per frame, see the header comment.  Layout: magic, tb_rdo_frame_t (pointers zeroed), frame_num, nsb,
+ * orig Y U V (visible, compact), per reference Y U V (whole padded planes); then, after the last super block: rec Y U V (visible, compact),
+ * tb_rdo_blk_t grid, int32 cost per super block. */
+static void dump_plane(FILE *fp, const void *p, int stride, int w, int h, int esz) {
+  for (int y = 0; y < h; y++) fwrite((const char *)p + (size_t)y * stride * esz, (size_t)esz, (size_t)w, fp);
+}
+static void capture_begin(encoder_info_t *e, const tb_rdo_frame_t *f, int esz) {
+  const char *dir = getenv("TB_RDO_DUMP");
+  char path[1024];
+  snprintf(path, sizeof(path), "%s/frame_%03d.job", dir, (int)e->frame_info.frame_num);
+  G.dump = fopen(path, "wb");
+  if (!G.dump) { fprintf(stderr, "[tb_rdo_shim] cannot write %s\n", path); exit(2); }
+  tb_rdo_frame_t h = *f;
+  memset(h.orig, 0, sizeof(h.orig)); memset(h.ref, 0, sizeof(h.ref)); memset(h.rec, 0, sizeof(h.rec)); h.blk = NULL; h.leaves = NULL; h.leaf_count = NULL; h.coeffs = NULL;
+  const int32_t extra[2] = {(int32_t)e->frame_info.frame_num, (int32_t)G.nsb};
+  fwrite("TBJOB1\0\0", 1, 8, G.dump);
+  fwrite(&h, sizeof(h), 1, G.dump);
+  fwrite(extra, sizeof(extra), 1, G.dump);
+  const int w = f->width, hh = f->height;
+  for (int p = 0; p < 3; p++) dump_plane(G.dump, f->orig[p], f->orig_stride[p ? 1 : 0], p ? w >> 1 : w, p ? hh >> 1 : hh, esz);
+  const int pad = f->ref_pad, padc = pad >> 1;
+  for (int r = 0; r < f->num_ref; r++)
+    for (int p = 0; p < 3; p++) {
+      const int st = f->ref_stride[p ? 1 : 0], pd = p ? padc : pad, ph = (p ? hh >> 1 : hh) + 2 * pd;
+      fwrite((const char *)f->ref[r][p] - ((size_t)pd * st + pd) * esz, (size_t)esz, (size_t)st * ph, G.dump);
+    }
+}
+static void capture_end(encoder_info_t *e, const tb_rdo_frame_t *f, int esz) {
+  const int w = f->width, hh = f->height;
+  for (int p = 0; p < 3; p++) dump_plane(G.dump, f->rec[p], f->rec_stride[p ? 1 : 0], p ? w >> 1 : w, p ? hh >> 1 : hh, esz);
+  deblock_to_blk(e);
+  fwrite(G.blk, sizeof(tb_rdo_blk_t), (size_t)(hh / 4) * (w / 4), G.dump);
+  fwrite(G.sb_cost, sizeof(int32_t), (size_t)G.nsb, G.dump);
+  fclose(G.dump);
+  G.dump = NULL;
+}
+
 static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, int qp, int sub, int hbd) {
   int (*real)(encoder_info_t *, int, int, int, int, int) = hbd ? __real_process_block_hbd : __real_process_block_lbd;
   const int esz = hbd ? 2 : 1;
@@ -200,6 +247,18 @@ static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, i
   const int x1 = xpos + sb < e->width ? xpos + sb : e->width, y1 = ypos + sb < e->height ? ypos + sb : e->height;
   tb_rdo_frame_t f;
   fill_desc(&f, e, esz);
+
+  if (!tb_rdo_encode_frame && !G.verify) { /* capture link: the reference decides, the shim observes */
+    const int dumping = getenv("TB_RDO_DUMP") != NULL;
+    if (dumping && xpos == 0 && ypos == 0) capture_begin(e, &f, esz);
+    const double t0 = now_s();
+    const int ret = real(e, size, ypos, xpos, qp, sub);
+    G.t_ref += now_s() - t0;
+    G.sb_cost[sbi] = ret;
+    if (xpos == 0 && ypos == 0) G.frames_host++;
+    if (dumping && G.dump && x1 == e->width && y1 == e->height) capture_end(e, &f, esz);
+    return ret;
+  }
 
   if (G.verify) {
     if (!tb_rdo_encode_sb) { fprintf(stderr, "[tb_rdo_shim] TB_RDO_VERIFY needs tb_rdo_encode_sb (oracle/librdo_hostcheck.so)\n"); exit(2); }

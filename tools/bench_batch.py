@@ -42,7 +42,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SQUARED_LAMBDA_QP = {32: 77.7672, 33: 98.6706, 34: 125.1926, 35: 158.8437}  # enc/encode_tables.c:29-36

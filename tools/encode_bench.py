@@ -60,6 +60,9 @@ def main():
     bit, rec, t_gpu, err = run("Thorenc_b200_rdo", flags, args, "gpu", args.tmp, {"TB_RDO_STATS": "1", "TB_RDO_TRACE": "1"})
     m = re.search(r"frames decided by tb_rdo_encode_frame: (\d+), by the reference's host loop: (\d+); seconds in tb_rdo_encode_frame ([\d.]+), in serialisation ([\d.]+)", err)
     per_frame = [float(x) for x in re.findall(r"tb_rdo_encode_frame ([\d.]+) ms", err)]
+    for line in err.splitlines():
+        if "[tb_rdo prof]" in line:
+            print(line, file=sys.stderr)
     out.update({"gpu_seconds_whole_process": round(t_gpu, 2), "gpu_mpixel_s_whole_process": round(px / t_gpu / 1e6, 4),
                 "frames_on_device": int(m.group(1)) if m else None, "frames_on_host_loop": int(m.group(2)) if m else None,
                 "rd_loop_seconds": float(m.group(3)) if m else None, "serialise_seconds": float(m.group(4)) if m else None,
