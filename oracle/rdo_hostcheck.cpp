@@ -88,6 +88,7 @@ template <class S> struct OracleBackend {
   int warp() const { return wid; }
   bool mine(int k) const { return (k % X->nw) == wid; }
   void cta_sync() const { X->barrier(); }
+  void mark(int) const {}  // phase timers exist only on the device
   void put_me(int ref, const Mv *mv16, uint32_t sad) const { memcpy(X->mv[ref], mv16, 16 * sizeof(Mv)); X->sad[ref] = sad; }
   void get_me(int ref, Mv *mv16, uint32_t *sad) const { memcpy(mv16, X->mv[ref], 16 * sizeof(Mv)); *sad = X->sad[ref]; }
   int reduce_best(uint32_t *cost, int *idx) const {

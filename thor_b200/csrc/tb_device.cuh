@@ -48,6 +48,9 @@
 // TB_LDG: read-only-path load of data that no thread writes during the kernel (frames, work items).  TB_LDF: load of reconstructed
 // samples that ANOTHER CTA may have written earlier in the same kernel (wavefront RD loop, tb_rdo.cu): that translation unit maps
 // TB_LDG to a plain load (its "original" block can be a scratch block written moments ago) and TB_LDF to an L1-bypassing load.
+#ifndef TB_SAD_ROWS
+#define TB_SAD_ROWS 0
+#endif
 #ifndef TB_LDG
 #define TB_LDG(p) __ldg(p)
 #endif
@@ -232,12 +235,59 @@ __device__ __noinline__ uint32_t multi_sad_wide(const S *o, int os, const S *r, 
   }
   return out;
 }
+// The same for the device-resident RD loop (tb_rdo.cu, TB_SAD_ROWS), where ONE warp walks blocks of up to 128x128 alone and nothing else hides its latency:
+// the lanes of a load request lie along a ROW (32-byte .. 128-byte contiguous segments: one or two L1 wavefronts per request instead of one per lane when
+// the rows are dealt to lanes), five positions share each load of the original (a telescope grid row: their reference segments overlap), and the five
+// accumulations are independent.  Rows >= 8 words; lane = (row % RP) * LW + word, RP rows per pass.
+template <class S>
+__device__ __noinline__ uint32_t multi_sad_rows(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
+  constexpr int PW = Word<S>::PW, CH = 5;
+  const int lane = lane_id();
+  const int LW = w / PW, LWe = LW < 32 ? LW : 32, RP = 32 / LWe, CI = LW / LWe;  // words per row, lanes per row, rows per pass, column iterations
+  const int col0 = lane & (LWe - 1), rsub = lane / LWe;
+  const int osw = (os * (int)sizeof(S)) >> 2;
+  const uint32_t *oq = (const uint32_t *)o;
+  uint32_t out = 0;
+  for (int base = 0; base < n; base += CH) {
+    const uint32_t *rq[CH];
+    unsigned sh[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const int off = __shfl_sync(FULL, roff, min(base + k, n - 1));
+      const uintptr_t a = (uintptr_t)(r + off);
+      rq[k] = (const uint32_t *)(a & ~(uintptr_t)3);
+      sh[k] = (unsigned)(a & 3) * 8;
+    }
+    const int rsw = (rs * (int)sizeof(S)) >> 2;
+    uint32_t acc[CH] = {0, 0, 0, 0, 0};
+    for (int row = rsub; row < h; row += RP) {
+      for (int ci = 0; ci < CI; ci++) {
+        const int col = col0 + ci * 32;
+        const uint32_t a = TB_LDG(oq + row * osw + col);
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+          const uint32_t *q = rq[k] + row * rsw + col;
+          acc[k] += word_sad<S>(a, __funnelshift_r(TB_LDG(q), TB_LDG(q + 1), sh[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const uint32_t t = warp_sum(acc[k]);
+      if (lane == base + k && base + k < n) out = t;
+    }
+  }
+  return out;
+}
 template <class S, int TW = 1>
 __device__ __forceinline__ uint32_t multi_sad(const S *o, int os, const S *r, int rs, int w, int h, int roff, int n) {
 #if TB_SAD_V4
   // only the CTA-team searches (blocks >= 2048 samples) take the wide form: a second callee at the call sites of the one-warp
   // searches costs them more in spills than the 32x32 blocks would gain
   if (TW > 1 && (w / Word<S>::PW) * h >= 256 && h >= 16 && w * (int)sizeof(S) >= 16) return multi_sad_wide<S>(o, os, r, rs, w, h, roff, n);
+#endif
+#if TB_SAD_ROWS
+  if (TW == 1 && w / Word<S>::PW >= 8) return multi_sad_rows<S>(o, os, r, rs, w, h, roff, n);
 #endif
   return multi_sad_narrow<S>(o, os, r, rs, w, h, roff, n);
 }

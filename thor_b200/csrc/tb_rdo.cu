@@ -16,6 +16,9 @@
 // The device code of this unit lives in its own namespace (the headers define __constant__ tables).
 #define TB_LDG(p) (*(p))
 #define TB_LDF(p) __ldcg(p)
+#ifndef TB_SAD_ROWS
+#define TB_SAD_ROWS 1  // integer-position SADs of blocks >= 32 bytes wide: lanes along the row (multi_sad_rows)
+#endif
 #define tb tb_rdo_tu
 #include <cstdio>
 #include <cstdlib>
@@ -34,16 +37,18 @@ enum { PF_INTERP, PF_ME, PF_MEBI, PF_TX, PF_BITS, PF_SSD, PF_INTRA, PF_COPY, PF_
 // always-on work counters (SURVEY.md §8d algorithmic samples of what the RD loop actually executed: the loop is data dependent) behind the cycle counters:
 // searches, integer block SADs, sub-pel probes, search samples, predictions, prediction samples, transform chains, chain samples, intra predictions, intra samples,
 // SSD/SAD samples, super blocks
-enum { ST_ME = PF_N, ST_ME_INT, ST_ME_SUB, ST_ME_SAMPLES, ST_IP, ST_IP_SAMPLES, ST_TX, ST_TX_SAMPLES, ST_INTRA, ST_INTRA_SAMPLES, ST_SSD_SAMPLES, ST_SB, ST_END };
+enum { ST_ME = PF_N, ST_ME_INT, ST_ME_SUB, ST_ME_SAMPLES, ST_IP, ST_IP_SAMPLES, ST_TX, ST_TX_SAMPLES, ST_INTRA, ST_INTRA_SAMPLES, ST_SSD_SAMPLES, ST_SB,
+       ST_ME_SZ /* cycles of searches by coding-block size 8..128 */, ST_TX_SZ = ST_ME_SZ + 5 /* chains by transform size 4..128 */, ST_IP_SZ = ST_TX_SZ + 6 /* predictions by width 4..128 */,
+       ST_PH = ST_IP_SZ + 6 /* wall cycles of warp 0 by decision phase (tb_rdo.h PH_*) */, ST_END = ST_PH + tbr::PH_N };
 struct Prof {
   long long *acc;
-  int k;
+  int k, k2;
   long long t0;
 #ifdef __CUDA_ARCH__
-  __device__ __forceinline__ Prof(long long *a, int kk) : acc(a), k(kk), t0(clock64()) {}
-  __device__ __forceinline__ ~Prof() { acc[k] += clock64() - t0; }
+  __device__ __forceinline__ Prof(long long *a, int kk, int kk2 = -1) : acc(a), k(kk), k2(kk2), t0(clock64()) {}
+  __device__ __forceinline__ ~Prof() { const long long d = clock64() - t0; acc[k] += d; if (k2 >= 0) acc[k2] += d; }
 #else
-  Prof(long long *a, int kk) : acc(a), k(kk), t0(0) {}
+  Prof(long long *a, int kk, int kk2 = -1) : acc(a), k(kk), k2(kk2), t0(0) {}
 #endif
 };
 
@@ -65,6 +70,7 @@ struct RdoCta {
 // per-warp scratch
 template <class S> struct RdoShared {
   long long prof[ST_END];
+  long long t_mark;
   TxScratch sc;
   alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual
   alignas(16) int16_t out16[256];                // transform output of the early-skip test; coefficient scan for the bit count
@@ -82,6 +88,9 @@ template <class S> struct DevBackend {
   __device__ __forceinline__ int warp() const { return wid; }
   __device__ __forceinline__ bool mine(int k) const { return (k % nw) == wid; }
   __device__ void cta_sync() const { __threadfence(); __syncthreads(); }
+  __device__ __forceinline__ void mark(int k) const {
+    if (wid == 0 && (threadIdx.x & 31) == 0) { const long long t = clock64(); sh->prof[ST_PH + k] += t - sh->t_mark; sh->t_mark = t; }
+  }
   __device__ void put_me(int ref, const Mv *mv16, uint32_t sad) const {
     if ((threadIdx.x & 31) < 16) cta->x_mv[ref][threadIdx.x & 31] = mv16[threadIdx.x & 31];
     if ((threadIdx.x & 31) == 0) cta->x_sad[ref] = sad;
@@ -127,6 +136,7 @@ template <class S> struct DevBackend {
 
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
 #define PROF(k) Prof prof__(sh->prof, k)
+#define PROF2(k, k2) Prof prof__(sh->prof, k, k2)
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 
   __device__ tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const {
@@ -146,7 +156,7 @@ template <class S> struct DevBackend {
   }
   // prediction of one block; widths that are not powers of two (rectangular blocks at the right frame edge) take the per-sample form
   __device__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
-    PROF(PF_INTERP);
+    PROF2(PF_INTERP, ST_IP_SZ + min(5, max(0, ilog2(max(w, h)) - 2)));
     if (lane() == 0) { sh->prof[ST_IP] += 1; sh->prof[ST_IP_SAMPLES] += (xf_any(mv, chroma) ? (w + 5) * (h + 5) : w * h) + w * h; }
     sync();
     if (!(w & (w - 1))) warp_interp<S>(dst, ds, ref, rs, w, h, mv.x, mv.y, sign, chroma, bip, pw, ph, xpos, ypos, F->bitdepth);
@@ -226,7 +236,7 @@ template <class S> struct DevBackend {
     sync();
   }
   __device__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
-    PROF(PF_TX);
+    PROF2(PF_TX, ST_TX_SZ + ilog2(size) - 2);
     if (lane() == 0) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * size * size; }
     sync();
     int cbp;
@@ -280,7 +290,7 @@ template <class S> struct DevBackend {
   }
   __device__ int me(const S *org, int os, const S *ref, int rs, int size, int w, int h, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
                     int ncand) const {
-    PROF(PF_ME);
+    PROF2(PF_ME, ST_ME_SZ + ilog2(size) - 3);
     sync();
     MeCtx c;
     c.size = size; c.width = w; c.height = h; c.sign = sign; c.s = sign ? -1 : 1; c.xpos = xpos; c.ypos = ypos; c.fw = F->width; c.fh = F->height;
@@ -378,7 +388,10 @@ template <class S> struct DevBackend {
   }
 };
 
-constexpr int RDO_WARPS = 8;  // warps per CTA: 8 x 32 threads x 255 registers = the whole register file of an SM
+#ifndef TB_RDO_WARPS
+#define TB_RDO_WARPS 8
+#endif
+constexpr int RDO_WARPS = TB_RDO_WARPS;  // warps per CTA: 8 x 32 threads x 255 registers = the whole register file of an SM
 
 // One row of super blocks of one frame of the batch.  Rows are the unit a CTA claims; super blocks inside a row are sequential.
 struct RowDesc { int frame, row, nsbx, pad; };
@@ -467,7 +480,9 @@ __global__ void __launch_bounds__(32 * RDO_WARPS, 1)
     int sbx = cta.x_idx[0];
     while (true) {
       Rdo<S, DevBackend<S>> R(fctx, works[blockIdx.x * nw + wid], works[blockIdx.x * nw], be);
+      if (lane == 0) sh.t_mark = clock64();
       R.process_sb(sbx, rd.row);
+      be.mark(tbr::PH_OTHER);
       __threadfence();  // every writing thread orders its stores before the flag
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -633,16 +648,16 @@ template <class S> int batch_launch(tb_rdo_batch *b, int n_active, cudaStream_t 
   }
   b->grid = grid;
   if (!b->prof) CK(cudaMalloc((void **)&b->prof, sizeof(unsigned long long) * ST_END));
-  CK(cudaMemcpyAsync(b->rows_dev, b->rows_host, sizeof(RowDesc) * nrows, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(b->ctx_dev, b->ctx_host, sizeof(FrameCtx<S>) * n_active, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(b->rows_dev, b->rows_host, sizeof(RowDesc) * nrows, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(b->ctx_dev, b->ctx_host, sizeof(FrameCtx<S>) * n_active, cudaMemcpyDefault, st));
   CK(cudaMemsetAsync(b->sched_dev, 0, sizeof(int) * (2 * (size_t)nrows + CTL_N), st));
   b->ctl_host[CTL_REMAINING] = nsb_total; b->ctl_host[CTL_ERROR] = 0; b->ctl_host[2] = b->ctl_host[3] = 0;
-  CK(cudaMemcpyAsync(b->sched_dev + 2 * (size_t)nrows, b->ctl_host, sizeof(int) * CTL_N, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(b->sched_dev + 2 * (size_t)nrows, b->ctl_host, sizeof(int) * CTL_N, cudaMemcpyDefault, st));
   CK(cudaMemsetAsync(b->prof, 0, sizeof(unsigned long long) * ST_END, st));
   rdo_batch_kernel<S><<<grid, 32 * RDO_WARPS, smem, st>>>((const FrameCtx<S> *)b->ctx_dev, b->rows_dev, nrows, (Work<S> *)b->works, b->sched_dev, b->sched_dev + nrows,
                                                          b->sched_dev + 2 * (size_t)nrows, b->prof);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(b->ctl_host, b->sched_dev + 2 * (size_t)nrows, sizeof(int) * CTL_N, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->ctl_host, b->sched_dev + 2 * (size_t)nrows, sizeof(int) * CTL_N, cudaMemcpyDefault, st));
   return TB_OK;
 }
 
@@ -693,10 +708,10 @@ int tb_rdo_batch_upload(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f) {
   // uploads: source (visible area), references (whole padded planes: one contiguous copy each)
   for (int p = 0; p < 3; p++)
     CK(cudaMemcpy2DAsync((char *)D.org[p] + (p ? oc : oy), (size_t)(p ? D.sc : D.sy) * esz, f->orig[p], (size_t)f->orig_stride[p ? 1 : 0] * esz, (size_t)(p ? w >> 1 : w) * esz,
-                         p ? h >> 1 : h, cudaMemcpyHostToDevice, st));
+                         p ? h >> 1 : h, cudaMemcpyDefault, st));
   for (int r = 0; r < f->num_ref; r++)
     for (int p = 0; p < 3; p++)
-      CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(D.ref[r][p], (const char *)f->ref[r][p] - (p ? oc : oy), p ? ref_c_bytes : ref_y_bytes, cudaMemcpyDefault, st));
   D.used = 1;
   return TB_OK;
 }
@@ -723,11 +738,11 @@ int tb_rdo_batch_download(tb_rdo_batch_t *b, int slot, const tb_rdo_frame_t *f) 
   for (int p = 0; p < 3; p++)
     if (f->rec[p])
       CK(cudaMemcpy2DAsync(f->rec[p], (size_t)f->rec_stride[p ? 1 : 0] * esz, (const char *)D.rec[p] + (p ? oc : oy), (size_t)(p ? D.sc : D.sy) * esz, (size_t)(p ? w >> 1 : w) * esz,
-                           p ? h >> 1 : h, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->blk, D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDeviceToHost, st));
+                           p ? h >> 1 : h, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(f->blk, D.blk, sizeof(tb_rdo_blk_t) * (size_t)(h / 4) * (w / 4), cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(f->leaves, D.leaves, sizeof(tb_rdo_leaf_t) * (size_t)nsb * TB_RDO_MAX_LEAVES, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(f->leaf_count, D.leaf_count, sizeof(int) * nsb, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(f->coeffs, D.coeffs, sizeof(int16_t) * (size_t)nsb * TB_RDO_SB_COEFFS, cudaMemcpyDefault, st));
   return TB_OK;
 }
 
@@ -741,6 +756,19 @@ int tb_rdo_batch_sync(tb_rdo_batch_t *b) {
     static const char *names[PF_N] = {"interp", "me", "me_bi", "tx_chain", "coeff_bits", "ssd_sad", "intra", "copy_avg", "early_skip", "idle", "total"};
     fprintf(stderr, "[tb_rdo prof] %d rows on %d CTAs x %d warps:", b->nrows, b->grid, RDO_WARPS);
     for (int k = 0; k < PF_N; k++) fprintf(stderr, " %s %.1f%%", names[k], 100.0 * (double)pr[k] / (double)(pr[PF_TOTAL] ? pr[PF_TOTAL] : 1));
+    {
+      static const char *ph[tbr::PH_N] = {"other", "early_skip", "skip_merge_cand", "search", "inter_cand", "bipred", "intra_search", "intra_cand", "commit"};
+      unsigned long long tot = 0;
+      for (int k = 0; k < tbr::PH_N; k++) tot += pr[ST_PH + k];
+      fprintf(stderr, "\n[tb_rdo prof] wall time of a super block by decision phase (warp 0):");
+      for (int k = 0; k < tbr::PH_N; k++) fprintf(stderr, " %s %.1f%%", ph[k], 100.0 * (double)pr[ST_PH + k] / (double)(tot ? tot : 1));
+    }
+    fprintf(stderr, "\n[tb_rdo prof] search cycles by coding-block size 8..128:");
+    for (int k = 0; k < 5; k++) fprintf(stderr, " %.1f%%", 100.0 * (double)pr[ST_ME_SZ + k] / (double)(pr[PF_ME] ? pr[PF_ME] : 1));
+    fprintf(stderr, "; transform chains by size 4..128:");
+    for (int k = 0; k < 6; k++) fprintf(stderr, " %.1f%%", 100.0 * (double)pr[ST_TX_SZ + k] / (double)(pr[PF_TX] ? pr[PF_TX] : 1));
+    fprintf(stderr, "; predictions by size 4..128:");
+    for (int k = 0; k < 6; k++) fprintf(stderr, " %.1f%%", 100.0 * (double)pr[ST_IP_SZ + k] / (double)(pr[PF_INTERP] ? pr[PF_INTERP] : 1));
     fprintf(stderr, "\n");
   }
   if (b->ctl_host && (b->ctl_host[CTL_ERROR] || b->ctl_host[CTL_REMAINING] != 0)) {

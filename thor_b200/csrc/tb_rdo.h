@@ -35,6 +35,8 @@ enum { MODE_SKIP = 0, MODE_INTRA, MODE_INTER, MODE_BIPRED, MODE_MERGE };
 enum { PART_NONE = 0, PART_HOR, PART_VER, PART_QUAD };
 enum { I_FRAME = 0, P_FRAME, B_FRAME };
 enum { MIN_BLOCK = 8, MIN_PB = 4, MAX_TR = 128, EARLY_SKIP_BLOCK = 32 };
+// phases of one block decision for the device's timers (be.mark(k): the time since the previous mark belongs to phase k)
+enum { PH_OTHER = 0, PH_EARLY_SKIP, PH_SKIP_MERGE, PH_SEARCH, PH_INTER_CAND, PH_BIPRED, PH_INTRA_SEARCH, PH_INTRA_CAND, PH_COMMIT, PH_N };
 constexpr uint32_t MAX_U32 = 1u << 31;  // MAX_UINT32 of common/global.h:62 (sic: 1<<31)
 
 typedef tb_mv_t Mv;
@@ -687,6 +689,7 @@ template <class S, class B> struct Rdo {
     if ((size < 128 || F.speed == 0) && !rectangular && size <= MAX_TR) {
       if (F.frame_type != I_FRAME) {
         t.tb_param = 0;
+        be.mark(PH_OTHER);
         for (int k = 0; k < bi.num_merge; k++) {
           set_from_ipred(t, bi.merge_cand[k], k);
           t.mode = MODE_MERGE;
@@ -704,6 +707,7 @@ template <class S, class B> struct Rdo {
         Mv mv_all[TB_RDO_MAX_REF][4][4], mv_center[TB_RDO_MAX_REF], mvp;
         uint32_t sad_inter_r[TB_RDO_MAX_REF];
         const S *oy = F.org[0] + ypos * F.org_stride[0] + xpos;
+        be.mark(PH_SKIP_MERGE);
         mvp = get_mv_pred(ypos, xpos, size, size);  // the same for every reference (its ref_idx argument is unused, inter_prediction.c:413)
         bi.mvp = mvp;
         // (1) the searches: reference ref_idx on warp (ref_idx - min_idx) mod NW.  A reference's searches only read and extend ITS candidate list
@@ -733,6 +737,7 @@ template <class S, class B> struct Rdo {
           mv_center[ref_idx] = mv_all[ref_idx][0][0];
         }
         be.cta_sync();
+        be.mark(PH_SEARCH);
         // (3) the RD candidates of every reference
         for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
           t.ref_idx0 = t.ref_idx1 = ref_idx;
@@ -758,6 +763,7 @@ template <class S, class B> struct Rdo {
           be.reduce_range(&worst_cost, &best_cost);
           if (worst_cost && (uint64_t)worst_cost * 3 > (uint64_t)best_cost * 4) best_ref = 0;  // best_ref_idx is never updated in the reference (:1868, :2019)
         }
+        be.mark(PH_INTER_CAND);
 
         if (F.num_ref > 1 && F.enable_bipred && do_inter) {
           int r0, r1;
@@ -777,6 +783,7 @@ template <class S, class B> struct Rdo {
           }
         }
       }
+      be.mark(PH_BIPRED);
       if (do_intra) {
         t.mode = MODE_INTRA;
         if (F.intra_rdo) {
@@ -798,10 +805,13 @@ template <class S, class B> struct Rdo {
         } else
           search_intra(bi, &intra_mode);
         t.intra_mode = intra_mode;
+        be.mark(PH_INTRA_SEARCH);
         for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; t.mode = MODE_INTRA; try_cand(bi, t, size, size); }
       }
     }
-    return cand_group_end(bi, owner);
+    const uint32_t cost_ = cand_group_end(bi, owner);
+    be.mark(PH_INTRA_CAND);
+    return cost_;
   }
 
   // ---------------------------------------------------------------------------------------------------------------
@@ -957,8 +967,12 @@ template <class S, class B> struct Rdo {
         if (f.encode_this && F.frame_type != I_FRAME && F.early_skip_thr > 0.0f) {
           uint32_t cost;
           int owner;
-          if (search_early_skip(bi, &cost, &owner)) {
+          be.mark(PH_OTHER);
+          const int es = search_early_skip(bi, &cost, &owner);
+          be.mark(PH_EARLY_SKIP);
+          if (es) {
             commit_block(bi, cost, owner, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
+            be.mark(PH_COMMIT);
             ret = cost; have_ret = true; sp--; continue;
           }
         }
@@ -999,8 +1013,10 @@ template <class S, class B> struct Rdo {
       if ((f.encode_this || f.encode_rect) && f.cost <= f.cost_small) {
         n_leaves = f.leaf_start; coeff_used = f.coeff_start;  // the children's blocks are replaced
         const bool from_td = f.top_down && f.child == 4;      // the children ran after this block's decision
+        be.mark(PH_OTHER);
         if (from_td) commit_block(f.bi, f.cost, 0, W0.td_y, W0.td_u, W0.td_v, W0.tdq_y, W0.tdq_u, W0.tdq_v);
         else commit_block(f.bi, f.cost, f.owner, W.best_y, W.best_u, W.best_v, W.bq_y, W.bq_u, W.bq_v);
+        be.mark(PH_COMMIT);
       }
       ret = f.cost < f.cost_small ? f.cost : f.cost_small; have_ret = true; sp--;
     }

@@ -19,6 +19,10 @@
  * reference planes) together with the reference's RESULT (reconstruction before the in-loop filters, per-4x4 block state, process_block's
  * return value per super block) to <dir>/frame_NNN.job — the workload and the expected answers of bench.py and tests/test_gpu_rdo_batch.py.
  *
+ * TB_RDO_PROGRESS=<file> (capture link): the file is mapped and updated after every super block with { uint64 pixels decided, double seconds
+ * inside process_block, uint64 frames finished } — bench.py's CPU arm reads it to measure the throughput of long-running reference encoders in
+ * fixed wall-clock slices without waiting for them to finish.
+ *
  * TB_RDO_VERIFY=1 (needs the per-super-block entry of oracle/librdo_hostcheck.so, TEST INFRASTRUCTURE): every super block is decided by
  * tb_rdo_encode_sb() AND by the reference's own process_block() on the same state; bits, reconstruction and deblock_data are compared
  * and the reference's result is kept.  That is how the control flow of tb_rdo.h is pinned against the reference in this container.
@@ -27,6 +31,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
 #include "global.h"
 #include "mainenc.h"
 #include "encode_block.h"
@@ -55,6 +62,7 @@ static struct {
   double t_rdo, t_emit, t_ref;
   int32_t *sb_cost; /* capture: process_block's return value per super block */
   FILE *dump;
+  volatile struct { uint64_t pixels; double t_rd; uint64_t frames; } *progress;
 } G;
 
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
@@ -90,6 +98,13 @@ static void ensure_buffers(int w, int h, int log2sb) {
     G.inited = 1;
     G.verify = getenv("TB_RDO_VERIFY") != NULL;
     atexit(shim_report);
+    if (getenv("TB_RDO_PROGRESS")) {
+      const int fd = open(getenv("TB_RDO_PROGRESS"), O_RDWR | O_CREAT, 0644);
+      if (fd < 0 || ftruncate(fd, 64) != 0) { fprintf(stderr, "[tb_rdo_shim] cannot open TB_RDO_PROGRESS file\n"); exit(2); }
+      G.progress = mmap(NULL, 64, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (G.progress == MAP_FAILED) { fprintf(stderr, "[tb_rdo_shim] cannot map TB_RDO_PROGRESS file\n"); exit(2); }
+      close(fd);
+    }
   }
 }
 
@@ -256,6 +271,11 @@ static int wrap_process_block(encoder_info_t *e, int size, int ypos, int xpos, i
     G.t_ref += now_s() - t0;
     G.sb_cost[sbi] = ret;
     if (xpos == 0 && ypos == 0) G.frames_host++;
+    if (G.progress) {
+      G.progress->pixels += (uint64_t)(x1 - xpos) * (uint64_t)(y1 - ypos);
+      G.progress->t_rd = G.t_ref;
+      if (x1 == e->width && y1 == e->height) G.progress->frames += 1;
+    }
     if (dumping && G.dump && x1 == e->width && y1 == e->height) capture_end(e, &f, esz);
     return ret;
   }
