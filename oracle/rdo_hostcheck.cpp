@@ -63,6 +63,7 @@ struct Exchange {
   Mv mv[TB_RDO_MAX_REF][16];
   uint32_t sad[TB_RDO_MAX_REF];
   unsigned char buf[256];
+  int queue[4] = {0, 0, 0, 0};
   // The oracle's functions keep static scratch buffers (not re-entrant), so the simulated warps never run at the same time: a thread
   // holds `run` while it executes and gives it up only while it waits at a barrier.  The interleaving is arbitrary, the semantics are
   // those of warps that only communicate at CTA barriers.
@@ -89,6 +90,15 @@ template <class S> struct OracleBackend {
   bool mine(int k) const { return (k % X->nw) == wid; }
   void cta_sync() const { X->barrier(); }
   void mark(int) const {}  // phase timers exist only on the device
+  int nwarps() const { return X->nw; }
+  void queue_reset() const { X->barrier(); if (wid == 0) for (int q = 0; q < 4; q++) X->queue[q] = 0; X->barrier(); }
+  // shared counters; the simulated warp gives the others a chance to run at every draw, so the distribution of the items varies from run to run
+  int next(int q) const {
+    const int v = X->queue[q]++;
+    if (X->nw > 1) { X->run.unlock(); std::this_thread::yield(); X->run.lock(); }
+    return v;
+  }
+  void copy_words(void *dst, const void *src, int nwords) const { memcpy(dst, src, (size_t)nwords * 4); }
   void put_me(int ref, const Mv *mv16, uint32_t sad) const { memcpy(X->mv[ref], mv16, 16 * sizeof(Mv)); X->sad[ref] = sad; }
   void get_me(int ref, Mv *mv16, uint32_t *sad) const { memcpy(mv16, X->mv[ref], 16 * sizeof(Mv)); *sad = X->sad[ref]; }
   int reduce_best(uint32_t *cost, int *idx) const {
@@ -156,6 +166,10 @@ template <class S> struct OracleBackend {
     else Orc<S>::ipred(left, top, tl, ypos + i, xpos + j, size, dst, ds, mode, F->bitdepth);
   }
   void cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride) const { Orc<S>::cfl(y, u, v, ry, n, cstride, stride, 1, F->bitdepth); }
+  void tx_multi(const tbr::TxJob<S> *jobs, int n, int *bit) {  // the device runs these side by side; here one after the other
+    for (int k = 0; k < n; k++)
+      bit[k] = tx_chain(jobs[k].orig, jobs[k].os, jobs[k].pred, jobs[k].ps, jobs[k].rec, jobs[k].rs, jobs[k].cq, jobs[k].size, jobs[k].qp, jobs[k].coeff_type, jobs[k].fast);
+  }
   int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) {
     Orc<S>::residual(block, pred, orig, size, ps, os);
     orc_transform(block, coeff, size, fast, F->bitdepth);

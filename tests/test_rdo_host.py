@@ -62,3 +62,18 @@ def test_whole_encode_through_the_c_abi_is_bit_exact(tmp_path, name, flags, w, h
     assert "frames decided by tb_rdo_encode_frame: %d," % n in err, err[-500:]
     assert bit == bit_ref, "bitstream differs"
     assert rec == rec_ref, "reconstruction differs"
+
+
+@needs
+@pytest.mark.parametrize("nw", [3, 8])
+def test_overlapped_decision_with_simulated_warps(tmp_path, nw):
+    """The device runs the control flow SPMD over the warps of a CTA; with more than one warp mode_decision_rdo overlaps the bi-prediction chain, the
+    inter candidates and the intra-mode search (shared work counters).  Host threads stand in for the warps (TBR_HOST_WARPS): every super block must
+    still equal the reference's process_block, whichever warp evaluated which candidate."""
+    name, flags, w, h, n, extra = CASES[0]
+    tmp = str(tmp_path)
+    synth_yuv(os.path.join(tmp, "in.yuv"), w, h, n, 8)
+    _, _, err = enc("Thorenc_rdocheck", flags, w, h, n, "chk", tmp, extra, {"TB_RDO_VERIFY": "1", "TB_RDO_VERBOSE": "1", "TBR_HOST_WARPS": str(nw)})
+    m = re.search(r"verify: (\d+) super blocks compared with the reference's process_block, (\d+) differ", err)
+    assert m, err[-1500:]
+    assert int(m.group(1)) == ((w + 127) // 128) * ((h + 127) // 128) * n and int(m.group(2)) == 0, err[-3000:]

@@ -65,6 +65,7 @@ struct RdoCta {
   tb_mv_t x_mv[TB_RDO_MAX_REF][16];
   uint32_t x_sad[TB_RDO_MAX_REF];
   alignas(16) int x_buf[32];
+  int x_queue[4];
   int sel;
 };
 // per-warp scratch
@@ -88,6 +89,22 @@ template <class S> struct DevBackend {
   __device__ __forceinline__ int warp() const { return wid; }
   __device__ __forceinline__ bool mine(int k) const { return (k % nw) == wid; }
   __device__ void cta_sync() const { __threadfence(); __syncthreads(); }
+  __device__ __forceinline__ int nwarps() const { return nw; }
+  __device__ void queue_reset() const {
+    __syncthreads();
+    if (threadIdx.x < 4) cta->x_queue[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  __device__ int next(int q) const {  // shared counter: every lane of the warp receives the drawn value
+    int v = 0;
+    if ((threadIdx.x & 31) == 0) v = atomicAdd(&cta->x_queue[q], 1);
+    return __shfl_sync(FULL, v, 0);
+  }
+  __device__ void copy_words(void *dst, const void *src, int nwords) const {
+    __syncwarp();
+    for (int k = threadIdx.x & 31; k < nwords; k += 32) ((int *)dst)[k] = ((const int *)src)[k];
+    __syncwarp();
+  }
   __device__ __forceinline__ void mark(int k) const {
     if (wid == 0 && (threadIdx.x & 31) == 0) { const long long t = clock64(); sh->prof[ST_PH + k] += t - sh->t_mark; sh->t_mark = t; }
   }
@@ -259,6 +276,30 @@ template <class S> struct DevBackend {
     }
     sync();
     return cbp;
+  }
+  // <= 12 chains of 4x4 / 8x8 transform blocks, chain k on lane k (thread_txfm4 in registers, thread_txfm8 in local arrays); bit[k] = its cbp
+  __device__ void tx_multi(const tbr::TxJob<S> *jobs, int n, int *bit) const {
+    PROF2(PF_TX, ST_TX_SZ + ilog2(jobs[0].size) - 2);
+    if (lane() == 0)
+      for (int k = 0; k < n; k++) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * jobs[k].size * jobs[k].size; }
+    sync();
+    const int l = lane();
+    int cbp = 0;
+    if (l < n) {
+      const tbr::TxJob<S> q = jobs[l];
+      uint64_t ssd;
+      int bits;
+      if (q.size == 8) cbp = thread_txfm8<S>(q.orig, q.os, q.pred, q.ps, q.rec, q.rs, q.cq, q.qp, q.coeff_type, F->bitdepth, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
+    }
+    if (l < n) {
+      const tbr::TxJob<S> q = jobs[l];
+      uint64_t ssd;
+      int bits;
+      if (q.size == 4) cbp = thread_txfm4<S>(q.orig, q.os, q.pred, q.ps, q.rec, q.rs, q.cq, q.qp, q.coeff_type, F->bitdepth, ssd, 0, bits);
+    }
+    sync();
+    for (int k = 0; k < n; k++) bit[k] = __shfl_sync(FULL, cbp, k);
+    sync();
   }
   __device__ int coeff_bits(const int16_t *cq, int size, int type) const {
     PROF(PF_BITS);

@@ -23,6 +23,9 @@
 #include <stdint.h>
 #include "../../include/thor_b200.h"
 
+#ifndef TBR_NO_OVERLAP
+#define TBR_NO_OVERLAP 0  // 1: every block through the serial form of mode_decision_rdo (A/B)
+#endif
 #ifdef __CUDACC__
 #define TBR_HD __device__  // under nvcc the header is only instantiated for the device backend
 #else
@@ -127,6 +130,12 @@ struct Cand {
   int ref_idx0, ref_idx1, dir;
   int cbp_y, cbp_u, cbp_v;
   int tb_param, tb_split;
+};
+// one transform chain of a candidate (residual -> DCT -> quant -> dequant -> inverse DCT -> reconstruction): the chains of a candidate's planes and
+// transform blocks are independent of each other when the predictions are complete, so the backend may run them side by side (tx_multi)
+template <class S> struct TxJob {
+  const S *orig; const S *pred; S *rec; int16_t *cq;
+  int os, ps, rs, size, qp, coeff_type, fast;
 };
 // block_info_t
 struct BlockInfo {
@@ -412,6 +421,30 @@ template <class S, class B> struct Rdo {
     const int fast = ((size == 64 && F.speed > 0) || F.speed > 1) ? 1 : 0;
     return be.tx_chain(orig, os, pred, size, rec, size, cq, size, qp, coeff_type, fast);
   }
+  // the chains of enc_rec_inter for one plane, appended to a job list (same order, same fast flags); returns the number of chains
+  TBR_HD int inter_jobs(TxJob<S> *jobs, const S *orig, int os, int size, int qp, const S *pred, int16_t *cq, S *rec, int coeff_type, int tb_split) const {
+    if (tb_split) {
+      const int s2 = size / 2;
+      int n = 0;
+      for (int i = 0; i < size; i += s2)
+        for (int j = 0; j < size; j += s2) {
+          TxJob<S> &q = jobs[n];
+          q.orig = orig + i * os + j; q.os = os; q.pred = pred + i * size + j; q.ps = size; q.rec = rec + i * size + j; q.rs = size; q.cq = cq + 256 * n; q.size = s2; q.qp = qp;
+          q.coeff_type = coeff_type; q.fast = (size == 64 || F.speed > 1) ? 1 : 0;
+          n++;
+        }
+      return 4;
+    }
+    TxJob<S> &q = jobs[0];
+    q.orig = orig; q.os = os; q.pred = pred; q.ps = size; q.rec = rec; q.rs = size; q.cq = cq; q.size = size; q.qp = qp; q.coeff_type = coeff_type;
+    q.fast = ((size == 64 && F.speed > 0) || F.speed > 1) ? 1 : 0;
+    return 1;
+  }
+  TBR_HD static int join_cbp(const int *bit, int n) {
+    int cbp = 0;
+    for (int k = 0; k < n; k++) cbp = (cbp << 1) + bit[k];
+    return cbp;
+  }
   // encode_and_reconstruct_block_intra :1100-1168 (luma) — prediction into pblock (pitch size), reconstruction into rec_block (pitch size)
   TBR_HD int enc_rec_intra(const S *orig, int os, S *recf, int rfs, int ypos, int xpos, int size, int qp, S *pblock, int16_t *cq, S *rec_block, int coeff_type,
                            int tb_split, int intra_mode, int upright, int downleft) {
@@ -431,6 +464,21 @@ template <class S, class B> struct Rdo {
     be.intra_predict(pblock, size, recf, rfs, (const S *)nullptr, 0, 0, 0, ypos, xpos, size, upright, downleft, 0, intra_mode);
     return be.tx_chain(orig, os, pblock, size, rec_block, size, cq, size, qp, coeff_type, fast);
   }
+  // the U and the V chain of one transform block: independent, side by side when they are thread-sized (<= 8x8)
+  TBR_HD void uv_chains(const S *ou, const S *ov, int os, const S *pu, const S *pv, int ps, S *ru, S *rv, int rs, int16_t *cqu, int16_t *cqv, int size, int qp, int coeff_type,
+                        int fast, int *bu, int *bv) {
+    if (size <= 8) {
+      TxJob<S> jobs[2];
+      int bit[2];
+      jobs[0].orig = ou; jobs[0].pred = pu; jobs[0].rec = ru; jobs[0].cq = cqu; jobs[1].orig = ov; jobs[1].pred = pv; jobs[1].rec = rv; jobs[1].cq = cqv;
+      for (int k = 0; k < 2; k++) { jobs[k].os = os; jobs[k].ps = ps; jobs[k].rs = rs; jobs[k].size = size; jobs[k].qp = qp; jobs[k].coeff_type = coeff_type; jobs[k].fast = fast; }
+      be.tx_multi(jobs, 2, bit);
+      *bu = bit[0]; *bv = bit[1];
+    } else {
+      *bu = be.tx_chain(ou, os, pu, ps, ru, rs, cqu, size, qp, coeff_type, fast);
+      *bv = be.tx_chain(ov, os, pv, ps, rv, rs, cqv, size, qp, coeff_type, fast);
+    }
+  }
   // encode_and_reconstruct_block_intra_uv :1170-1273; returns (cbp_u << 8) | cbp_v
   TBR_HD int enc_rec_intra_uv(const S *ou, const S *ov, int os, S *ru, S *rv, int rfs, int ypos, int xpos, int size, int qp, S *pu, S *pv, int16_t *cqu, int16_t *cqv,
                               S *rbu, S *rbv, int coeff_type, int tb_split, int intra_mode, int upright, int downleft, const S *pblock_y, const S *rec_y,
@@ -445,18 +493,18 @@ template <class S, class B> struct Rdo {
           be.intra_predict(pu + i * size + j, size, ru, rfs, rbu + i * size + j, size, i, j, ypos, xpos, s2, upright, downleft, 1, intra_mode);
           be.intra_predict(pv + i * size + j, size, rv, rfs, rbv + i * size + j, size, i, j, ypos, xpos, s2, upright, downleft, 1, intra_mode);
           if (pblock_y) be.cfl(pblock_y + i * size + j, pu + i * size + j, pv + i * size + j, rec_y + (i << 1) * rec_stride2 + (j << 1), s2 << 1, size << 1, rec_stride2);
-          int bit = be.tx_chain(ou + i * os + j, os, pu + i * size + j, size, rbu + i * size + j, size, cqu + index, s2, qp, coeff_type, fast);
-          cbp_u = (cbp_u << 1) + bit;
-          bit = be.tx_chain(ov + i * os + j, os, pv + i * size + j, size, rbv + i * size + j, size, cqv + index, s2, qp, coeff_type, fast);
-          cbp_v = (cbp_v << 1) + bit;
+          int bu, bv;
+          uv_chains(ou + i * os + j, ov + i * os + j, os, pu + i * size + j, pv + i * size + j, size, rbu + i * size + j, rbv + i * size + j, size, cqu + index, cqv + index, s2, qp,
+                    coeff_type, fast, &bu, &bv);
+          cbp_u = (cbp_u << 1) + bu;
+          cbp_v = (cbp_v << 1) + bv;
           index += 256;
         }
     } else {
       be.intra_predict(pu, size, ru, rfs, (const S *)nullptr, 0, 0, 0, ypos, xpos, size, upright, downleft, 0, intra_mode);
       be.intra_predict(pv, size, rv, rfs, (const S *)nullptr, 0, 0, 0, ypos, xpos, size, upright, downleft, 0, intra_mode);
       if (pblock_y) be.cfl(pblock_y, pu, pv, rec_y, size << 1, size << 1, rec_stride2);
-      cbp_u = be.tx_chain(ou, os, pu, size, rbu, size, cqu, size, qp, coeff_type, fast);
-      cbp_v = be.tx_chain(ov, os, pv, size, rbv, size, cqv, size, qp, coeff_type, fast);
+      uv_chains(ou, ov, os, pu, pv, size, rbu, rbv, size, cqu, cqv, size, qp, coeff_type, fast, &cbp_u, &cbp_v);
     }
     return (cbp_u << 8) | cbp_v;
   }
@@ -486,10 +534,27 @@ template <class S, class B> struct Rdo {
         be.copy(W.rec_v, sizeC, W.p_v, sizeC, sizeC, sizeC);
         c.cbp_y = c.cbp_u = c.cbp_v = 0;
       } else {
-        c.cbp_y = enc_rec_inter(oy, F.org_stride[0], size, F.qp, W.p_y, W.cq_y, W.rec_y, itype | 0, tb_split);
-        if (F.cfl_inter) be.cfl(W.p_y, W.p_u, W.p_v, W.rec_y, size, size, size);
-        c.cbp_u = enc_rec_inter(ou, F.org_stride[1], sizeC, F.qpc, W.p_u, W.cq_u, W.rec_u, itype | 1, tb_split && sizeC > 4);
-        c.cbp_v = enc_rec_inter(ov, F.org_stride[1], sizeC, F.qpc, W.p_v, W.cq_v, W.rec_v, itype | 1, tb_split && sizeC > 4);
+        if (!F.cfl_inter && sizeC <= 8) {
+          // small blocks: the chains of the three planes (<= 12 of 4x4 / 8x8, one thread each on the device) side by side; a 16x16 luma block goes first, alone
+          TxJob<S> jobs[12];
+          int bit[12], n = 0, ny = 0;
+          const int tbc = tb_split && sizeC > 4;
+          if (size == 16 && !tb_split) c.cbp_y = enc_rec_inter(oy, F.org_stride[0], size, F.qp, W.p_y, W.cq_y, W.rec_y, itype | 0, 0);
+          else { ny = inter_jobs(jobs, oy, F.org_stride[0], size, F.qp, W.p_y, W.cq_y, W.rec_y, itype | 0, tb_split); n = ny; }
+          const int nu = inter_jobs(jobs + n, ou, F.org_stride[1], sizeC, F.qpc, W.p_u, W.cq_u, W.rec_u, itype | 1, tbc);
+          n += nu;
+          const int nv = inter_jobs(jobs + n, ov, F.org_stride[1], sizeC, F.qpc, W.p_v, W.cq_v, W.rec_v, itype | 1, tbc);
+          n += nv;
+          be.tx_multi(jobs, n, bit);
+          if (ny) c.cbp_y = join_cbp(bit, ny);
+          c.cbp_u = join_cbp(bit + ny, nu);
+          c.cbp_v = join_cbp(bit + ny + nu, nv);
+        } else {
+          c.cbp_y = enc_rec_inter(oy, F.org_stride[0], size, F.qp, W.p_y, W.cq_y, W.rec_y, itype | 0, tb_split);
+          if (F.cfl_inter) be.cfl(W.p_y, W.p_u, W.p_v, W.rec_y, size, size, size);
+          c.cbp_u = enc_rec_inter(ou, F.org_stride[1], sizeC, F.qpc, W.p_u, W.cq_u, W.rec_u, itype | 1, tb_split && sizeC > 4);
+          c.cbp_v = enc_rec_inter(ov, F.org_stride[1], sizeC, F.qpc, W.p_v, W.cq_v, W.rec_v, itype | 1, tb_split && sizeC > 4);
+        }
       }
     }
     return block_bits(bi, c, W.cq_y, W.cq_u, W.cq_v);
@@ -666,7 +731,7 @@ template <class S, class B> struct Rdo {
     c.skip_idx = idx; c.ref_idx0 = p.ref_idx0; c.ref_idx1 = p.ref_idx1; c.mv0[0] = p.mv0; c.mv1[0] = p.mv1; c.dir = p.bipred_flag;
   }
 
-  TBR_HD uint32_t mode_decision_rdo(BlockInfo &bi, int *owner) {
+  TBR_HD uint32_t mode_decision_serial(BlockInfo &bi, int *owner) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos;
     const int rectangular = bi.bwidth != size || bi.bheight != size;
     const int intra_inter_sad = F.speed > 0;
@@ -812,6 +877,166 @@ template <class S, class B> struct Rdo {
     const uint32_t cost_ = cand_group_end(bi, owner);
     be.mark(PH_INTRA_CAND);
     return cost_;
+  }
+
+
+  // candidate `idx` (its position in the reference's evaluation order) evaluated by whichever warp calls this; the warp keeps its best (cost, idx)
+  TBR_HD void eval_cand(BlockInfo &bi, Cand &c, int w, int h, int idx, bool track_range) {
+    const int nbits = encode_block(bi, c);
+    const uint32_t cost = cost_calc(bi, w, h, nbits);
+    if (track_range) { loc_worst = loc_worst > cost ? loc_worst : cost; loc_bestc = loc_bestc < cost ? loc_bestc : cost; }
+    if (cost < loc_cost || (cost == loc_cost && idx < loc_idx)) { loc_cost = cost; loc_idx = idx; copy_best(bi, c); }
+  }
+  // one item of the intra-mode search (:2080-2097 with intra_rdo, else search_intra_prediction_params): the warp keeps its best (cost, k)
+  TBR_HD void intra_search_item(BlockInfo &bi, Cand &t, int k, uint32_t *best_cost, int *best_k) {
+    if (F.intra_rdo) {
+      t.intra_mode = k / bi.max_tb; t.tb_param = k % bi.max_tb; t.mode = MODE_INTRA;
+      const int nbits = encode_block(bi, t);
+      const uint32_t cost = cost_calc(bi, bi.size, bi.size, nbits);
+      if (cost < *best_cost || (cost == *best_cost && k < *best_k)) { *best_cost = cost; *best_k = k; }
+    } else {
+      int mode;
+      search_intra(bi, &mode);
+      *best_cost = 0; *best_k = mode * bi.max_tb;
+    }
+  }
+
+  // mode_decision_rdo for square blocks of inter frames at encoder_speed 0, with the sections of the decision that do not depend on each other
+  // OVERLAPPED over the warps of the CTA instead of run one after the other:
+  //   while the references' motion searches run (one warp per reference), the remaining warps start the intra-mode search;
+  //   then ONE warp runs the bi-prediction chain (search_bipred_prediction_params: every search depends on the previous one) and evaluates its
+  //   candidates, while the others draw the inter candidates and the rest of the intra-mode search from shared counters.
+  // Every candidate keeps the index it has in the reference's evaluation order, so the winner = min (cost, index) is the reference's
+  // "first candidate with the strictly smallest cost" whichever warp evaluated what.  The candidate lists the chain extends are copied to
+  // the other warps' replicas afterwards.
+  TBR_HD uint32_t mode_decision_overlap(BlockInfo &bi, int *owner) {
+    const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos, nw = be.nwarps();
+    be.queue_reset();
+    cand_group_begin();
+    Cand t;
+    t.mode = MODE_SKIP; t.intra_mode = 0; t.skip_idx = 0; t.pb_part = PART_NONE; t.ref_idx0 = t.ref_idx1 = 0; t.dir = 0; t.cbp_y = t.cbp_u = t.cbp_v = 0; t.tb_param = 0; t.tb_split = 0;
+    for (int i = 0; i < 4; i++) { t.mv0[i].x = t.mv0[i].y = t.mv1[i].x = t.mv1[i].y = 0; }
+    be.mark(PH_OTHER);
+    int idx = 0;
+    for (int k = 0; k < bi.num_skip; k++, idx++) {
+      if (!be.mine(idx)) continue;
+      set_from_ipred(t, bi.skip_cand[k], k);
+      t.mode = MODE_SKIP; t.tb_param = 0; t.pb_part = PART_NONE;
+      eval_cand(bi, t, bi.bwidth, bi.bheight, idx, false);
+    }
+    for (int k = 0; k < bi.num_merge; k++)
+      for (int tb = 0; tb <= bi.max_tb - 1; tb++, idx++) {
+        if (!be.mine(idx)) continue;
+        set_from_ipred(t, bi.merge_cand[k], k);
+        t.mode = MODE_MERGE; t.tb_param = tb; t.pb_part = PART_NONE;
+        eval_cand(bi, t, size, size, idx, false);
+      }
+    be.mark(PH_SKIP_MERGE);
+
+    int min_idx = 0;
+    const int max_idx = F.num_ref - 1;
+    if (F.frame_type == B_FRAME && F.interp_ref > 2) min_idx = 1;
+    const int nrs = max_idx - min_idx + 1;
+    Mv mv_all[TB_RDO_MAX_REF][4][4], mv_center[TB_RDO_MAX_REF], mvp;
+    uint32_t sad_inter_r[TB_RDO_MAX_REF];
+    const S *oy = F.org[0] + ypos * F.org_stride[0] + xpos;
+    mvp = get_mv_pred(ypos, xpos, size, size);
+    bi.mvp = mvp;
+    const int n_isearch = F.intra_rdo ? F.num_intra_modes * bi.max_tb : 1;
+    uint32_t my_icost = MAX_U32;
+    int my_ik = 0x7fffffff;
+    // (1) the searches, one reference per warp; warps without a reference begin the intra-mode search
+    for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
+      if (!be.mine(ref_idx - min_idx)) continue;
+      add_mvcandidate(mvp, ref_idx);
+      const int sign = F.ref_sign[ref_idx];
+      mv_center[ref_idx] = mvp;
+      uint32_t sad_inter = MAX_U32;
+      for (int part = 0; part < bi.max_pb; part++) {
+        const uint32_t sad = (uint32_t)search_inter(oy, F.org_stride[0], ref_idx, bi, mv_center[ref_idx], mvp, mv_all[ref_idx][part], part, sign, ref_idx);
+        for (int i = 0; i < 4; i++) add_mvcandidate(mv_all[ref_idx][part][i], ref_idx);
+        mv_center[ref_idx] = mv_all[ref_idx][0][0];
+        sad_inter = sad_inter < sad ? sad_inter : sad;
+      }
+      sad_inter_r[ref_idx] = sad_inter;
+      be.put_me(ref_idx, &mv_all[ref_idx][0][0], sad_inter);
+    }
+    if (be.warp() >= nrs)
+      for (int k; (k = be.next(1)) < n_isearch;) intra_search_item(bi, t, k, &my_icost, &my_ik);
+    be.cta_sync();
+    for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
+      if (be.mine(ref_idx - min_idx)) continue;
+      be.get_me(ref_idx, &mv_all[ref_idx][0][0], &sad_inter_r[ref_idx]);
+      add_mvcandidate(mvp, ref_idx);
+      for (int part = 0; part < bi.max_pb; part++)
+        for (int i = 0; i < 4; i++) add_mvcandidate(mv_all[ref_idx][part][i], ref_idx);
+      mv_center[ref_idx] = mv_all[ref_idx][0][0];
+    }
+    be.cta_sync();
+    be.mark(PH_SEARCH);
+
+    // (2) the bi-prediction chain on warp 0; inter candidates and the intra-mode search on everybody (warp 0 joins when its chain is done)
+    const int ntb = bi.max_tb + 1;  // tb_param -1 (no residual), 0, .. max_tb - 1 (encoder_speed < 1, :1990)
+    const int n_inter = nrs * bi.max_pb * ntb;
+    const int IDX_INTER = 64, IDX_BIPRED = IDX_INTER + n_inter, IDX_INTRA = IDX_BIPRED + 8;
+    const bool do_bipred = F.num_ref > 1 && F.enable_bipred;
+    if (do_bipred && be.warp() == 0) {
+      int r0, r1;
+      Mv a0[4], a1[4];
+      search_bipred(bi, 0, mv_center, mvp, &r0, &r1, a0, a1, 0);
+      t.pb_part = 0; t.ref_idx0 = r0; t.ref_idx1 = r1; t.dir = 0;
+      for (int i = 0; i < 4; i++) { t.mv0[i] = a0[i]; t.mv1[i] = a1[i]; }
+      t.mode = MODE_BIPRED;
+      for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; eval_cand(bi, t, size, size, IDX_BIPRED + tb, false); }
+      if (F.frame_type == B_FRAME) {
+        search_bipred(bi, 1, mv_center, mvp, &r0, &r1, a0, a1, 1);
+        t.pb_part = PART_NONE; t.ref_idx0 = r0; t.ref_idx1 = r1;
+        for (int i = 0; i < 4; i++) { t.mv0[i] = a0[i]; t.mv1[i] = a1[i]; }
+        t.tb_param = 0; t.mode = MODE_BIPRED;
+        eval_cand(bi, t, size, size, IDX_BIPRED + bi.max_tb, false);
+      }
+      be.mark(PH_BIPRED);
+    }
+    for (int k; (k = be.next(0)) < n_inter;) {
+      const int tb = k % ntb - 1, part = (k / ntb) % bi.max_pb, ref_idx = min_idx + k / (ntb * bi.max_pb);
+      t.ref_idx0 = t.ref_idx1 = ref_idx; t.pb_part = part;
+      for (int i = 0; i < 4; i++) t.mv0[i] = t.mv1[i] = mv_all[ref_idx][part][i];
+      t.mode = MODE_INTER; t.dir = 0; t.tb_param = tb;
+      eval_cand(bi, t, size, size, IDX_INTER + k, true);
+    }
+    be.mark(PH_INTER_CAND);
+    for (int k; (k = be.next(1)) < n_isearch;) intra_search_item(bi, t, k, &my_icost, &my_ik);
+    be.mark(PH_INTRA_SEARCH);
+    {
+      uint32_t worst_cost = loc_worst, best_cost = loc_bestc;
+      be.reduce_range(&worst_cost, &best_cost);
+      if (worst_cost && (uint64_t)worst_cost * 3 > (uint64_t)best_cost * 4) best_ref = 0;
+    }
+    if (do_bipred) {  // warp 0's searches extended (and scribbled on, :873-881) the candidate lists: everybody's replica follows
+      if (be.warp() != 0)
+        for (int r = 0; r < F.num_ref; r++) {
+          be.copy_words(W.mvcand[r], W0.mvcand[r], 64 * (int)sizeof(Mv) / 4);
+          W.mvcand_num[r] = W0.mvcand_num[r]; W.mvcand_mask[r] = W0.mvcand_mask[r];
+        }
+      be.cta_sync();
+    }
+    be.reduce_best(&my_icost, &my_ik);
+    const int intra_mode = my_icost == MAX_U32 ? 0 : my_ik / bi.max_tb;
+    t.intra_mode = intra_mode;
+    for (int tb = 0; tb <= bi.max_tb - 1; tb++) {
+      if (!be.mine(tb)) continue;
+      t.tb_param = tb; t.mode = MODE_INTRA;
+      eval_cand(bi, t, size, size, IDX_INTRA + tb, false);
+    }
+    const uint32_t cost_ = cand_group_end(bi, owner);
+    be.mark(PH_INTRA_CAND);
+    return cost_;
+  }
+
+  TBR_HD uint32_t mode_decision_rdo(BlockInfo &bi, int *owner) {
+    if (F.frame_type != I_FRAME && F.speed == 0 && bi.bwidth == bi.size && bi.bheight == bi.size && bi.size <= MAX_TR && be.nwarps() > 1 && !TBR_NO_OVERLAP)
+      return mode_decision_overlap(bi, owner);
+    return mode_decision_serial(bi, owner);
   }
 
   // ---------------------------------------------------------------------------------------------------------------
