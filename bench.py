@@ -229,7 +229,7 @@ STAT_NAMES = ["cyc_interp", "cyc_me", "cyc_me_bi", "cyc_tx_chain", "cyc_coeff_bi
               "searches", "int_block_sads", "subpel_probes", "search_samples", "predictions", "prediction_samples", "txfm_chains", "txfm_samples", "intra_predictions",
               "intra_samples", "ssd_sad_samples", "super_blocks"] + ["cyc_me_%d" % (8 << k) for k in range(5)] + ["cyc_tx_%d" % (4 << k) for k in range(6)] + \
              ["cyc_ip_%d" % (4 << k) for k in range(6)] + ["ph_" + n for n in ("other", "early_skip", "skip_merge_cand", "search", "inter_cand", "bipred", "intra_search", "intra_cand",
-                                                                               "commit")]
+                                                                               "commit")] + ["me_stage_" + n for n in ("telescope", "candidates", "hexagon", "halfpel", "quarterpel")]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -410,7 +410,7 @@ def run_gpu(args, cfg):
         "metric": cfg.metric(), "value": round(value, 4), "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if cfg.ESZ == 1 else "u16", "data": "synthetic",
         "config": {"workload": cfg.workload(), "frames_per_step": nfr, "steps_in_one_launch": K, "ctas": grid,
-                   "parallelism": ("GOP-per-GPU x%d; rank 0 scatters the raw source frames and gathers the RD costs over NCCL" % world) if world > 1 else "1 GPU, no collective",
+                   "parallelism": ("GOP-per-GPU x%d; rank 0 scatters the raw source frames over NCCL and gathers one int32 per super block from every rank (stand-in payload of the size of the RD costs; the decisions themselves are downloaded to each rank's host)" % world) if world > 1 else "1 GPU, no collective",
                    "l2_policy": "per-launch inputs+outputs %.0f MB > 126 MB L2" % ((h2d + d2h) * K / 1e6)},
         "e2e": {"value": round(e2e_value, 4), "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ems / Ke, 2), "steps": Ke},
         "gpu_launches": launches,
@@ -561,7 +561,7 @@ def main():
     ap.add_argument("--config", default="hdb", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the headline 1080p HDB_high_efficiency)")
     ap.add_argument("--size", default=None, help="WxH override (development: smaller clips)")
     ap.add_argument("--frames", type=int, default=0, help="clip length override")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end launch (0 = --steps)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps (GOPs) of the end-to-end launch: min(--steps, this); 0 = --steps")
     ap.add_argument("--cpu-procs", type=int, default=0, help="CPU arm: concurrent reference encoders (0 = one per host thread)")
     ap.add_argument("--cpu-slice", type=float, default=4.0, help="CPU arm: wall-clock seconds per slice (= one step of --impl reference)")
     ap.add_argument("--cpu-slices", type=int, default=3, help="CPU arm inside the GPU run (cpu_baseline): timed slices")

@@ -308,9 +308,9 @@ int tb_rdo_batch_grid(const tb_rdo_batch_t *b);                                 
  * chain, coefficient bits, SSD/SAD, intra, copies, early skip, idle, total); [11..22] work actually executed (the RD loop is data dependent):
  * searches, integer block SADs, sub-pel probes, search samples ((n_int+1) w h + n_sub ((w+5)(h+5) + w h)), predictions, prediction samples,
  * transform chains, chain samples (3 N^2), intra predictions, intra samples (4N + N^2), SSD/SAD samples (2 w h), super blocks */
-#define TB_RDO_NSTATS 49 /* [23..39]: cycles of searches by coding-block size 8..128 (5), of transform chains by size 4..128 (6), of predictions by size 4..128 (6);
+#define TB_RDO_NSTATS 60 /* [23..39]: cycles of searches by coding-block size 8..128 (5), of transform chains by size 4..128 (6), of predictions by size 4..128 (6);
                             [40..48]: wall cycles of a CTA by decision phase (other, early skip, skip/merge candidates, searches, inter candidates, bipred, intra search,
-                            intra candidates, commit) */
+                            intra candidates, commit); [49..53]: cycles of the searches of blocks <= 16 by stage (telescope, candidates, hexagon, half-pel, quarter-pel) */
 int tb_rdo_batch_stats(const tb_rdo_batch_t *b, uint64_t *out, int n);
 void tb_rdo_batch_destroy(tb_rdo_batch_t *b);
 const char *tb_rdo_last_error(void);

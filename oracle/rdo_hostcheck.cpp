@@ -90,6 +90,7 @@ template <class S> struct OracleBackend {
   bool mine(int k) const { return (k % X->nw) == wid; }
   void cta_sync() const { X->barrier(); }
   void mark(int) const {}  // phase timers exist only on the device
+  void mark2(int) const {}
   int nwarps() const { return X->nw; }
   void queue_reset() const { X->barrier(); if (wid == 0) for (int q = 0; q < 4; q++) X->queue[q] = 0; X->barrier(); }
   // shared counters; the simulated warp gives the others a chance to run at every draw, so the distribution of the items varies from run to run
@@ -191,7 +192,7 @@ template <class S> struct OracleBackend {
     return Orc<S>::me(compact, ref, size, rs, w, h, (orc_mv_t *)mv, (const orc_mv_t *)&mvc, (const orc_mv_t *)&mvp, lambda, F->speed, F->bitdepth, sign, F->width, F->height, xpos,
                       ypos, (const orc_mv_t *)cand, ncand, F->enable_bipred);
   }
-  int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand, int ncand) {
+  int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand, int ncand, S *, S *) {
     for (int i = 0; i < size; i++) memcpy(compact + i * size, org + i * os, (size_t)size * sizeof(S));
     return Orc<S>::me_bi(compact, ref0, ref1, size, rs, size, size, (orc_mv_t *)mv, (const orc_mv_t *)&mvc, (const orc_mv_t *)&mvp, lambda, F->bitdepth, sign, F->width, F->height,
                          xpos, ypos, (const orc_mv_t *)cand, ncand, 1);

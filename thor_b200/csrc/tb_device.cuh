@@ -51,6 +51,9 @@
 #ifndef TB_SAD_ROWS
 #define TB_SAD_ROWS 0
 #endif
+#ifndef TB_ME_STAGE_PROF
+#define TB_ME_STAGE_PROF 0
+#endif
 #ifndef TB_LDG
 #define TB_LDG(p) __ldg(p)
 #endif
@@ -961,7 +964,17 @@ struct MeCtx {
   // work counters for the roofline (not part of the result): integer-position block SADs and sub-pel probes
   unsigned n_int, n_sub;
   SubpelShared *sps;  // per-warp scratch of the shared-row sub-pel stage (8-bit samples)
+#if TB_ME_STAGE_PROF
+  long long cyc[5];   // cycles in telescope / candidates / hexagon / half-pel / quarter-pel (diagnostics of the RD loop)
+#endif
 };
+#if TB_ME_STAGE_PROF
+#define ME_STAGE_T0() long long me_t__ = clock64()
+#define ME_STAGE(k) do { const long long n__ = clock64(); c.cyc[k] += n__ - me_t__; me_t__ = n__; } while (0)
+#else
+#define ME_STAGE_T0() do {} while (0)
+#define ME_STAGE(k) do {} while (0)
+#endif
 
 // first-minimum over lanes < n of key (cost); returns winning lane (or -1 if n == 0) and its cost
 __device__ __forceinline__ int warp_first_min(uint32_t cost, int n, uint32_t &best) {
@@ -1004,6 +1017,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
   refx = (int)(int16_t)refx;
   refy = (int)(int16_t)refy;
 
+  ME_STAGE_T0();
   // ---- telescope search: 5x5 grids at steps 32,16,8,4 quarter-pels (:531-561)
   if ((c.size == 16 && c.bip) || c.speed == 0) {
     for (int step = 32; step >= 4; step >>= 1) {
@@ -1046,6 +1060,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
     }
   }
 
+  ME_STAGE(0);
   // ---- candidate search (:564-581); 16x16 blocks use the five-position wide SAD
   for (int base = 0; base < ncand; base += 32) {
     int n = min(32, ncand - base);
@@ -1085,6 +1100,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
   refx = optx;
   refy = opty;
 
+  ME_STAGE(1);
   // ---- hexagon refinement (:583-616): visit dir = start..end cyclically; first strict minimum wins
   {
     const int maxsteps = (c.size <= 16 || c.speed == 0) ? 6 : 0;
@@ -1116,6 +1132,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
     }
   }
 
+  ME_STAGE(2);
   int ydh = 0, xdh = 0, ydq = 0, xdq = 0;
   uint32_t cmin = min_sad;
   c.n_sub += c.speed == 0 ? 16 : 2;
@@ -1162,6 +1179,7 @@ __device__ void warp_motion_estimate(const S *orig_full, int os, const S *ref_fu
       } else {
         ydq = yd; xdq = xd;
       }
+      ME_STAGE(3 + stage);
     }
   } else {
     // ---- bilinear approximations (:664-703)
@@ -1378,11 +1396,42 @@ __device__ __noinline__ uint32_t bi_probe_sad(const S *o, int os, const S *ref0,
   return group_sum(acc, 4);
 }
 
+// The same with the whole warp on ONE probe (blocks >= 16x16 inside the device RD loop): integer positions are averaged and compared as 32-bit words
+// straight from the reference frames (lanes along the row); any other position is interpolated once per reference by the prediction routine
+// (warp_interp: DP4A strips) into the caller's two scratch blocks (pitch = size) and compared as words from there.
+template <class S>
+__device__ __noinline__ uint32_t bi_probe_sad_warp(const S *o, int os, const S *ref0, const S *ref1, int rs, int size, int mvx0, int mvy0, int mvx1, int mvy1, int sign, int bip,
+                                                   int fw, int fh, int xpos, int ypos, int bitdepth, S *s0, S *s1) {
+  constexpr int PW = Word<S>::PW;
+  int hi0, vi0, xf0, yf0, hi1, vi1, xf1, yf1;
+  split_mv(mvx0, mvy0, sign, 2, fw, fh, xpos, ypos, size, size, hi0, vi0, xf0, yf0);
+  split_mv(mvx1, mvy1, 1 - sign, 2, fw, fh, xpos, ypos, size, size, hi1, vi1, xf1, yf1);
+  const S *p0 = ref0 + vi0 * rs + hi0, *p1 = ref1 + vi1 * rs + hi1;
+  int st0 = rs, st1 = rs;
+  if (xf0 | yf0) { __syncwarp(); warp_interp<S>(s0, size, ref0, rs, size, size, mvx0, mvy0, sign, 0, bip, fw, fh, xpos, ypos, bitdepth); p0 = s0; st0 = size; }
+  if (xf1 | yf1) { __syncwarp(); warp_interp<S>(s1, size, ref1, rs, size, size, mvx1, mvy1, 1 - sign, 0, bip, fw, fh, xpos, ypos, bitdepth); p1 = s1; st1 = size; }
+  __syncwarp();
+  const int lane = lane_id(), LW = size / PW, LWe = LW < 32 ? LW : 32, RP = 32 / LWe, CI = LW / LWe;
+  const int col0 = lane & (LWe - 1), rsub = lane / LWe;
+  uint32_t acc = 0;
+  for (int row = rsub; row < size; row += RP)
+    for (int ci = 0; ci < CI; ci++) {
+      const int col = (col0 + ci * 32) * PW;
+      const uint32_t a = *(const uint32_t *)(o + row * os + col), r0 = ldw_any(p0 + row * st0 + col), r1 = ldw_any(p1 + row * st1 + col);
+      acc += word_sad<S>(a, sizeof(S) == 1 ? __vhaddu4(r0, r1) : __vhaddu2(r0, r1));  // (v0 + v1) >> 1 per sample
+    }
+  __syncwarp();
+  return warp_sum(acc);
+}
+
 template <class S>
 __device__ void warp_motion_estimate_bi(const S *orig, int os, const S *ref0, const S *ref1, int rs, int size, int sign, int xpos, int ypos, int fw, int fh, int bitdepth, int bip,
                                         double lambda, int mvcx, int mvcy, int mvpx, int mvpy, const int16_t *cand, int ncand, int &out_mvx, int &out_mvy,
-                                        uint32_t &out_cost) {
-  const int lane = lane_id(), shift = bitdepth - 8, grp = lane >> 2;
+                                        uint32_t &out_cost, S *scratch0 = nullptr, S *scratch1 = nullptr) {
+  const int lane = lane_id(), shift = bitdepth - 8;
+  // with scratch blocks and >= 16x16: one probe at a time on the whole warp (bi_probe_sad_warp); else eight probes at a time on 4-lane groups
+  const bool whole = scratch0 != nullptr && size >= 16;
+  const int gl = whole ? 32 : 4, grp = lane / gl, per = 32 / gl;
   uint32_t min_sad = 1u << 31;
   int optx = 0, opty = 0;
   int refx = (int)(int16_t)(((mvcx + 2) >> 2) << 2), refy = (int)(int16_t)(((mvcy + 2) >> 2) << 2);
@@ -1390,7 +1439,7 @@ __device__ void warp_motion_estimate_bi(const S *orig, int os, const S *ref0, co
   for (int stage = 0; stage < 7; stage++) {
     const int step = stage < 6 ? (32 >> stage) : 0;
     const int nslots = stage < 6 ? 9 : 6;
-    for (int base = 0; base < nslots; base += 8) {
+    for (int base = 0; base < nslots; base += per) {
       // slot handled by this lane group
       const int slot = base + grp;
       bool valid = slot < nslots;
@@ -1415,12 +1464,14 @@ __device__ void warp_motion_estimate_bi(const S *orig, int os, const S *ref0, co
       clip_mv(c0x, c0y, ypos, xpos, fw, fh, size, size, sign);
       int c1x = c0x, c1y = c0y;  // the second clip runs on the already clipped vector; its result is the one kept
       clip_mv(c1x, c1y, ypos, xpos, fw, fh, size, size, 1 - sign);
-      uint32_t sad = bi_probe_sad<S>(orig, os, ref0, ref1, rs, size, c0x, c0y, c1x, c1y, sign, bip, fw, fh, xpos, ypos, bitdepth);
+      uint32_t sad = 0;
+      if (!whole) sad = bi_probe_sad<S>(orig, os, ref0, ref1, rs, size, c0x, c0y, c1x, c1y, sign, bip, fw, fh, xpos, ypos, bitdepth);
+      else if (valid) sad = bi_probe_sad_warp<S>(orig, os, ref0, ref1, rs, size, c0x, c0y, c1x, c1y, sign, bip, fw, fh, xpos, ypos, bitdepth, scratch0, scratch1);  // warp-uniform
       uint32_t cost = (sad >> shift) + mv_cost(lambda, quote_mv_bits((int)(int16_t)(c1y - mvpy), (int)(int16_t)(c1x - mvpx)));
-      for (int t = 0; t < 8; t++) {
-        bool v = __shfl_sync(FULL, (int)valid, t * 4) != 0;
-        uint32_t ct = __shfl_sync(FULL, cost, t * 4);
-        int tx = __shfl_sync(FULL, c1x, t * 4), ty = __shfl_sync(FULL, c1y, t * 4);
+      for (int t = 0; t < per; t++) {
+        bool v = __shfl_sync(FULL, (int)valid, t * gl) != 0;
+        uint32_t ct = __shfl_sync(FULL, cost, t * gl);
+        int tx = __shfl_sync(FULL, c1x, t * gl), ty = __shfl_sync(FULL, c1y, t * gl);
         if (v && ct < min_sad) { min_sad = ct; optx = tx; opty = ty; }
       }
     }

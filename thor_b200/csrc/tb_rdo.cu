@@ -16,6 +16,7 @@
 // The device code of this unit lives in its own namespace (the headers define __constant__ tables).
 #define TB_LDG(p) (*(p))
 #define TB_LDF(p) __ldcg(p)
+#define TB_ME_STAGE_PROF 1  // cycles per search stage (telescope, candidates, hexagon, half-pel, quarter-pel) of blocks <= 16 in the kernel's counters
 #ifndef TB_SAD_ROWS
 #define TB_SAD_ROWS 1  // integer-position SADs of blocks >= 32 bytes wide: lanes along the row (multi_sad_rows)
 #endif
@@ -39,7 +40,8 @@ enum { PF_INTERP, PF_ME, PF_MEBI, PF_TX, PF_BITS, PF_SSD, PF_INTRA, PF_COPY, PF_
 // SSD/SAD samples, super blocks
 enum { ST_ME = PF_N, ST_ME_INT, ST_ME_SUB, ST_ME_SAMPLES, ST_IP, ST_IP_SAMPLES, ST_TX, ST_TX_SAMPLES, ST_INTRA, ST_INTRA_SAMPLES, ST_SSD_SAMPLES, ST_SB,
        ST_ME_SZ /* cycles of searches by coding-block size 8..128 */, ST_TX_SZ = ST_ME_SZ + 5 /* chains by transform size 4..128 */, ST_IP_SZ = ST_TX_SZ + 6 /* predictions by width 4..128 */,
-       ST_PH = ST_IP_SZ + 6 /* wall cycles of warp 0 by decision phase (tb_rdo.h PH_*) */, ST_END = ST_PH + tbr::PH_N };
+       ST_PH = ST_IP_SZ + 6 /* wall cycles of warp 0 by decision phase (tb_rdo.h PH_*) */, ST_MESTAGE = ST_PH + tbr::PH_N /* search stages, coding blocks <= 16 */,
+       ST_X = ST_MESTAGE + 5 /* search phase of a block decision: warp 0 {own searches, -, barrier wait}, warp nw-1 {-, intra items, barrier wait} */, ST_END = ST_X + 6 };
 struct Prof {
   long long *acc;
   int k, k2;
@@ -71,7 +73,8 @@ struct RdoCta {
 // per-warp scratch
 template <class S> struct RdoShared {
   long long prof[ST_END];
-  long long t_mark;
+  long long t_mark, t_mark2;
+  alignas(16) unsigned char jobs[12 * 64];  // tx_multi: the chains' parameters
   TxScratch sc;
   alignas(16) int16_t blk16[256];                // early skip: averaged residual / chroma residual
   alignas(16) int16_t out16[256];                // transform output of the early-skip test; coefficient scan for the bit count
@@ -90,7 +93,7 @@ template <class S> struct DevBackend {
   __device__ __forceinline__ bool mine(int k) const { return (k % nw) == wid; }
   __device__ void cta_sync() const { __threadfence(); __syncthreads(); }
   __device__ __forceinline__ int nwarps() const { return nw; }
-  __device__ void queue_reset() const {
+  __device__ __noinline__ void queue_reset() const {
     __syncthreads();
     if (threadIdx.x < 4) cta->x_queue[threadIdx.x] = 0;
     __syncthreads();
@@ -100,10 +103,17 @@ template <class S> struct DevBackend {
     if ((threadIdx.x & 31) == 0) v = atomicAdd(&cta->x_queue[q], 1);
     return __shfl_sync(FULL, v, 0);
   }
-  __device__ void copy_words(void *dst, const void *src, int nwords) const {
+  __device__ __noinline__ void copy_words(void *dst, const void *src, int nwords) const {
     __syncwarp();
     for (int k = threadIdx.x & 31; k < nwords; k += 32) ((int *)dst)[k] = ((const int *)src)[k];
     __syncwarp();
+  }
+  __device__ __forceinline__ void mark2(int k) const {  // per-warp timers of the search phase, kept for warp 0 and the last warp
+    if ((wid == 0 || wid == nw - 1) && (threadIdx.x & 31) == 0) {
+      const long long t = clock64();
+      if (k >= 0) sh->prof[ST_X + (wid == 0 ? 0 : 3) + k] += t - sh->t_mark2;
+      sh->t_mark2 = t;
+    }
   }
   __device__ __forceinline__ void mark(int k) const {
     if (wid == 0 && (threadIdx.x & 31) == 0) { const long long t = clock64(); sh->prof[ST_PH + k] += t - sh->t_mark; sh->t_mark = t; }
@@ -117,7 +127,7 @@ template <class S> struct DevBackend {
     for (int k = 0; k < 16; k++) mv16[k] = cta->x_mv[ref][k];
     *sad = cta->x_sad[ref];
   }
-  __device__ int reduce_best(uint32_t *cost, int *idx) const {
+  __device__ __noinline__ int reduce_best(uint32_t *cost, int *idx) const {
     if ((threadIdx.x & 31) == 0) { cta->x_cost[wid] = *cost; cta->x_idx[wid] = *idx; }
     __syncthreads();
     int w = 0;
@@ -127,7 +137,7 @@ template <class S> struct DevBackend {
     __syncthreads();
     return w;
   }
-  __device__ void bcast(void *p, int nbytes, int owner) const {  // p: per-thread (replicated) object, multiple of 4 bytes, <= 128
+  __device__ __noinline__ void bcast(void *p, int nbytes, int owner) const {  // p: per-thread (replicated) object, multiple of 4 bytes, <= 128
     int *q = (int *)p;
     if (wid == owner && (threadIdx.x & 31) == 0)
       for (int k = 0; k < nbytes / 4; k++) cta->x_buf[k] = q[k];
@@ -136,13 +146,13 @@ template <class S> struct DevBackend {
       for (int k = 0; k < nbytes / 4; k++) q[k] = cta->x_buf[k];
     __syncthreads();
   }
-  __device__ void reduce_range(uint32_t *worst, uint32_t *best) const {
+  __device__ __noinline__ void reduce_range(uint32_t *worst, uint32_t *best) const {
     if ((threadIdx.x & 31) == 0) { cta->x_rng[wid][0] = *worst; cta->x_rng[wid][1] = *best; }
     __syncthreads();
     for (int k = 0; k < nw; k++) { *worst = max(*worst, cta->x_rng[k][0]); *best = min(*best, cta->x_rng[k][1]); }
     __syncthreads();
   }
-  __device__ int reduce_or(int f) const {
+  __device__ __noinline__ int reduce_or(int f) const {
     if ((threadIdx.x & 31) == 0) cta->x_flag[wid] = f;
     __syncthreads();
     int r = 0;
@@ -156,7 +166,7 @@ template <class S> struct DevBackend {
 #define PROF2(k, k2) Prof prof__(sh->prof, k, k2)
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 
-  __device__ tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const {
+  __device__ __noinline__ tb_rdo_blk_t ld_blk(const tb_rdo_blk_t *p) const {
     // 20 bytes, 4-byte aligned; written by another CTA earlier in this launch -> L2
     const int *q = (const int *)p;
     int w[5];
@@ -172,7 +182,7 @@ template <class S> struct DevBackend {
     mv.x = (int16_t)x; mv.y = (int16_t)y;
   }
   // prediction of one block; widths that are not powers of two (rectangular blocks at the right frame edge) take the per-sample form
-  __device__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
+  __device__ __noinline__ void interp_any(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int chroma, int bip, int pw, int ph, int xpos, int ypos) const {
     PROF2(PF_INTERP, ST_IP_SZ + min(5, max(0, ilog2(max(w, h)) - 2)));
     if (lane() == 0) { sh->prof[ST_IP] += 1; sh->prof[ST_IP_SAMPLES] += (xf_any(mv, chroma) ? (w + 5) * (h + 5) : w * h) + w * h; }
     sync();
@@ -200,7 +210,7 @@ template <class S> struct DevBackend {
   __device__ void interp_chroma(S *dst, int ds, const S *ref, int rs, int w, int h, Mv mv, int sign, int pw, int ph, int xc, int yc) const {
     interp_any(dst, ds, ref, rs, w, h, mv, sign, 1, 0, pw, ph, xc, yc);
   }
-  __device__ void avg(S *dst, const S *a, const S *b, int stride, int w, int h) const {
+  __device__ __noinline__ void avg(S *dst, const S *a, const S *b, int stride, int w, int h) const {
     PROF(PF_COPY);
     sync();
     for (int p = lane(); p < w * h; p += 32) {
@@ -209,7 +219,7 @@ template <class S> struct DevBackend {
     }
     sync();
   }
-  __device__ void sat2ab(S *dst, const S *org, int os, const S *pred, int size) const {
+  __device__ __noinline__ void sat2ab(S *dst, const S *org, int os, const S *pred, int size) const {
     PROF(PF_COPY);
     const int maxv = (1 << F->bitdepth) - 1, ls = ilog2(size);
     sync();
@@ -219,7 +229,7 @@ template <class S> struct DevBackend {
     }
     sync();
   }
-  __device__ void copy(S *dst, int ds, const S *src, int ss, int w, int h) const {
+  __device__ __noinline__ void copy(S *dst, int ds, const S *src, int ss, int w, int h) const {
     PROF(PF_COPY);
     sync();
     for (int p = lane(); p < w * h; p += 32) {
@@ -228,13 +238,13 @@ template <class S> struct DevBackend {
     }
     sync();
   }
-  __device__ void copy_coeff(int16_t *dst, const int16_t *src) const {
+  __device__ __noinline__ void copy_coeff(int16_t *dst, const int16_t *src) const {
     PROF(PF_COPY);
     sync();
     for (int p = lane(); p < 1024 / 4; p += 32) ((uint2 *)dst)[p] = ((const uint2 *)src)[p];
     sync();
   }
-  __device__ void intra_predict(S *dst, int ds, const S *recf, int rfs, const S *rblock, int rbs, int i, int j, int ypos, int xpos, int size, int ur, int dl, int tbs,
+  __device__ __noinline__ void intra_predict(S *dst, int ds, const S *recf, int rfs, const S *rblock, int rbs, int i, int j, int ypos, int xpos, int size, int ur, int dl, int tbs,
                                 int mode) const {
     PROF(PF_INTRA);
     if (lane() == 0) { sh->prof[ST_INTRA] += 1; sh->prof[ST_INTRA_SAMPLES] += 4 * size + size * size; }
@@ -246,62 +256,170 @@ template <class S> struct DevBackend {
     else warp_intra_pred<S>(sh->left, sh->top, tl, ypos + i, xpos + j, size, dst, ds, mode, F->bitdepth, sh->filt);
     sync();
   }
-  __device__ void cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride) const {
+  __device__ __noinline__ void cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride) const {
     PROF(PF_INTRA);
     sync();
     warp_cfl<S>(y, u, v, ry, n, cstride, stride, 1, F->bitdepth);
     sync();
   }
-  __device__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
+  __device__ __noinline__ int tx_chain(const S *orig, int os, const S *pred, int ps, S *rec, int rs, int16_t *cq, int size, int qp, int coeff_type, int fast) const {
+    int cbp;
+    if (size < 16) {  // 4x4 / 8x8: the loop form below, one chain
+      tbr::TxJob<S> j;
+      j.orig = orig; j.pred = pred; j.rec = rec; j.cq = cq; j.os = os; j.ps = ps; j.rs = rs; j.size = size; j.qp = qp; j.coeff_type = coeff_type; j.fast = fast;
+      tx_multi(&j, 1, &cbp);
+      return cbp;
+    }
     PROF2(PF_TX, ST_TX_SZ + ilog2(size) - 2);
     if (lane() == 0) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * size * size; }
     sync();
-    int cbp;
-    if (size >= 16) {
-      tb_txfm_item_t q;
-      q.orig = orig; q.pred = pred; q.rec = rec; q.coeffq = cq; q.ostride = os; q.pstride = ps; q.rstride = rs;
-      q.size = (uint8_t)size; q.qp = (uint8_t)qp; q.coeff_type = (uint8_t)coeff_type; q.fast = (uint8_t)(fast ? TB_TXFM_FAST : 0);
-      tx_big_chain<S, 1>(q, F->bitdepth, sh->sc, nullptr, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, nullptr, nullptr, &sh->res);
-      sync();
-      cbp = sh->res.cbp;
-    } else {
-      cbp = 0;
-      if (lane() == 0) {
-        uint64_t ssd;
-        int bits;
-        if (size == 4) cbp = thread_txfm4<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, ssd, 0, bits);
-        else cbp = thread_txfm8<S>(orig, os, pred, ps, rec, rs, cq, qp, coeff_type, F->bitdepth, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
-      }
-      cbp = __shfl_sync(FULL, cbp, 0);
-    }
+    tb_txfm_item_t q;
+    q.orig = orig; q.pred = pred; q.rec = rec; q.coeffq = cq; q.ostride = os; q.pstride = ps; q.rstride = rs;
+    q.size = (uint8_t)size; q.qp = (uint8_t)qp; q.coeff_type = (uint8_t)coeff_type; q.fast = (uint8_t)(fast ? TB_TXFM_FAST : 0);
+    tx_big_chain<S, 1>(q, F->bitdepth, sh->sc, nullptr, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, nullptr, nullptr, &sh->res);
+    sync();
+    cbp = sh->res.cbp;
     sync();
     return cbp;
   }
-  // <= 12 chains of 4x4 / 8x8 transform blocks, chain k on lane k (thread_txfm4 in registers, thread_txfm8 in local arrays); bit[k] = its cbp
-  __device__ void tx_multi(const tbr::TxJob<S> *jobs, int n, int *bit) const {
+  // <= 12 chains of 4x4 / 8x8 transform blocks (residual -> DCT -> quantiser -> dequantiser -> inverse DCT -> reconstruction, the arithmetic of
+  // common/transform.c:245-308, 411-494, enc/encode_block.c:84-171, common/common_block.c:45-83), all of them together on the warp.  Written as LOOPS over
+  // (chain, element) work items dealt to the lanes: the RD loop is bound by instruction fetch (ncu: 19 stalled warps per issued instruction wait for
+  // instructions), so a few hundred instructions that stay in the instruction cache beat the unrolled one-thread-per-chain forms (5.6 k instructions
+  // streamed from L2 per call).  Tiles of 64 int16 per chain in the warp's scratch; the quantiser's level-mode walk is sequential: one lane per chain.
+  __device__ __noinline__ void tx_multi(const tbr::TxJob<S> *jobs, int n, int *bit) const {
     PROF2(PF_TX, ST_TX_SZ + ilog2(jobs[0].size) - 2);
-    if (lane() == 0)
-      for (int k = 0; k < n; k++) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * jobs[k].size * jobs[k].size; }
-    sync();
     const int l = lane();
+    if (l == 0)
+      for (int k = 0; k < n; k++) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * jobs[k].size * jobs[k].size; }
+    int16_t *A = sh->sc.in, *B = sh->sc.in + 768;  // 12 tiles of 64 each
+    // chain parameters in shared memory (per warp): the loops index them by chain
+    tbr::TxJob<S> *J = (tbr::TxJob<S> *)sh->jobs;
+    sync();
+    if (l < n) J[l] = jobs[l];
+    sync();
+    const int bd = F->bitdepth, maxv = (1 << bd) - 1;
+    // (1) residual -> A[k][i * N + j]
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63;
+      const tbr::TxJob<S> &q = J[k];
+      const int N = q.size, ln = N == 8 ? 3 : 2;
+      if (e < N * N) { const int i = e >> ln, j = e & (N - 1); A[w] = (int16_t)((int)q.orig[i * q.os + j] - (int)q.pred[i * q.ps + j]); }
+    }
+    sync();
+    // (2) forward, first dimension: B[k][i][j] = (sum_t M[i][t] * A[k][j][t] + add1) >> shift1
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
+      if (e < N * N) {
+        const int i = e >> ln, j = e & (N - 1);
+        const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0) + (i << ln), *a = A + (k << 6) + (j << ln);
+        int sum = 0;
+        for (int t = 0; t < N; t++) sum += (int)M[t] * (int)a[t];
+        const int shift1 = ln + bd - 8;
+        B[w] = (int16_t)((sum + (1 << (shift1 - 1))) >> shift1);
+      }
+    }
+    sync();
+    // (3) forward, second dimension: A[k][i][j] = (sum_t M[i][t] * B[k][j][t] + add2) >> shift2   (coefficients, raster)
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
+      int v = 0;
+      if (e < N * N) {
+        const int i = e >> ln, j = e & (N - 1);
+        const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0) + (i << ln), *b = B + (k << 6) + (j << ln);
+        int sum = 0;
+        for (int t = 0; t < N; t++) sum += (int)M[t] * (int)b[t];
+        const int shift2 = ln + 5;
+        v = (sum + (1 << (shift2 - 1))) >> shift2;
+      }
+      if (e < N * N) A[w] = (int16_t)v;  // A was consumed by (2)
+    }
+    sync();
+    // (4) zig-zag scan order -> B[k][pos]
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
+      if (e < N * N) B[(k << 6) + zigzag_index(e >> ln, e & (N - 1), N)] = A[w];
+    }
+    sync();
+    // (5) quantiser (sequential level-mode walk), lane k on chain k: levels in scan order -> B[k][pos] in place; cbp
     int cbp = 0;
     if (l < n) {
-      const tbr::TxJob<S> q = jobs[l];
-      uint64_t ssd;
-      int bits;
-      if (q.size == 8) cbp = thread_txfm8<S>(q.orig, q.os, q.pred, q.ps, q.rec, q.rs, q.cq, q.qp, q.coeff_type, F->bitdepth, cta->tab8, cta->tab8 + DCT_TAB8_SIZE, ssd, 0, bits);
-    }
-    if (l < n) {
-      const tbr::TxJob<S> q = jobs[l];
-      uint64_t ssd;
-      int bits;
-      if (q.size == 4) cbp = thread_txfm4<S>(q.orig, q.os, q.pred, q.ps, q.rec, q.rs, q.cq, q.qp, q.coeff_type, F->bitdepth, ssd, 0, bits);
+      const tbr::TxJob<S> &q = J[l];
+      const int N = q.size, nq = N * N, intra = (q.coeff_type >> 1) & 1, scale = c_quant[q.qp % 6], shift2 = 21 - (N == 8 ? 3 : 2) + q.qp / 6;
+      int16_t *sc_ = B + (l << 6);
+      const int offset = (intra ? 38 : -26) * (1 << (shift2 - 8));
+      int level = 0, pos = nq - 1;
+      while (level == 0 && pos >= 0) {
+        const int v = iabs((int)sc_[pos]) * scale + offset;  // < 2^31: |c| <= 32768, scale <= 26214
+        level = iabs(v) >> shift2;
+        pos--;
+      }
+      const int last_pos = level ? pos + 1 : pos;
+      const int off0 = (intra ? 102 : 51) << (shift2 - 8), off1 = (intra ? 115 : 90) << (shift2 - 8);
+      int level_mode = 1;
+      for (pos = 0; pos <= last_pos; pos++) {
+        const int c = sc_[pos];
+        const unsigned ac = (unsigned)scale * (unsigned)iabs(c);
+        const int level0 = (int)(ac >> shift2);
+        const int lev = (int)((ac + (unsigned)((level0 > (1 - level_mode)) ? off1 : off0)) >> shift2);
+        sc_[pos] = (int16_t)(c < 0 ? -lev : lev);
+        cbp |= lev != 0;
+        if (level_mode) { if (lev == 0) level_mode = 0; }
+        else if (lev > 1) level_mode = 1;
+      }
+      for (pos = last_pos + 1; pos < nq; pos++) sc_[pos] = 0;
     }
     sync();
-    for (int k = 0; k < n; k++) bit[k] = __shfl_sync(FULL, cbp, k);
+    const unsigned nzmask = __ballot_sync(FULL, cbp != 0);
+    // (6) quantised coefficients, raster: to the caller's buffer (reference layout) and, dequantised, to A[k] (dequantize(), common/common_block.c:45)
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63;
+      const tbr::TxJob<S> &q = J[k];
+      const int N = q.size, ln = N == 8 ? 3 : 2;
+      if (e < N * N) {
+        const int c = B[(k << 6) + zigzag_index(e >> ln, e & (N - 1), N)];
+        q.cq[e] = (int16_t)c;
+        const int lshift = q.qp / 6, rshift = ln - 1, dscale = c_dequant[q.qp % 6];
+        A[w] = lshift >= rshift ? (int16_t)((c * dscale) << (lshift - rshift)) : (int16_t)((c * dscale + (1 << (rshift - lshift - 1))) >> (rshift - lshift));
+      }
+    }
     sync();
+    // (7) inverse, first dimension: B[k][i][j] = sat16((sum_t M[t][j] * A[k][t][i] + 64) >> 7)
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
+      if (e < N * N && ((nzmask >> k) & 1)) {
+        const int i = e >> ln, j = e & (N - 1);
+        const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0), *a = A + (k << 6);
+        int o = 0;
+        for (int t = 0; t < N; t++) o += (int)M[(t << ln) + j] * (int)a[(t << ln) + i];
+        o = (o + 64) >> 7;
+        B[w] = (int16_t)iclip(o, -32768, 32767);
+      }
+    }
+    sync();
+    // (8) inverse, second dimension + reconstruction: rec = clip(pred + sat16((sum_t M[t][j] * B[k][t][i] + round) >> (20 - bitdepth))); no coefficient: rec = pred
+    for (int w = l; w < n * 64; w += 32) {
+      const int k = w >> 6, e = w & 63;
+      const tbr::TxJob<S> &q = J[k];
+      const int N = q.size, ln = N == 8 ? 3 : 2;
+      if (e < N * N) {
+        const int i = e >> ln, j = e & (N - 1);
+        int v = (int)q.pred[i * q.ps + j];
+        if ((nzmask >> k) & 1) {
+          const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0), *b = B + (k << 6);
+          int o = 0;
+          for (int t = 0; t < N; t++) o += (int)M[(t << ln) + j] * (int)b[(t << ln) + i];
+          const int sh2 = 20 - bd;
+          o = (o + (1 << (sh2 - 1))) >> sh2;
+          v = sat_px(v + iclip(o, -32768, 32767), maxv);
+        }
+        q.rec[i * q.rs + j] = (S)v;
+      }
+    }
+    sync();
+    for (int k = 0; k < n; k++) bit[k] = (nzmask >> k) & 1;
   }
-  __device__ int coeff_bits(const int16_t *cq, int size, int type) const {
+  __device__ __noinline__ int coeff_bits(const int16_t *cq, int size, int type) const {
     PROF(PF_BITS);
     const int qs = min(size, 16), nq = qs * qs, lq = ilog2(qs);
     sync();
@@ -311,7 +429,7 @@ template <class S> struct DevBackend {
     sync();
     return bits;
   }
-  __device__ uint64_t ssd(const S *a, int as, const S *b, int bs, int w, int h) const {
+  __device__ __noinline__ uint64_t ssd(const S *a, int as, const S *b, int bs, int w, int h) const {
     PROF(PF_SSD);
     if (lane() == 0) sh->prof[ST_SSD_SAMPLES] += 2 * w * h;
     sync();
@@ -323,19 +441,20 @@ template <class S> struct DevBackend {
     }
     return warp_sum64(acc);
   }
-  __device__ unsigned sad(const S *a, int as, const S *b, int bs, int w, int h) const {
+  __device__ __noinline__ unsigned sad(const S *a, int as, const S *b, int bs, int w, int h) const {
     PROF(PF_SSD);
     if (lane() == 0) sh->prof[ST_SSD_SAMPLES] += 2 * w * h;
     sync();
     return warp_sad<S>(a, as, b, bs, w, h);
   }
-  __device__ int me(const S *org, int os, const S *ref, int rs, int size, int w, int h, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
+  __device__ __noinline__ int me(const S *org, int os, const S *ref, int rs, int size, int w, int h, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
                     int ncand) const {
     PROF2(PF_ME, ST_ME_SZ + ilog2(size) - 3);
     sync();
     MeCtx c;
     c.size = size; c.width = w; c.height = h; c.sign = sign; c.s = sign ? -1 : 1; c.xpos = xpos; c.ypos = ypos; c.fw = F->width; c.fh = F->height;
     c.bitdepth = F->bitdepth; c.speed = F->speed; c.bip = F->enable_bipred; c.mvpx = mvp.x; c.mvpy = mvp.y; c.lambda = lambda; c.n_int = 0; c.n_sub = 0; c.sps = nullptr;
+    for (int k = 0; k < 5; k++) c.cyc[k] = 0;
     MeTeam<1> tm;
     tm.xch = nullptr; tm.warp = 0; tm.phase = 0;
     int mx, my;
@@ -345,26 +464,28 @@ template <class S> struct DevBackend {
     mv->x = (int16_t)mx; mv->y = (int16_t)my;
     if (lane() == 0) {
       sh->prof[ST_ME] += 1; sh->prof[ST_ME_INT] += c.n_int; sh->prof[ST_ME_SUB] += c.n_sub;
+      if (size <= 16)
+        for (int k = 0; k < 5; k++) sh->prof[ST_MESTAGE + k] += c.cyc[k];
       sh->prof[ST_ME_SAMPLES] += (long long)(c.n_int + 1) * w * h + (long long)c.n_sub * ((w + 5) * (h + 5) + w * h);
     }
     sync();
     return (int)cost;
   }
-  __device__ int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
-                       int ncand) const {
+  __device__ __noinline__ int me_bi(const S *org, int os, const S *ref0, const S *ref1, int rs, int size, Mv *mv, Mv mvc, Mv mvp, double lambda, int sign, int xpos, int ypos, const Mv *cand,
+                       int ncand, S *scratch0, S *scratch1) const {
     PROF(PF_MEBI);
     sync();
     int mx, my;
     uint32_t cost;
     warp_motion_estimate_bi<S>(org, os, ref0, ref1, rs, size, sign, xpos, ypos, F->width, F->height, F->bitdepth, 1, lambda, mvc.x, mvc.y, mvp.x, mvp.y, (const int16_t *)cand,
-                               ncand, mx, my, cost);
+                               ncand, mx, my, cost, scratch0, scratch1);
     mx = __shfl_sync(FULL, mx, 0); my = __shfl_sync(FULL, my, 0); cost = __shfl_sync(FULL, cost, 0);
     mv->x = (int16_t)mx; mv->y = (int16_t)my;
     sync();
     return (int)cost;
   }
   // check_early_skip_sub_block (enc/encode_block.c:2147-2180): 2x2 average of the residual, (size/2)-point transform, any |c| > threshold
-  __device__ int es_luma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+  __device__ __noinline__ int es_luma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
     PROF(PF_ES);
     const int s2 = size / 2, l2 = ilog2(s2);
     sync();
@@ -386,7 +507,7 @@ template <class S> struct DevBackend {
     return hit;
   }
   // check_early_skip_sub_blockC :2214-2229 with calc_cbp_simd
-  __device__ int es_chroma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
+  __device__ __noinline__ int es_chroma(const S *orig, int os, const S *pred, int ps, int size, int threshold) const {
     PROF(PF_ES);
     const int ls = ilog2(size);
     sync();
@@ -399,7 +520,7 @@ template <class S> struct DevBackend {
     sync();
     return r;
   }
-  __device__ void store_blk(tb_rdo_blk_t *blk, int stride, int by, int bx, int nbw, int nbh, int div, tb_rdo_blk_t v, const Mv *mv0, const Mv *mv1) const {
+  __device__ __noinline__ void store_blk(tb_rdo_blk_t *blk, int stride, int by, int bx, int nbw, int nbh, int div, tb_rdo_blk_t v, const Mv *mv0, const Mv *mv1) const {
     sync();
     for (int p = lane(); p < nbw * nbh; p += 32) {
       const int m = p / nbw, n = p - m * nbw;
@@ -410,7 +531,7 @@ template <class S> struct DevBackend {
     }
     sync();
   }
-  __device__ void pack_coeff(int16_t *dst, const int16_t *q, int size, int tb_split, int nonzero) const {
+  __device__ __noinline__ void pack_coeff(int16_t *dst, const int16_t *q, int size, int tb_split, int nonzero) const {
     const int t = tb_split ? size / 2 : size, qs = t < 16 ? t : 16, n = tb_split ? 4 : 1, nq = qs * qs;
     sync();
     for (int p = lane(); p < n * nq; p += 32) {
@@ -432,12 +553,15 @@ template <class S> struct DevBackend {
 #ifndef TB_RDO_WARPS
 #define TB_RDO_WARPS 8
 #endif
+#ifndef TB_RDO_CTAS_PER_SM
+#define TB_RDO_CTAS_PER_SM 1
+#endif
 constexpr int RDO_WARPS = TB_RDO_WARPS;  // warps per CTA: 8 x 32 threads x 255 registers = the whole register file of an SM
 
 // One row of super blocks of one frame of the batch.  Rows are the unit a CTA claims; super blocks inside a row are sequential.
 struct RowDesc { int frame, row, nsbx, pad; };
 // scheduler words behind the per-row arrays
-enum { CTL_REMAINING = 0, CTL_ERROR = 1, CTL_N = 4 };
+enum { CTL_REMAINING = 0, CTL_ERROR = 1, CTL_EVENT = 2 /* bumped after every finished super block */, CTL_N = 4 };
 
 // Persistent CTAs draw READY super blocks from the rows of every frame of the batch (dataflow scheduling): row r of a frame may process
 // super block c when row r-1 has published min(c+2, nsbx) super blocks (left, up-left, up, up-right neighbours: get_mv_pred / intra
@@ -446,7 +570,7 @@ enum { CTL_REMAINING = 0, CTL_ERROR = 1, CTL_N = 4 };
 // so a CTA never holds an SM while it waits for a neighbour: a row migrates between CTAs at super-block boundaries (all per-super-block
 // state is re-initialised by process_sb; data of other super blocks is read through L2, see TB_LDF above).
 template <class S>
-__global__ void __launch_bounds__(32 * RDO_WARPS, 1)
+__global__ void __launch_bounds__(32 * RDO_WARPS, TB_RDO_CTAS_PER_SM)
     rdo_batch_kernel(const FrameCtx<S> *ctxs, const RowDesc *rows, int nrows, Work<S> *works, int *prog, int *claimed, int *ctl, unsigned long long *prof_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RdoCta &cta = *(RdoCta *)smem_raw;
@@ -470,7 +594,7 @@ __global__ void __launch_bounds__(32 * RDO_WARPS, 1)
     int sel;
     {
       Prof pw(sh.prof, PF_WAIT);
-      if (threadIdx.x == 0) cta.sel = 0x7fffffff;
+      if (threadIdx.x == 0) { cta.sel = 0x7fffffff; cta.x_idx[1] = vctl[CTL_EVENT]; }  // the event count BEFORE the scan: progress made during the scan is not lost
       __syncthreads();
       int mine = 0x7fffffff;
       for (int g = threadIdx.x; g < nrows; g += blockDim.x) {
@@ -484,11 +608,17 @@ __global__ void __launch_bounds__(32 * RDO_WARPS, 1)
       sel = cta.sel;
       if (sel == 0x7fffffff) {  // nothing ready: finished, failed, or wait for the running super blocks
         if (threadIdx.x == 0) {
+          // ONE thread polls ONE word (the event counter) at a low rate: a super block takes ~100 ms, and every CTA of the grid scanning the row
+          // table in a tight loop turns its few cache lines into a hot spot of one L2 slice that slows the working CTAs down
           int f = 0;
-          if (vctl[CTL_REMAINING] <= 0) f = 1;
-          // ~30 s of SM clocks without any work for this CTA while work remains: a row stopped publishing (it faulted): do not hang the launch
-          else if (vctl[CTL_ERROR] != 0 || clock64() - idle_since > 60000000000ll) { vctl[CTL_ERROR] = 1; f = 1; }
-          else __nanosleep(1000);
+          const int ev0 = cta.x_idx[1];
+          while (true) {
+            if (vctl[CTL_REMAINING] <= 0) { f = 1; break; }
+            // ~30 s of SM clocks without any work for this CTA while work remains: a row stopped publishing (it faulted): do not hang the launch
+            if (vctl[CTL_ERROR] != 0 || clock64() - idle_since > 60000000000ll) { vctl[CTL_ERROR] = 1; f = 1; break; }
+            if (vctl[CTL_EVENT] != ev0) break;
+            __nanosleep(20000);
+          }
           cta.x_flag[0] = f;
         }
         __syncthreads();
@@ -533,6 +663,8 @@ __global__ void __launch_bounds__(32 * RDO_WARPS, 1)
         const int nx = sbx + 1;
         const int cont = nx < rd.nsbx && (rd.row == 0 || vprog[sel - 1] >= min(nx + 2, rd.nsbx));
         if (!cont) { __threadfence(); atomicExch(&claimed[sel], 0); }
+        __threadfence();
+        atomicAdd(&ctl[CTL_EVENT], 1);
         cta.x_flag[0] = cont;
       }
       __syncthreads();
@@ -804,6 +936,15 @@ int tb_rdo_batch_sync(tb_rdo_batch_t *b) {
       fprintf(stderr, "\n[tb_rdo prof] wall time of a super block by decision phase (warp 0):");
       for (int k = 0; k < tbr::PH_N; k++) fprintf(stderr, " %s %.1f%%", ph[k], 100.0 * (double)pr[ST_PH + k] / (double)(tot ? tot : 1));
     }
+    {
+      static const char *stg[5] = {"telescope", "candidates", "hexagon", "half-pel", "quarter-pel"};
+      unsigned long long tot = 0;
+      for (int k = 0; k < 5; k++) tot += pr[ST_MESTAGE + k];
+      fprintf(stderr, "\n[tb_rdo prof] search stages (coding blocks <= 16):");
+      for (int k = 0; k < 5; k++) fprintf(stderr, " %s %.1f%%", stg[k], 100.0 * (double)pr[ST_MESTAGE + k] / (double)(tot ? tot : 1));
+    }
+    fprintf(stderr, "\n[tb_rdo prof] search phase: warp 0 own searches %.0f, (intra items %.0f), barrier wait %.0f | last warp (searches %.0f) intra items %.0f, barrier wait %.0f  [Mcycles]",
+            pr[ST_X] / 1e6, pr[ST_X + 1] / 1e6, pr[ST_X + 2] / 1e6, pr[ST_X + 3] / 1e6, pr[ST_X + 4] / 1e6, pr[ST_X + 5] / 1e6);
     fprintf(stderr, "\n[tb_rdo prof] search cycles by coding-block size 8..128:");
     for (int k = 0; k < 5; k++) fprintf(stderr, " %.1f%%", 100.0 * (double)pr[ST_ME_SZ + k] / (double)(pr[PF_ME] ? pr[PF_ME] : 1));
     fprintf(stderr, "; transform chains by size 4..128:");

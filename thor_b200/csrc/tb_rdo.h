@@ -26,6 +26,13 @@
 #ifndef TBR_NO_OVERLAP
 #define TBR_NO_OVERLAP 0  // 1: every block through the serial form of mode_decision_rdo (A/B)
 #endif
+// TBR_NI: the functions of the control flow exist ONCE in the device code (no inlining at their many call sites): the RD loop is one kernel whose warps run
+// different parts of it at the same time, and an all-inlined build (2.5 MB of SASS) lives on instruction fetches from L2
+#ifdef __CUDACC__
+#define TBR_NI __noinline__
+#else
+#define TBR_NI
+#endif
 #ifdef __CUDACC__
 #define TBR_HD __device__  // under nvcc the header is only instantiated for the device backend
 #else
@@ -192,7 +199,7 @@ template <class S, class B> struct Rdo {
   TBR_HD static IPred zero_pred() { IPred p; p.mv0.x = p.mv0.y = p.mv1.x = p.mv1.y = 0; p.ref_idx0 = p.ref_idx1 = 0; p.bipred_flag = 0; return p; }
 
   // common/inter_prediction.c:413-524
-  TBR_HD Mv get_mv_pred(int ypos, int xpos, int bw, int bh) const {
+  TBR_HD TBR_NI Mv get_mv_pred(int ypos, int xpos, int bw, int bh) const {
     const int size = imax(bw, bh), bsz = size / MIN_PB, bst = F.blk_stride, bi = (ypos / MIN_PB) * bst + xpos / MIN_PB;
     const int up0 = bi - bst, up1 = bi - bst + (bsz - 1) / 2, up2 = bi - bst + bsz - 1, l0 = bi - 1, l1 = bi + bst * ((bsz - 1) / 2) - 1,
               l2 = bi + bst * (bsz - 1) - 1, dl = bi + bst * bsz - 1, ur = bi - bst + bsz, ul = bi - bst - 1;
@@ -216,7 +223,7 @@ template <class S, class B> struct Rdo {
     return p;
   }
   // get_mv_merge / get_mv_skip (LIMITED_SKIP = 1: two candidates, identical derivation), common/inter_prediction.c:526-836
-  TBR_HD int get_mv_skip_merge(int ypos, int xpos, int bw, int bh, IPred *out) const {
+  TBR_HD TBR_NI int get_mv_skip_merge(int ypos, int xpos, int bw, int bh, IPred *out) const {
     const int size = imax(bw, bh), bsz = size / MIN_PB, bst = F.blk_stride, bi = (ypos / MIN_PB) * bst + xpos / MIN_PB;
     const int up0 = bi - bst, l0 = bi - 1, ur = bi - bst + bsz;
     int up2 = bi - bst + bsz - 1, l2 = bi + bst * (bsz - 1) - 1;
@@ -234,7 +241,7 @@ template <class S, class B> struct Rdo {
     return n;
   }
   // common/common_block.c:283-303
-  TBR_HD Ctx3 find_block_contexts(int ypos, int xpos, int size) const {
+  TBR_HD TBR_NI Ctx3 find_block_contexts(int ypos, int xpos, int size) const {
     Ctx3 c;
     if (ypos >= MIN_BLOCK && xpos >= MIN_BLOCK && ypos + size < F.height && xpos + size < F.width && F.use_block_contexts && size <= MAX_TR) {
       const int bs = F.blk_stride, bi = (ypos / MIN_PB) * bs + xpos / MIN_PB;
@@ -256,7 +263,7 @@ template <class S, class B> struct Rdo {
   // ---------------------------------------------------------------------------------------------------------------
   // bits: write_super_mode + write_block, enc/write_bits.c:255-600 (counting only)
   // ---------------------------------------------------------------------------------------------------------------
-  TBR_HD int super_mode_bits(const BlockInfo &bi, const Cand &c, int split_flag, int encode_this_size) const {
+  TBR_HD TBR_NI int super_mode_bits(const BlockInfo &bi, const Cand &c, int split_flag, int encode_this_size) const {
     const int size = bi.size;
     if (F.frame_type != I_FRAME) {
       if (!encode_this_size) return 1;
@@ -300,7 +307,7 @@ template <class S, class B> struct Rdo {
 
   TBR_HD int coeff_bits_plane(const int16_t *cq, int size, int type) const { return be.coeff_bits(cq, size, type); }
 
-  TBR_HD int block_bits(const BlockInfo &bi, const Cand &c, const int16_t *cqy, const int16_t *cqu, const int16_t *cqv) const {
+  TBR_HD TBR_NI int block_bits(const BlockInfo &bi, const Cand &c, const int16_t *cqy, const int16_t *cqu, const int16_t *cqv) const {
     const int size = bi.size, tb_split = c.tb_split, mode = c.mode, size_uv = size >> 1;
     const int coeff_type = (mode == MODE_INTRA) << 1;
     static const int8_t cbp_table_[8] = {1, 0, 5, 2, 6, 3, 7, 4};
@@ -376,7 +383,7 @@ template <class S, class B> struct Rdo {
   // prediction
   // ---------------------------------------------------------------------------------------------------------------
   // get_inter_prediction_yuv, common/inter_prediction.c:185-233: pitch of the compact blocks = pos_size (block_pos->size)
-  TBR_HD void inter_pred_yuv(int ref_idx, S *py, S *pu, S *pv, int ypos, int xpos, int pos_size, int pbw, int pbh, const Mv *mv_arr, int sign, int split) {
+  TBR_HD TBR_NI void inter_pred_yuv(int ref_idx, S *py, S *pu, S *pv, int ypos, int xpos, int pos_size, int pbw, int pbh, const Mv *mv_arr, int sign, int split) {
     const int div = split + 1, bw = pbw / div, bh = pbh / div, pst = pos_size, rsy = F.ref_stride[0], rsc = F.ref_stride[1];
     const int yc = ypos >> 1, xc = xpos >> 1;
     const S *ry = F.ref[ref_idx][0] + ypos * rsy + xpos, *ru = F.ref[ref_idx][1] + yc * rsc + xc, *rv = F.ref[ref_idx][2] + yc * rsc + xc;
@@ -392,7 +399,7 @@ template <class S, class B> struct Rdo {
     }
   }
   // the inter prediction of a candidate into W.p_* (encode_block :1424-1451)
-  TBR_HD void predict_inter(const BlockInfo &bi, const Cand &c) {
+  TBR_HD TBR_NI void predict_inter(const BlockInfo &bi, const Cand &c) {
     const int split = (c.mode == MODE_INTER || c.mode == MODE_BIPRED) ? F.enable_pb_split : 0;
     if (c.dir == 2 || c.mode == MODE_BIPRED) {
       inter_pred_yuv(c.ref_idx0, W.p0_y, W.p0_u, W.p0_v, bi.ypos, bi.xpos, bi.size, bi.bwidth, bi.bheight, c.mv0, F.ref_sign[c.ref_idx0], split);
@@ -405,7 +412,7 @@ template <class S, class B> struct Rdo {
   }
 
   // encode_and_reconstruct_block_inter :1275-1338 for one plane (orig/pred/rec compact or strided; coefficients in the reference layout)
-  TBR_HD int enc_rec_inter(const S *orig, int os, int size, int qp, const S *pred, int16_t *cq, S *rec, int coeff_type, int tb_split) {
+  TBR_HD TBR_NI int enc_rec_inter(const S *orig, int os, int size, int qp, const S *pred, int16_t *cq, S *rec, int coeff_type, int tb_split) {
     if (tb_split) {
       const int s2 = size / 2;
       int cbp = 0, index = 0;
@@ -446,7 +453,7 @@ template <class S, class B> struct Rdo {
     return cbp;
   }
   // encode_and_reconstruct_block_intra :1100-1168 (luma) — prediction into pblock (pitch size), reconstruction into rec_block (pitch size)
-  TBR_HD int enc_rec_intra(const S *orig, int os, S *recf, int rfs, int ypos, int xpos, int size, int qp, S *pblock, int16_t *cq, S *rec_block, int coeff_type,
+  TBR_HD TBR_NI int enc_rec_intra(const S *orig, int os, S *recf, int rfs, int ypos, int xpos, int size, int qp, S *pblock, int16_t *cq, S *rec_block, int coeff_type,
                            int tb_split, int intra_mode, int upright, int downleft) {
     const int fast = F.speed > 1;
     if (tb_split) {
@@ -465,7 +472,7 @@ template <class S, class B> struct Rdo {
     return be.tx_chain(orig, os, pblock, size, rec_block, size, cq, size, qp, coeff_type, fast);
   }
   // the U and the V chain of one transform block: independent, side by side when they are thread-sized (<= 8x8)
-  TBR_HD void uv_chains(const S *ou, const S *ov, int os, const S *pu, const S *pv, int ps, S *ru, S *rv, int rs, int16_t *cqu, int16_t *cqv, int size, int qp, int coeff_type,
+  TBR_HD TBR_NI void uv_chains(const S *ou, const S *ov, int os, const S *pu, const S *pv, int ps, S *ru, S *rv, int rs, int16_t *cqu, int16_t *cqv, int size, int qp, int coeff_type,
                         int fast, int *bu, int *bv) {
     if (size <= 8) {
       TxJob<S> jobs[2];
@@ -480,7 +487,7 @@ template <class S, class B> struct Rdo {
     }
   }
   // encode_and_reconstruct_block_intra_uv :1170-1273; returns (cbp_u << 8) | cbp_v
-  TBR_HD int enc_rec_intra_uv(const S *ou, const S *ov, int os, S *ru, S *rv, int rfs, int ypos, int xpos, int size, int qp, S *pu, S *pv, int16_t *cqu, int16_t *cqv,
+  TBR_HD TBR_NI int enc_rec_intra_uv(const S *ou, const S *ov, int os, S *ru, S *rv, int rfs, int ypos, int xpos, int size, int qp, S *pu, S *pv, int16_t *cqu, int16_t *cqv,
                               S *rbu, S *rbv, int coeff_type, int tb_split, int intra_mode, int upright, int downleft, const S *pblock_y, const S *rec_y,
                               int rec_stride2) {
     const int fast = F.speed > 1;
@@ -513,7 +520,7 @@ template <class S, class B> struct Rdo {
   // encode_block :1340-1514 — evaluates candidate c into W.rec_* / W.cq_*, fills c.cbp_*, returns the bits write_block would emit.
   // (c.cbp_* keep the coded values; the deblocking values (1,1,1 when tb_split, :1494-1497) are applied by commit_block.)
   // ---------------------------------------------------------------------------------------------------------------
-  TBR_HD int encode_block(const BlockInfo &bi, Cand &c) {
+  TBR_HD TBR_NI int encode_block(const BlockInfo &bi, Cand &c) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos, yc = ypos >> 1, xc = xpos >> 1, sizeC = size >> 1;
     const int tb_split = imax(0, c.tb_param), zero_block = c.tb_param == -1;
     c.tb_split = tb_split;
@@ -561,7 +568,7 @@ template <class S, class B> struct Rdo {
   }
 
   // cost_calc :916-926 (sub = 1)
-  TBR_HD uint32_t cost_calc(const BlockInfo &bi, int width, int height, int nbits) {
+  TBR_HD TBR_NI uint32_t cost_calc(const BlockInfo &bi, int width, int height, int nbits) {
     const int size = bi.size, yc = bi.ypos >> 1, xc = bi.xpos >> 1;
     const S *oy = F.org[0] + bi.ypos * F.org_stride[0] + bi.xpos, *ou = F.org[1] + yc * F.org_stride[1] + xc, *ov = F.org[2] + yc * F.org_stride[1] + xc;
     const uint64_t ssd = be.ssd(oy, F.org_stride[0], W.rec_y, size, width, height) + be.ssd(ou, F.org_stride[1], W.rec_u, size >> 1, width >> 1, height >> 1) +
@@ -572,7 +579,7 @@ template <class S, class B> struct Rdo {
   }
 
   // copy_best_parameters :1615-1677
-  TBR_HD void copy_best(BlockInfo &bi, const Cand &c) {
+  TBR_HD TBR_NI void copy_best(BlockInfo &bi, const Cand &c) {
     const int size = bi.size, sc = size >> 1;
     be.copy(W.best_y, size, W.rec_y, size, size, size);
     be.copy(W.best_u, sc, W.rec_u, sc, sc, sc);
@@ -602,7 +609,7 @@ template <class S, class B> struct Rdo {
   // searches
   // ---------------------------------------------------------------------------------------------------------------
   // search_inter_prediction_params :1033-1098.  org: block origin (pitch os), ref_idx selects the frame; candidates = W.mvcand[cand_ref]
-  TBR_HD int search_inter(const S *org, int os, int ref_idx, const BlockInfo &bi, Mv mvc, Mv mvp, Mv *mv_arr, int part, int sign, int cand_ref) {
+  TBR_HD TBR_NI int search_inter(const S *org, int os, int ref_idx, const BlockInfo &bi, Mv mvc, Mv mvp, Mv *mv_arr, int part, int sign, int cand_ref) {
     const int size = bi.size, rs = F.ref_stride[0];
     const S *ref = F.ref[ref_idx][0] + bi.ypos * rs + bi.xpos;
     Mv mvp2 = mvp, mv;
@@ -638,7 +645,7 @@ template <class S, class B> struct Rdo {
   }
 
   // search_intra_prediction_params :928-1031 (SAD-based; order DC, HOR, VER, PLANAR, then the six angular modes)
-  TBR_HD int search_intra(const BlockInfo &bi, int *intra_mode) {
+  TBR_HD TBR_NI int search_intra(const BlockInfo &bi, int *intra_mode) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos;
     const int ur = upright_available(ypos, xpos, size, size, F.width, F.height, F.sb_size), dl = downleft_available(ypos, xpos, size, size, F.width, F.height, F.sb_size);
     const S *oy = F.org[0] + ypos * F.org_stride[0] + xpos;
@@ -658,14 +665,14 @@ template <class S, class B> struct Rdo {
   }
 
   // search_bipred_prediction_params :1679-1833
-  TBR_HD int search_bipred(const BlockInfo &bi, int part, const Mv *mv_center, Mv mvp, int *ref_idx0, int *ref_idx1, Mv *mv_arr0, Mv *mv_arr1, int me_mode) {
+  TBR_HD TBR_NI int search_bipred(const BlockInfo &bi, int part, const Mv *mv_center, Mv mvp, int *ref_idx0, int *ref_idx1, Mv *mv_arr0, Mv *mv_arr1, int me_mode) {
     const int size = bi.size;
     const S *oy = F.org[0] + bi.ypos * F.org_stride[0] + bi.xpos;
     if (me_mode) {
       const int r0 = F.interp_ref ? 1 : 0, r1 = F.interp_ref ? 2 : 1, rs = F.ref_stride[0];
       const S *ref0 = F.ref[r0][0] + bi.ypos * rs + bi.xpos, *ref1 = F.ref[r1][0] + bi.ypos * rs + bi.xpos;
       Mv mv;
-      const int sad = be.me_bi(oy, F.org_stride[0], ref0, ref1, rs, size, &mv, mv_center[r0], mvp, F.sqrt_lambda, 0, bi.xpos, bi.ypos, W.mvcand[r0], W.mvcand_num[r0]);
+      const int sad = be.me_bi(oy, F.org_stride[0], ref0, ref1, rs, size, &mv, mv_center[r0], mvp, F.sqrt_lambda, 0, bi.xpos, bi.ypos, W.mvcand[r0], W.mvcand_num[r0], W.p0_y, W.p1_y);
       // motion_estimate_bi scribbles on the caller's list (:873-881): entries num..3 are zeroed, [4] = mvp (quarter-pel, sic), [5] = 0; the
       // list length is unchanged, so entries 4 and 5 stay visible to every later search of this super block once the list is that long
       for (int idx = W.mvcand_num[r0]; idx < 4; idx++) { W.mvcand[r0][idx].x = 0; W.mvcand[r0][idx].y = 0; }
@@ -711,7 +718,7 @@ template <class S, class B> struct Rdo {
   // ---------------------------------------------------------------------------------------------------------------
   TBR_HD void cand_group_begin() { cidx = 0; loc_idx = 0x7fffffff; loc_cost = MAX_U32; loc_worst = 0; loc_bestc = MAX_U32; }
   // candidate number cidx of the current group: evaluated by the warp that owns it; track_range: also the worst / best cost (:1998-1999)
-  TBR_HD void try_cand(BlockInfo &bi, Cand &c, int w, int h, bool track_range = false) {
+  TBR_HD TBR_NI void try_cand(BlockInfo &bi, Cand &c, int w, int h, bool track_range = false) {
     const int my = cidx++;
     if (!be.mine(my)) return;
     const int nbits = encode_block(bi, c);
@@ -731,7 +738,7 @@ template <class S, class B> struct Rdo {
     c.skip_idx = idx; c.ref_idx0 = p.ref_idx0; c.ref_idx1 = p.ref_idx1; c.mv0[0] = p.mv0; c.mv1[0] = p.mv1; c.dir = p.bipred_flag;
   }
 
-  TBR_HD uint32_t mode_decision_serial(BlockInfo &bi, int *owner) {
+  TBR_HD TBR_NI uint32_t mode_decision_serial(BlockInfo &bi, int *owner) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos;
     const int rectangular = bi.bwidth != size || bi.bheight != size;
     const int intra_inter_sad = F.speed > 0;
@@ -881,14 +888,14 @@ template <class S, class B> struct Rdo {
 
 
   // candidate `idx` (its position in the reference's evaluation order) evaluated by whichever warp calls this; the warp keeps its best (cost, idx)
-  TBR_HD void eval_cand(BlockInfo &bi, Cand &c, int w, int h, int idx, bool track_range) {
+  TBR_HD TBR_NI void eval_cand(BlockInfo &bi, Cand &c, int w, int h, int idx, bool track_range) {
     const int nbits = encode_block(bi, c);
     const uint32_t cost = cost_calc(bi, w, h, nbits);
     if (track_range) { loc_worst = loc_worst > cost ? loc_worst : cost; loc_bestc = loc_bestc < cost ? loc_bestc : cost; }
     if (cost < loc_cost || (cost == loc_cost && idx < loc_idx)) { loc_cost = cost; loc_idx = idx; copy_best(bi, c); }
   }
   // one item of the intra-mode search (:2080-2097 with intra_rdo, else search_intra_prediction_params): the warp keeps its best (cost, k)
-  TBR_HD void intra_search_item(BlockInfo &bi, Cand &t, int k, uint32_t *best_cost, int *best_k) {
+  TBR_HD TBR_NI void intra_search_item(BlockInfo &bi, Cand &t, int k, uint32_t *best_cost, int *best_k) {
     if (F.intra_rdo) {
       t.intra_mode = k / bi.max_tb; t.tb_param = k % bi.max_tb; t.mode = MODE_INTRA;
       const int nbits = encode_block(bi, t);
@@ -909,9 +916,10 @@ template <class S, class B> struct Rdo {
   // Every candidate keeps the index it has in the reference's evaluation order, so the winner = min (cost, index) is the reference's
   // "first candidate with the strictly smallest cost" whichever warp evaluated what.  The candidate lists the chain extends are copied to
   // the other warps' replicas afterwards.
-  TBR_HD uint32_t mode_decision_overlap(BlockInfo &bi, int *owner) {
+  TBR_HD TBR_NI uint32_t mode_decision_overlap(BlockInfo &bi, int *owner) {
     const int size = bi.size, ypos = bi.ypos, xpos = bi.xpos, nw = be.nwarps();
     be.queue_reset();
+    be.mark2(-1);
     cand_group_begin();
     Cand t;
     t.mode = MODE_SKIP; t.intra_mode = 0; t.skip_idx = 0; t.pb_part = PART_NONE; t.ref_idx0 = t.ref_idx1 = 0; t.dir = 0; t.cbp_y = t.cbp_u = t.cbp_v = 0; t.tb_param = 0; t.tb_split = 0;
@@ -961,9 +969,12 @@ template <class S, class B> struct Rdo {
       sad_inter_r[ref_idx] = sad_inter;
       be.put_me(ref_idx, &mv_all[ref_idx][0][0], sad_inter);
     }
+    be.mark2(0);  // (diagnostics) own searches done
     if (be.warp() >= nrs)
       for (int k; (k = be.next(1)) < n_isearch;) intra_search_item(bi, t, k, &my_icost, &my_ik);
+    be.mark2(1);  // intra items taken while the searches run
     be.cta_sync();
+    be.mark2(2);  // wait for the slowest warp of the phase
     for (int ref_idx = min_idx; ref_idx <= max_idx; ref_idx++) {
       if (be.mine(ref_idx - min_idx)) continue;
       be.get_me(ref_idx, &mv_all[ref_idx][0][0], &sad_inter_r[ref_idx]);
@@ -1048,7 +1059,7 @@ template <class S, class B> struct Rdo {
     const double fql = (double)(1 << shift2) / (double)gquant[qp % 6];
     return (int)(rel * fql);
   }
-  TBR_HD int check_early_skip_block(const BlockInfo &bi, const Cand &c) {
+  TBR_HD TBR_NI int check_early_skip_block(const BlockInfo &bi, const Cand &c) {
     const int size = bi.size, size0 = imin(size, EARLY_SKIP_BLOCK), size0c = size0 >> 1;
     float thr = F.early_skip_thr;
     if (F.speed > 1 && size == F.sb_size) thr += thr / 4;
@@ -1076,7 +1087,7 @@ template <class S, class B> struct Rdo {
     return !significant;
   }
   // :2352-2392.  Skip candidate k (its early-skip test and, if it passes, its RD cost) on warp k mod NW
-  TBR_HD int search_early_skip(BlockInfo &bi, uint32_t *cost, int *owner) {
+  TBR_HD TBR_NI int search_early_skip(BlockInfo &bi, uint32_t *cost, int *owner) {
     int flag = 0;
     Cand t;
     t.intra_mode = 0; t.pb_part = PART_NONE; t.cbp_y = t.cbp_u = t.cbp_v = 0; t.tb_split = 0;
@@ -1102,7 +1113,7 @@ template <class S, class B> struct Rdo {
   // ---------------------------------------------------------------------------------------------------------------
   // Only warp `owner` (the one whose scratch holds the winning blocks) stores; every warp advances the leaf / coefficient counters; the CTA
   // barrier at the end publishes the block to the other warps (and, through the row's progress counter, to the other CTAs).
-  TBR_HD void commit_block(const BlockInfo &bi, uint32_t cost, int owner, const S *by, const S *bu, const S *bv, const int16_t *qy, const int16_t *qu, const int16_t *qv) {
+  TBR_HD TBR_NI void commit_block(const BlockInfo &bi, uint32_t cost, int owner, const S *by, const S *bu, const S *bv, const int16_t *qy, const int16_t *qu, const int16_t *qv) {
     const int size = bi.size, sc = size >> 1, bw = bi.bwidth, bh = bi.bheight;
     const Cand &b = bi.best;
     const bool has_coeff = b.mode != MODE_SKIP && (b.cbp_y || b.cbp_u || b.cbp_v);
