@@ -423,10 +423,13 @@ def run_gpu(args, cfg):
                      # block, wavefront between super blocks); what bounds it is single-warp latency, see `binding`
                      "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "unit": "GB/s", "frac": round(achieved / peak, 5),
-                     "traffic": int(tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
-                     "binding": "latency of the serial decision chain (per-warp dependent issue; frames are L2-resident)",
+                     # DRAM bytes of this launch, scaled per super block from the committed ncu capture of the same kernel on a smaller batch (profiles/ncu_traffic.json)
+                     "traffic": int(tr["dram_bytes_total"] / tr["super_blocks"] * st["super_blocks"]) if tr and tr.get("super_blocks") else None,
+                     "traffic_source": tr.get("capture") if tr else None,
+                     "binding": "instruction delivery (ncu: ~19 stalled warps per issued instruction wait for instructions; issue slots 4 % busy; DRAM 0.1 %, L2 2 % of peak): "
+                                "a serial decision chain per super block run by one 8-warp CTA whose code streams from L2",
                      "cta_busy_frac": round(busy, 4), "algorithmic_bytes": int(alg_bytes), "ms_per_launch": round(ms, 2), "share_of_step": 1.0,
-                     "ncu": {k: tr[k] for k in tr if k.endswith("_pct")} if tr else None,
+                     "ncu": {k: tr[k] for k in tr if k.endswith("_pct") or k.startswith("stalled_")} if tr else None,
                      "work": {k: st[k] for k in STAT_NAMES[11:23]},
                      "cycles_share": {k[4:]: round(st[k] / max(1, st["cyc_total"]), 4) for k in STAT_NAMES[:10] + STAT_NAMES[23:40]},
                      "phase_share_of_a_super_block": {k[3:]: round(st[k] / max(1, sum(st[n] for n in STAT_NAMES[40:])), 4) for k in STAT_NAMES[40:]}},
