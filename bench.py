@@ -432,7 +432,8 @@ def run_gpu(args, cfg):
                      "ncu": {k: tr[k] for k in tr if k.endswith("_pct") or k.startswith("stalled_")} if tr else None,
                      "work": {k: st[k] for k in STAT_NAMES[11:23]},
                      "cycles_share": {k[4:]: round(st[k] / max(1, st["cyc_total"]), 4) for k in STAT_NAMES[:10] + STAT_NAMES[23:40]},
-                     "phase_share_of_a_super_block": {k[3:]: round(st[k] / max(1, sum(st[n] for n in STAT_NAMES[40:])), 4) for k in STAT_NAMES[40:]}},
+                     "phase_share_of_a_super_block": {k[3:]: round(st[k] / max(1, sum(st[n] for n in STAT_NAMES[40:49])), 4) for k in STAT_NAMES[40:49]},
+                     "small_search_stage_share": {k[9:]: round(st[k] / max(1, sum(st[n] for n in STAT_NAMES[49:54])), 4) for k in STAT_NAMES[49:54]}},
         "single_stream_reference": meta,
     }
     if world > 1:

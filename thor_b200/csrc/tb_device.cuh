@@ -51,6 +51,9 @@
 #ifndef TB_SAD_ROWS
 #define TB_SAD_ROWS 0
 #endif
+#ifndef TB_ROLL
+#define TB_ROLL  // tb_rdo.cu: "#pragma unroll 1" on the simple per-sample loops (its kernel is bound by instruction fetch)
+#endif
 #ifndef TB_ME_STAGE_PROF
 #define TB_ME_STAGE_PROF 0
 #endif
@@ -299,6 +302,7 @@ __device__ __forceinline__ uint32_t multi_sad(const S *o, int os, const S *r, in
 template <class S> __device__ __forceinline__ uint64_t warp_ssd(const S *a, int as, const S *b, int bs, int w, int h) {
   uint64_t acc = 0;
   const int lw = ilog2(w);
+  TB_ROLL
   for (int p = lane_id(); p < (h << lw); p += 32) {
     int row = p >> lw, col = p & (w - 1);
     int d = (int)a[row * as + col] - (int)b[row * bs + col];
@@ -2200,20 +2204,24 @@ __device__ void warp_make_top_and_left(S *left, S *top, S &top_left, const S *re
   const int leftlen = downleft ? size + 1 : size, toplen = upright ? size + 1 : size;
   S tl = mid;
   if (ypos + i == 0) {
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) top[k] = mid;
   } else {
     const S *src = (i == 0) ? rec_frame - fstride + j : rblock - rbstride;
     S val = TB_LDF(src + toplen - 1);
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) top[k] = k < toplen ? TB_LDF(src + k) : (k >= size ? val : TB_LDF(src + k));
     if (xpos > 0) tl = (i == 0) ? TB_LDF(rec_frame - fstride + j - 1) : ((j > 0) ? TB_LDF(rblock - rbstride - 1) : TB_LDF(rec_frame + (i - 1) * fstride - 1));
     else tl = TB_LDF(src);
   }
   if (xpos + j == 0) {
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) left[k] = mid;
   } else {
     const S *base = (j == 0) ? rec_frame + i * fstride - 1 : rblock - 1;
     const int st = (j == 0) ? fstride : rbstride;
     S val = TB_LDF(base + (leftlen - 1) * st);
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) left[k] = k < leftlen ? TB_LDF(base + k * st) : (k >= size ? val : TB_LDF(base + k * st));
   }
   __syncwarp();
@@ -2240,15 +2248,19 @@ __device__ void warp_intra_pred(const S *left, const S *top, S top_left, int ypo
   int tlF = 0, dc = 0;
   int16_t ptlF = 0;
   if (mode == 4 || mode == 7 || mode == 8) {
+    TB_ROLL
     for (int k = lane; k < size; k += 32) { tF[k] = (S)f121<S>(top, k, size); lF[k] = (S)f121<S>(left, k, size); }
     tlF = (int)(S)((2 * (int)top_left + left[0] + top[0] + 2) >> 2);
   } else if (mode == 5 || mode == 6) {
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) tF[k] = (S)f121<S>(top, k, 2 * size);
   } else if (mode == 9) {
+    TB_ROLL
     for (int k = lane; k < 2 * size; k += 32) lF[k] = (S)f121<S>(left, k, 2 * size);
   } else if (mode == 0) {
     const S *l = xpos != 0 ? left : top, *t = ypos != 0 ? top : left;
     unsigned sum = 0;
+    TB_ROLL
     for (int k = lane; k < size; k += 32) sum += (unsigned)t[k] + (unsigned)l[k];
     sum = warp_sum(sum);
     dc = (int)((sum + (unsigned)size) / (2u * (unsigned)size));
@@ -2256,6 +2268,7 @@ __device__ void warp_intra_pred(const S *left, const S *top, S top_left, int ypo
     ptlF = (int16_t)(left[1] + 2 * left[0] + 2 * (int)top_left + 2 * top[0] + top[1]);
   }
   __syncwarp();
+  TB_ROLL
   for (int p = lane; p < size * size; p += 32) {
     int i = p >> ls, j = p & (size - 1), v, d;
     switch (mode) {
@@ -2293,6 +2306,7 @@ __device__ void warp_intra_pred(const S *left, const S *top, S top_left, int ypo
 template <class S> __device__ void warp_cfl(const S *y, S *u, S *v, const S *ry, int n, int cstride, int stride, int sub, int bitdepth) {
   const int lane = lane_id(), nc = n >> sub, lognc = ilog2(nc), cs = cstride >> sub, maxv = (1 << bitdepth) - 1, ln = ilog2(n);
   int64_t sq = 0;
+  TB_ROLL
   for (int p = lane; p < n * n; p += 32) {
     int i = p >> ln, j = p & (n - 1);
     int d = (int)ry[i * stride + j] - (int)y[i * n + j];
@@ -2301,6 +2315,7 @@ template <class S> __device__ void warp_cfl(const S *y, S *u, S *v, const S *ry,
   sq = (int64_t)warp_sum64((uint64_t)sq);
   if ((sq >> (2 * ln)) <= (64 << 2 * (bitdepth - 8))) return;
   int64_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ysum usum vsum yy yu yv uu vv
+  TB_ROLL
   for (int p = lane; p < nc * nc; p += 32) {
     int i = p >> lognc, j = p & (nc - 1);
     int us = u[i * cs + j], vs = v[i * cs + j];
@@ -2327,6 +2342,7 @@ template <class S> __device__ void warp_cfl(const S *y, S *u, S *v, const S *ry,
     int64_t bb = b64 + (1 << 15);
     int64_t lo = -((int64_t)1 << 31), hi = ((int64_t)1 << 31) - 1;
     int32_t b = (int32_t)(bb < lo ? lo : (bb > hi ? hi : bb));
+    TB_ROLL
     for (int p = lane; p < nc * nc; p += 32) {
       int i = p >> lognc, j = p & (nc - 1);
       int out;

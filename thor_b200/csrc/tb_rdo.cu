@@ -16,6 +16,7 @@
 // The device code of this unit lives in its own namespace (the headers define __constant__ tables).
 #define TB_LDG(p) (*(p))
 #define TB_LDF(p) __ldcg(p)
+#define TB_ROLL _Pragma("unroll 1")  // loops stay loops: the kernel is bound by instruction fetch, not by loop overhead
 #define TB_ME_STAGE_PROF 1  // cycles per search stage (telescope, candidates, hexagon, half-pel, quarter-pel) of blocks <= 16 in the kernel's counters
 #ifndef TB_SAD_ROWS
 #define TB_SAD_ROWS 1  // integer-position SADs of blocks >= 32 bytes wide: lanes along the row (multi_sad_rows)
@@ -140,9 +141,11 @@ template <class S> struct DevBackend {
   __device__ __noinline__ void bcast(void *p, int nbytes, int owner) const {  // p: per-thread (replicated) object, multiple of 4 bytes, <= 128
     int *q = (int *)p;
     if (wid == owner && (threadIdx.x & 31) == 0)
+      TB_ROLL
       for (int k = 0; k < nbytes / 4; k++) cta->x_buf[k] = q[k];
     __syncthreads();
     if (wid != owner)
+      TB_ROLL
       for (int k = 0; k < nbytes / 4; k++) q[k] = cta->x_buf[k];
     __syncthreads();
   }
@@ -192,6 +195,7 @@ template <class S> struct DevBackend {
       split_mv(mv.x, mv.y, sign, chroma ? 3 : 2, pw, ph, xpos, ypos, w, h, hi, vi, xf, yf);
       const S *ip = ref + vi * rs + hi;
       const int maxv = (1 << F->bitdepth) - 1;
+      TB_ROLL
       for (int p = lane(); p < w * h; p += 32) {
         const int row = p / w, col = p - row * w;
         const S *q = ip + row * rs + col;
@@ -213,6 +217,7 @@ template <class S> struct DevBackend {
   __device__ __noinline__ void avg(S *dst, const S *a, const S *b, int stride, int w, int h) const {
     PROF(PF_COPY);
     sync();
+    TB_ROLL
     for (int p = lane(); p < w * h; p += 32) {
       const int row = p / w, col = p - row * w, o = row * stride + col;
       dst[o] = (S)(((int)a[o] + (int)b[o]) >> 1);
@@ -223,6 +228,7 @@ template <class S> struct DevBackend {
     PROF(PF_COPY);
     const int maxv = (1 << F->bitdepth) - 1, ls = ilog2(size);
     sync();
+    TB_ROLL
     for (int p = lane(); p < size * size; p += 32) {
       const int row = p >> ls, col = p & (size - 1);
       dst[p] = (S)sat_px(2 * (int)org[row * os + col] - (int)pred[p], maxv);
@@ -232,6 +238,7 @@ template <class S> struct DevBackend {
   __device__ __noinline__ void copy(S *dst, int ds, const S *src, int ss, int w, int h) const {
     PROF(PF_COPY);
     sync();
+    TB_ROLL
     for (int p = lane(); p < w * h; p += 32) {
       const int row = p / w, col = p - row * w;
       dst[row * ds + col] = src[row * ss + col];
@@ -241,6 +248,7 @@ template <class S> struct DevBackend {
   __device__ __noinline__ void copy_coeff(int16_t *dst, const int16_t *src) const {
     PROF(PF_COPY);
     sync();
+    TB_ROLL
     for (int p = lane(); p < 1024 / 4; p += 32) ((uint2 *)dst)[p] = ((const uint2 *)src)[p];
     sync();
   }
@@ -291,6 +299,7 @@ template <class S> struct DevBackend {
     PROF2(PF_TX, ST_TX_SZ + ilog2(jobs[0].size) - 2);
     const int l = lane();
     if (l == 0)
+      TB_ROLL
       for (int k = 0; k < n; k++) { sh->prof[ST_TX] += 1; sh->prof[ST_TX_SAMPLES] += 3 * jobs[k].size * jobs[k].size; }
     int16_t *A = sh->sc.in, *B = sh->sc.in + 768;  // 12 tiles of 64 each
     // chain parameters in shared memory (per warp): the loops index them by chain
@@ -300,6 +309,7 @@ template <class S> struct DevBackend {
     sync();
     const int bd = F->bitdepth, maxv = (1 << bd) - 1;
     // (1) residual -> A[k][i * N + j]
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63;
       const tbr::TxJob<S> &q = J[k];
@@ -308,12 +318,14 @@ template <class S> struct DevBackend {
     }
     sync();
     // (2) forward, first dimension: B[k][i][j] = (sum_t M[i][t] * A[k][j][t] + add1) >> shift1
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
       if (e < N * N) {
         const int i = e >> ln, j = e & (N - 1);
         const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0) + (i << ln), *a = A + (k << 6) + (j << ln);
         int sum = 0;
+        TB_ROLL
         for (int t = 0; t < N; t++) sum += (int)M[t] * (int)a[t];
         const int shift1 = ln + bd - 8;
         B[w] = (int16_t)((sum + (1 << (shift1 - 1))) >> shift1);
@@ -321,6 +333,7 @@ template <class S> struct DevBackend {
     }
     sync();
     // (3) forward, second dimension: A[k][i][j] = (sum_t M[i][t] * B[k][j][t] + add2) >> shift2   (coefficients, raster)
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
       int v = 0;
@@ -328,6 +341,7 @@ template <class S> struct DevBackend {
         const int i = e >> ln, j = e & (N - 1);
         const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0) + (i << ln), *b = B + (k << 6) + (j << ln);
         int sum = 0;
+        TB_ROLL
         for (int t = 0; t < N; t++) sum += (int)M[t] * (int)b[t];
         const int shift2 = ln + 5;
         v = (sum + (1 << (shift2 - 1))) >> shift2;
@@ -336,6 +350,7 @@ template <class S> struct DevBackend {
     }
     sync();
     // (4) zig-zag scan order -> B[k][pos]
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
       if (e < N * N) B[(k << 6) + zigzag_index(e >> ln, e & (N - 1), N)] = A[w];
@@ -357,6 +372,7 @@ template <class S> struct DevBackend {
       const int last_pos = level ? pos + 1 : pos;
       const int off0 = (intra ? 102 : 51) << (shift2 - 8), off1 = (intra ? 115 : 90) << (shift2 - 8);
       int level_mode = 1;
+      TB_ROLL
       for (pos = 0; pos <= last_pos; pos++) {
         const int c = sc_[pos];
         const unsigned ac = (unsigned)scale * (unsigned)iabs(c);
@@ -367,11 +383,13 @@ template <class S> struct DevBackend {
         if (level_mode) { if (lev == 0) level_mode = 0; }
         else if (lev > 1) level_mode = 1;
       }
+      TB_ROLL
       for (pos = last_pos + 1; pos < nq; pos++) sc_[pos] = 0;
     }
     sync();
     const unsigned nzmask = __ballot_sync(FULL, cbp != 0);
     // (6) quantised coefficients, raster: to the caller's buffer (reference layout) and, dequantised, to A[k] (dequantize(), common/common_block.c:45)
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63;
       const tbr::TxJob<S> &q = J[k];
@@ -385,12 +403,14 @@ template <class S> struct DevBackend {
     }
     sync();
     // (7) inverse, first dimension: B[k][i][j] = sat16((sum_t M[t][j] * A[k][t][i] + 64) >> 7)
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63, N = J[k].size, ln = N == 8 ? 3 : 2;
       if (e < N * N && ((nzmask >> k) & 1)) {
         const int i = e >> ln, j = e & (N - 1);
         const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0), *a = A + (k << 6);
         int o = 0;
+        TB_ROLL
         for (int t = 0; t < N; t++) o += (int)M[(t << ln) + j] * (int)a[(t << ln) + i];
         o = (o + 64) >> 7;
         B[w] = (int16_t)iclip(o, -32768, 32767);
@@ -398,6 +418,7 @@ template <class S> struct DevBackend {
     }
     sync();
     // (8) inverse, second dimension + reconstruction: rec = clip(pred + sat16((sum_t M[t][j] * B[k][t][i] + round) >> (20 - bitdepth))); no coefficient: rec = pred
+    TB_ROLL
     for (int w = l; w < n * 64; w += 32) {
       const int k = w >> 6, e = w & 63;
       const tbr::TxJob<S> &q = J[k];
@@ -408,6 +429,7 @@ template <class S> struct DevBackend {
         if ((nzmask >> k) & 1) {
           const int16_t *M = cta->tab16 + (N == 8 ? 16 : 0), *b = B + (k << 6);
           int o = 0;
+          TB_ROLL
           for (int t = 0; t < N; t++) o += (int)M[(t << ln) + j] * (int)b[(t << ln) + i];
           const int sh2 = 20 - bd;
           o = (o + (1 << (sh2 - 1))) >> sh2;
@@ -423,6 +445,7 @@ template <class S> struct DevBackend {
     PROF(PF_BITS);
     const int qs = min(size, 16), nq = qs * qs, lq = ilog2(qs);
     sync();
+    TB_ROLL
     for (int p = lane(); p < nq; p += 32) sh->out16[zigzag_index(p >> lq, p & (qs - 1), qs)] = cq[p];
     sync();
     const int bits = warp_coeff_bits(sh->out16, nq, size, type);
@@ -435,6 +458,7 @@ template <class S> struct DevBackend {
     sync();
     if (!(w & (w - 1))) return warp_ssd<S>(a, as, b, bs, w, h);
     uint64_t acc = 0;
+    TB_ROLL
     for (int p = lane(); p < w * h; p += 32) {
       const int row = p / w, col = p - row * w, d = (int)a[row * as + col] - (int)b[row * bs + col];
       acc += (uint64_t)(uint32_t)(d * d);
@@ -489,6 +513,7 @@ template <class S> struct DevBackend {
     PROF(PF_ES);
     const int s2 = size / 2, l2 = ilog2(s2);
     sync();
+    TB_ROLL
     for (int p = lane(); p < s2 * s2; p += 32) {
       const int i = p >> l2, j = p & (s2 - 1);
       int sum = 2;
@@ -501,6 +526,7 @@ template <class S> struct DevBackend {
     sync();
     warp_fwd_transform(sh->blk16, s2, s2, 0, F->bitdepth, sh->sc, sh->out16, cta->tab16);
     int hit = 0;
+    TB_ROLL
     for (int p = lane(); p < s2 * s2; p += 32) hit |= iabs((int)sh->out16[p]) > threshold;
     hit = __any_sync(FULL, hit);
     sync();
@@ -511,6 +537,7 @@ template <class S> struct DevBackend {
     PROF(PF_ES);
     const int ls = ilog2(size);
     sync();
+    TB_ROLL
     for (int p = lane(); p < size * size; p += 32) {
       const int i = p >> ls, j = p & (size - 1);
       sh->blk16[p] = (int16_t)((int)orig[i * os + j] - (int)pred[i * ps + j]);
@@ -522,6 +549,7 @@ template <class S> struct DevBackend {
   }
   __device__ __noinline__ void store_blk(tb_rdo_blk_t *blk, int stride, int by, int bx, int nbw, int nbh, int div, tb_rdo_blk_t v, const Mv *mv0, const Mv *mv1) const {
     sync();
+    TB_ROLL
     for (int p = lane(); p < nbw * nbh; p += 32) {
       const int m = p / nbw, n = p - m * nbw;
       const int m0 = div > 0 ? m / div : 0, n0 = div > 0 ? n / div : 0, index = 2 * m0 + n0;
@@ -534,6 +562,7 @@ template <class S> struct DevBackend {
   __device__ __noinline__ void pack_coeff(int16_t *dst, const int16_t *q, int size, int tb_split, int nonzero) const {
     const int t = tb_split ? size / 2 : size, qs = t < 16 ? t : 16, n = tb_split ? 4 : 1, nq = qs * qs;
     sync();
+    TB_ROLL
     for (int p = lane(); p < n * nq; p += 32) {
       const int k = p / nq, i = p - k * nq;
       dst[p] = nonzero ? q[k * 256 + i] : (int16_t)0;

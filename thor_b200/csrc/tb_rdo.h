@@ -383,7 +383,8 @@ template <class S, class B> struct Rdo {
   // prediction
   // ---------------------------------------------------------------------------------------------------------------
   // get_inter_prediction_yuv, common/inter_prediction.c:185-233: pitch of the compact blocks = pos_size (block_pos->size)
-  TBR_HD TBR_NI void inter_pred_yuv(int ref_idx, S *py, S *pu, S *pv, int ypos, int xpos, int pos_size, int pbw, int pbh, const Mv *mv_arr, int sign, int split) {
+  // luma_only: search_bipred_prediction_params (:1768) predicts all three planes but reads only the luma block; the chroma predictions have no effect
+  TBR_HD TBR_NI void inter_pred_yuv(int ref_idx, S *py, S *pu, S *pv, int ypos, int xpos, int pos_size, int pbw, int pbh, const Mv *mv_arr, int sign, int split, int luma_only = 0) {
     const int div = split + 1, bw = pbw / div, bh = pbh / div, pst = pos_size, rsy = F.ref_stride[0], rsc = F.ref_stride[1];
     const int yc = ypos >> 1, xc = xpos >> 1;
     const S *ry = F.ref[ref_idx][0] + ypos * rsy + xpos, *ru = F.ref[ref_idx][1] + yc * rsc + xc, *rv = F.ref[ref_idx][2] + yc * rsc + xc;
@@ -394,6 +395,7 @@ template <class S, class B> struct Rdo {
       Mv mv = mv_arr[index];
       be.clip_mv(mv, ypos, xpos, F.width, F.height, bw, bh, sign);
       be.interp_luma(py + opy, pst, ry + ory, rsy, bw, bh, mv, sign, F.enable_bipred, F.width, F.height, xpos, ypos);
+      if (luma_only) continue;
       be.interp_chroma(pu + opc, pst >> 1, ru + orc, rsc, bw >> 1, bh >> 1, mv, sign, F.width >> 1, F.height >> 1, xc, yc);
       be.interp_chroma(pv + opc, pst >> 1, rv + orc, rsc, bw >> 1, bh >> 1, mv, sign, F.width >> 1, F.height >> 1, xc, yc);
     }
@@ -691,7 +693,7 @@ template <class S, class B> struct Rdo {
       for (int list = 1; list >= stop; list--) {
         const Mv mv = list ? min0[0] : min1[0];
         int ref_idx = list ? min_ref_idx0 : min_ref_idx1;
-        inter_pred_yuv(ref_idx, W.p_y, W.p_u, W.p_v, bi.ypos, bi.xpos, bi.size, bi.bwidth, bi.bheight, list ? min0 : min1, F.ref_sign[ref_idx], part > 0);
+        inter_pred_yuv(ref_idx, W.p_y, W.p_u, W.p_v, bi.ypos, bi.xpos, bi.size, bi.bwidth, bi.bheight, list ? min0 : min1, F.ref_sign[ref_idx], part > 0, 1);
         be.sat2ab(W.org8, oy, F.org_stride[0], W.p_y, size);
         int ref_start, ref_end;
         if (F.frame_type == P_FRAME) { ref_start = 0; ref_end = F.num_ref - 1; }
