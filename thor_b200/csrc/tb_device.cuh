@@ -159,9 +159,11 @@ __device__ __forceinline__ uint32_t sad_partial(const S *o, int os, const S *r, 
   }
 #endif
   uint32_t acc = 0;
+  TB_ROLL
   for (int row = sub; row < h; row += nl) {
     const uint32_t *q = rq + row * rsw, *a = oq + row * osw;
     uint32_t prev = TB_LDG(q);
+    TB_ROLL
     for (int c = 0; c < ww; c++) {
       uint32_t nxt = TB_LDG(q + c + 1);
       acc += word_sad<S>(TB_LDG(a + c), __funnelshift_r(prev, nxt, sh));
@@ -266,7 +268,9 @@ __device__ __noinline__ uint32_t multi_sad_rows(const S *o, int os, const S *r, 
     }
     const int rsw = (rs * (int)sizeof(S)) >> 2;
     uint32_t acc[CH] = {0, 0, 0, 0, 0};
+    TB_ROLL
     for (int row = rsub; row < h; row += RP) {
+      TB_ROLL
       for (int ci = 0; ci < CI; ci++) {
         const int col = col0 + ci * 32;
         const uint32_t a = TB_LDG(oq + row * osw + col);
