@@ -431,6 +431,7 @@ __device__ void warp_interp(S *dst, int ds, const S *ref, int rs, int w, int h, 
     warp_interp_strips_u8((uint8_t *)dst, ds, (const uint8_t *)ip, rs, w, h, xf, yf, bip);
     return;
   }
+  TB_ROLL
   for (int p = sub; p < (h << lw); p += nl) {
     int row = p >> lw, col = p & (w - 1);
     const S *q = ip + row * rs + col;

@@ -184,9 +184,11 @@ template <class S, class B> struct Rdo {
   // distributed candidate evaluation: running candidate index and this warp's best so far
   int cidx, loc_idx;
   uint32_t loc_cost, loc_worst, loc_bestc;
+  // the candidate about to be evaluated has the same inter prediction as the previous one of this warp (same vectors, another tb_param): W.p_* is still valid
+  bool reuse_pred;
 
   TBR_HD Rdo(FrameCtx<S> &f, Work<S> &w, Work<S> &w0, B &b)
-      : F(f), W(w), W0(w0), be(b), best_ref(-1), sb_index(0), n_leaves(0), coeff_used(0), cidx(0), loc_idx(0), loc_cost(MAX_U32), loc_worst(0), loc_bestc(MAX_U32) {}
+      : F(f), W(w), W0(w0), be(b), best_ref(-1), sb_index(0), n_leaves(0), coeff_used(0), cidx(0), loc_idx(0), loc_cost(MAX_U32), loc_worst(0), loc_bestc(MAX_U32), reuse_pred(false) {}
 
   // ---------------------------------------------------------------------------------------------------------------
   // neighbour state
@@ -536,7 +538,7 @@ template <class S, class B> struct Rdo {
                                       tb_split && sizeC > 4, c.intra_mode, ur, dl, F.cfl_intra ? W.p_y : (const S *)nullptr, W.rec_y, size);
       c.cbp_u = uv >> 8; c.cbp_v = uv & 255;
     } else {
-      predict_inter(bi, c);
+      if (!(reuse_pred && !F.cfl_inter)) predict_inter(bi, c);  // the reference predicts again for every tb_param of the same vectors: identical samples
       if (c.mode == MODE_SKIP || zero_block) {
         be.copy(W.rec_y, size, W.p_y, size, size, size);
         be.copy(W.rec_u, sizeC, W.p_u, sizeC, sizeC, sizeC);
@@ -934,13 +936,17 @@ template <class S, class B> struct Rdo {
       t.mode = MODE_SKIP; t.tb_param = 0; t.pb_part = PART_NONE;
       eval_cand(bi, t, bi.bwidth, bi.bheight, idx, false);
     }
-    for (int k = 0; k < bi.num_merge; k++)
+    for (int k = 0; k < bi.num_merge; k++) {  // the tb_param variants of one merge candidate share its prediction: same warp
+      const bool my = be.mine(bi.num_skip + k);
       for (int tb = 0; tb <= bi.max_tb - 1; tb++, idx++) {
-        if (!be.mine(idx)) continue;
+        if (!my) continue;
         set_from_ipred(t, bi.merge_cand[k], k);
         t.mode = MODE_MERGE; t.tb_param = tb; t.pb_part = PART_NONE;
+        reuse_pred = tb > 0;
         eval_cand(bi, t, size, size, idx, false);
       }
+      reuse_pred = false;
+    }
     be.mark(PH_SKIP_MERGE);
 
     int min_idx = 0;
@@ -1000,7 +1006,8 @@ template <class S, class B> struct Rdo {
       t.pb_part = 0; t.ref_idx0 = r0; t.ref_idx1 = r1; t.dir = 0;
       for (int i = 0; i < 4; i++) { t.mv0[i] = a0[i]; t.mv1[i] = a1[i]; }
       t.mode = MODE_BIPRED;
-      for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; eval_cand(bi, t, size, size, IDX_BIPRED + tb, false); }
+      for (int tb = 0; tb <= bi.max_tb - 1; tb++) { t.tb_param = tb; reuse_pred = tb > 0; eval_cand(bi, t, size, size, IDX_BIPRED + tb, false); }
+      reuse_pred = false;
       if (F.frame_type == B_FRAME) {
         search_bipred(bi, 1, mv_center, mvp, &r0, &r1, a0, a1, 1);
         t.pb_part = PART_NONE; t.ref_idx0 = r0; t.ref_idx1 = r1;
@@ -1010,12 +1017,17 @@ template <class S, class B> struct Rdo {
       }
       be.mark(PH_BIPRED);
     }
-    for (int k; (k = be.next(0)) < n_inter;) {
-      const int tb = k % ntb - 1, part = (k / ntb) % bi.max_pb, ref_idx = min_idx + k / (ntb * bi.max_pb);
+    for (int g; (g = be.next(0)) < nrs * bi.max_pb;) {  // one draw = the tb_param variants of one (reference, partition): they share the prediction
+      const int part = g % bi.max_pb, ref_idx = min_idx + g / bi.max_pb;
       t.ref_idx0 = t.ref_idx1 = ref_idx; t.pb_part = part;
       for (int i = 0; i < 4; i++) t.mv0[i] = t.mv1[i] = mv_all[ref_idx][part][i];
-      t.mode = MODE_INTER; t.dir = 0; t.tb_param = tb;
-      eval_cand(bi, t, size, size, IDX_INTER + k, true);
+      t.mode = MODE_INTER; t.dir = 0;
+      for (int v = 0; v < ntb; v++) {
+        t.tb_param = v - 1;
+        reuse_pred = v > 0;
+        eval_cand(bi, t, size, size, IDX_INTER + g * ntb + v, true);
+      }
+      reuse_pred = false;
     }
     be.mark(PH_INTER_CAND);
     for (int k; (k = be.next(1)) < n_isearch;) intra_search_item(bi, t, k, &my_icost, &my_ik);
