@@ -338,6 +338,13 @@ def run_gpu(args, cfg):
             pin = torch.from_numpy(flat.view(np.uint8 if cfg.ESZ == 1 else np.int16).copy()).pin_memory()
         cost_dev = torch.zeros(sum(j.nsb for j in jobs), dtype=torch.int32, device="cuda")
         scatter_bytes = (world - 1) * src_elems * cfg.ESZ; gather_bytes = (world - 1) * cost_dev.numel() * 4
+        # untimed warm-up of the two collectives (NCCL sets its point-to-point connections up on first use)
+        if rank == 0:
+            dist.scatter(mine_src, [pin.to("cuda", non_blocking=True) for _ in range(world)], src=0)
+            dist.gather(cost_dev, [torch.empty_like(cost_dev) for _ in range(world)], dst=0)
+        else:
+            dist.scatter(mine_src, None, src=0)
+            dist.gather(cost_dev, None, dst=0)
     barrier()
     t0, t1 = ev(), ev()
     c0, c1, c2, c3 = ev(), ev(), ev(), ev()
