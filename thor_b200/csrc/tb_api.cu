@@ -325,7 +325,11 @@ tb_frame_t *tb_frame_create(int width, int height, int pad, int sample_bytes) {
     f->pw[p] = width >> sub; f->ph[p] = height >> sub; f->padh[p] = pad >> sub; f->padv[p] = pad >> sub;
     f->stride[p] = (f->pw[p] + 2 * f->padh[p] + 15) & ~15;
     f->bytes[p] = ((size_t)(f->ph[p] + 2 * f->padv[p]) * f->stride[p] + 64) * sample_bytes;
-    if (cudaMalloc(&f->base[p], f->bytes[p]) != cudaSuccess) { delete f; return nullptr; }
+    if (cudaMalloc(&f->base[p], f->bytes[p]) != cudaSuccess) {
+      for (int q = 0; q < p; q++) cudaFree(f->base[q]);  // the planes already allocated
+      delete f;
+      return nullptr;
+    }
     cudaMemsetAsync(f->base[p], 0, f->bytes[p], g.stream);
     f->origin[p] = (char *)f->base[p] + ((size_t)f->padv[p] * f->stride[p] + f->padh[p]) * sample_bytes;
   }
@@ -374,6 +378,7 @@ void *tb_frame_plane(const tb_frame_t *f, int plane, int *stride) {
 // ---------------------------------------------------------------------------------------------------------------
 int tb_sad_batch(const tb_sad_item_t *items, int n, int sample_bytes, int kind, uint32_t *out, int32_t *out2, uint64_t *out64) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_sad_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   if (sample_bytes == 1) LAUNCH(sad_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, kind, out, out2, out64);
   else LAUNCH(sad_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, kind, out, out2, out64);
@@ -382,6 +387,7 @@ int tb_sad_batch(const tb_sad_item_t *items, int n, int sample_bytes, int kind, 
 int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *cand, int sample_bytes, int bitdepth, int speed, int bip, int fw, int fh,
                              tb_me_result_t *out) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_motion_estimate_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   // stream-ordered scratch: the sorted item list and the scheduler's counters (see me_batch_kernel)
   int *meta = nullptr, *idx = nullptr;
@@ -401,6 +407,7 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
 }
 int tb_motion_estimate_bi_batch(const tb_me_bi_item_t *items, int n, const int16_t *cand, int sample_bytes, int bitdepth, int bip, int fw, int fh, tb_me_result_t *out) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_motion_estimate_bi_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   if (sample_bytes == 1) LAUNCH(me_bi_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, bip, fw, fh, out);
   else LAUNCH(me_bi_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, 0, items, n, cand, bitdepth, bip, fw, fh, out);
@@ -420,6 +427,7 @@ int tb_me_set_stats(uint64_t *stats_dev) {
 }
 int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int bitdepth, int bipred) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_interp_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   if (sample_bytes == 1) LAUNCH(interp_batch_kernel<uint8_t>, grid_for_warps((n + 3) / 4), CTA_THREADS, 0, items, n, bitdepth, bipred);
   else LAUNCH(interp_batch_kernel<uint16_t>, grid_for_warps((n + 3) / 4), CTA_THREADS, 0, items, n, bitdepth, bipred);
@@ -427,6 +435,7 @@ int tb_interp_batch(const tb_interp_item_t *items, int n, int sample_bytes, int 
 }
 int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, int bitdepth, tb_txfm_result_t *out) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_txfm_chain_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   size_t smem = TX_TABLE_BYTES + sizeof(TxScratch) * WARPS_PER_CTA;
   int *meta = nullptr, *idx = nullptr;
@@ -446,6 +455,7 @@ int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, in
 }
 int tb_intra_batch(const tb_intra_item_t *items, int n, int sample_bytes, int bitdepth) {
   API_BEGIN();
+  if (sample_bytes != 1 && sample_bytes != 2) { set_err("tb_intra_batch: sample_bytes must be 1 or 2", cudaSuccess); return TB_ERR_ARG; }
   if (n <= 0) return TB_OK;
   if (sample_bytes == 1) LAUNCH(intra_batch_kernel<uint8_t>, grid_for_warps(n), CTA_THREADS, sizeof(IntraShared<uint8_t>) * WARPS_PER_CTA, items, n, bitdepth);
   else LAUNCH(intra_batch_kernel<uint16_t>, grid_for_warps(n), CTA_THREADS, sizeof(IntraShared<uint16_t>) * WARPS_PER_CTA, items, n, bitdepth);
