@@ -446,7 +446,7 @@ def run_gpu(args, cfg):
     if world > 1:
         line["collective"] = {"backend": "nccl", "scatter_bytes_per_step": int(scatter_bytes // max(1, Ke)), "gather_bytes_per_step": int(gather_bytes // max(1, Ke)),
                               "ms": round(coll_ms, 3), "share_of_e2e": round(coll_ms / ems, 5)}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the reported CPU baseline is measured at N = 1 only
         line["cpu_baseline"] = cpu_arm(args, cfg, brief=True)
     print(json.dumps(line))
     L.tb_rdo_batch_destroy(batch)
@@ -472,6 +472,16 @@ def cpu_arm(args, cfg, brief=False):
     except Exception:
         phys = None
     nproc = args.cpu_procs or cores
+    if brief and not args.cpu_fresh:  # cpu_baseline of the GPU arm: a measurement of this box less than an hour old (the --impl reference run) is reused
+        try:
+            for d in sorted(os.listdir(args.cache)):
+                if d.startswith("cpu_arm_%s_%dx%d_" % (cfg.name, cfg.W, cfg.H)):
+                    last = json.load(open(os.path.join(args.cache, d, "last_result.json")))
+                    if time.time() - last["time"] < 3600 and last["res"]["cores"] == nproc:
+                        last["res"]["reused"] = "measured %.0f s earlier on this box by bench.py --impl reference / a previous run (--cpu-fresh re-measures)" % (time.time() - last["time"])
+                        return last["res"]
+        except Exception:
+            pass
     gop = 1
     if "-num_reorder_pics" in cfg.flags:
         gop = int(cfg.flags[cfg.flags.index("-num_reorder_pics") + 1]) + 1
@@ -552,6 +562,10 @@ def cpu_arm(args, cfg, brief=False):
            "seconds": round(sum(s[2] for s in slices), 2), "slices_rd_loop_mpixel_s": [round(s[0], 4) for s in slices],
            "wall_clock_value": round(float(np.mean([s[1] for s in slices])), 4),
            "per_thread_mpixel_s": round(value / nproc, 5)}
+    try:  # the two arms run back to back on one box: the other arm may reuse this measurement instead of holding the box for minutes again
+        json.dump({"time": time.time(), "res": res}, open(os.path.join(tmp, "last_result.json"), "w"))
+    except Exception:
+        pass
     if brief:
         return res
     line = {"impl": "reference", "metric": cfg.metric(), "value": res["value"], "unit": "Mpixel/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": len(slices),
@@ -579,6 +593,7 @@ def main():
     ap.add_argument("--cpu-settle-limit", type=float, default=240.0, help="CPU arm: give up waiting for the steady state after this many seconds")
     ap.add_argument("--cache", default=os.environ.get("THOR_B200_CACHE", "/tmp/thor_b200_bench"))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-fresh", action="store_true", help="cpu_baseline: measure again even if a recent measurement of this box exists in the cache")
     args = ap.parse_args()
     cfg = Cfg(args.config, tuple(int(v) for v in args.size.split("x")) if args.size else None, args.frames or None)
     os.makedirs(args.cache, exist_ok=True)
