@@ -240,7 +240,7 @@ int tb_interpolate_frames(tb_frame_t *out, const tb_frame_t *ref0, const tb_fram
 /* ---- device-resident RD loop.  tb_rdo_encode_frame() runs the reference's process_block() recursion
  * (enc/encode_block.c:2401-2565: early skip :2231-2399, mode_decision_rdo :1835-2120, encode_block :1340-1514, the bit
  * counting of write_block enc/write_bits.c:255-600, the MV predictors / skip / merge candidates common/inter_prediction.c:413-836 and
- * find_block_contexts common/common_block.c:283-303) for EVERY super block of one frame on the GPU, one CTA per super block, super
+ * find_block_contexts common/common_block.c:283-303) for EVERY super block of one frame on the GPU (one CTA works on one super block at a time), super
  * blocks in a wavefront (left, up-left, up, up-right dependencies), and returns the decisions.  The host then only serialises them
  * (write_super_mode / write_block of the reference's own bit writer: thor_b200/csrc/tb_rdo_shim.c is that binding).
  * Supported: 4:2:0, sync = 0, qmtx = 0, interp_ref != 2, max_delta_qp = 0, bitrate = 0 (every BASELINE.json configuration);

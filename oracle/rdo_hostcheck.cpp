@@ -6,7 +6,7 @@
 // unmodified objects + thor_b200/csrc/tb_rdo_shim.c + this library; with TB_RDO_VERIFY=1 every super block of a real encode is decided by
 // this code AND by the reference's process_block() on the same state and compared (bits, reconstruction, deblock_data), and without it
 // the whole encode runs through tb_rdo_encode_frame() below and the .bit file must equal the reference's.  tests/test_rdo_host.py.
-// The CUDA build of the same header (tb_rdo_dev.cuh) differs only in the backend, whose primitives are parity-tested separately.
+// The CUDA build of the same header (thor_b200/csrc/tb_rdo.cu) differs only in the backend, whose primitives are parity-tested separately.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>

@@ -1,5 +1,5 @@
 """SURVEY §8f.1 on the GPU: oracle/_ref/Thorenc_b200_rdo = the reference's unmodified HOST objects + thor_b200/csrc/tb_rdo_shim.c
-(--wrap=process_block_*) + libthor_b200.so.  Every frame's RD loop runs in rdo_frame_kernel (tb_rdo_encode_frame), the in-loop filters and
+(--wrap=process_block_*) + libthor_b200.so.  Every frame's RD loop runs in rdo_batch_kernel (tb_rdo_encode_frame), the in-loop filters and
 the temporal interpolation run through the drop-in CUDA symbols, and the host only drives the sequence and writes bits.  The .bit file and
 the reconstruction must equal the all-reference encoder's — with B frames, interpolated references, bipred and (one case) CDEF on."""
 import os

@@ -1,13 +1,14 @@
 // tb_rdo.h — the reference's per-super-block RD loop, written once for two builds:
-//   * nvcc, device backend (tb_rdo_dev.cuh): the product — one CTA per super block inside rdo_frame_kernel;
+//   * nvcc, device backend (tb_rdo.cu): the product — one 8-warp CTA per super block at a time inside the persistent rdo_batch_kernel;
 //   * g++,  oracle backend (oracle/rdo_hostcheck.cpp): TEST INFRASTRUCTURE — the same control flow over the plain-C oracle's
 //     primitives, used here (no GPU in the build container) to pin the control flow against the compiled reference SB by SB.
 // The control flow is scalar and warp-uniform, and it is SPMD over the NW warps of a CTA (NW = 1 on the host unless the host check
 // simulates warps with threads): every warp executes the whole control flow on its own scratch blocks (Work), so sequential sections
 // (neighbour derivation, the bipred refinement, the recursion itself) are simply replicated and stay consistent without communication.
 // Two kinds of sections are DISTRIBUTED: the motion searches of the reference frames (one reference per warp; results exchanged through
-// the backend and the candidate lists replayed by the other warps) and the RD candidates of a block (candidate k is evaluated by warp
-// k mod NW).  The reference keeps the first candidate with the strictly smallest cost; that is the minimum of (cost, k), which the
+// the backend and the candidate lists replayed by the other warps) and the RD candidates of a block (round robin in the serial form of the
+// decision, drawn from shared counters in the overlapped form: mode_decision_overlap).  The reference keeps the first candidate with the
+// strictly smallest cost; that is the minimum of (cost, k), k = the candidate's position in the reference's evaluation order, which the
 // backend's reduction returns together with the warp that holds the winning reconstruction; that warp alone commits the block.
 // The backend's primitives are the warp-cooperative routines of tb_device.cuh.  Nothing in this file touches samples directly.
 //
