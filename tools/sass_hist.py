@@ -20,6 +20,7 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            cur = cur.replace("(anonymous namespace)::", "")
             cur = re.sub(r"\(.*", "", cur)
             kernels[cur] = collections.Counter()
             continue
