@@ -127,3 +127,40 @@ def test_binding_example_compiles_against_reference_headers():
             r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I", "/root/reference/common", "-I", "/root/reference/enc", "-I", os.path.join(root, "include")]
                                + extra + [os.path.join(root, "examples", src)], capture_output=True, text=True)
             assert r.returncode == 0, (src, r.stderr[-1200:])
+
+
+def test_rdo_struct_layouts_match_header(tmp_path):
+    """tb_rdo_frame_t / tb_rdo_blk_t / tb_rdo_leaf_t (include/thor_b200.h) against their Python mirrors (thor_b200/rdo_jobs.py): sizes and the offsets of the
+    fields the mirrors address; the RD-loop entry points are exported; without a GPU they refuse to compute."""
+    import ctypes as C
+    import thor_b200 as t
+    from thor_b200 import rdo_jobs as RJ
+    fields = ["width", "lambda", "early_skip_thr", "ref_sign", "orig", "orig_stride", "ref", "ref_stride", "ref_pad", "rec", "rec_stride", "blk", "leaves", "leaf_count", "coeffs"]
+    src = tmp_path / "rdo.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "thor_b200.h"\nint main(){printf("%zu %zu %zu %d %d %d\\n",sizeof(tb_rdo_frame_t),sizeof(tb_rdo_blk_t),'
+                   'sizeof(tb_rdo_leaf_t),TB_RDO_MAX_REF,TB_RDO_MAX_LEAVES,TB_RDO_SB_COEFFS);' +
+                   "".join('printf("%%zu\\n",offsetof(tb_rdo_frame_t,%s));' % f for f in fields) +
+                   'printf("%zu %zu %zu\\n",offsetof(tb_rdo_leaf_t,mv_arr0),offsetof(tb_rdo_leaf_t,coeff_ofs),offsetof(tb_rdo_leaf_t,cost));return 0;}\n')
+    exe = tmp_path / "rdo"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out[:6]] == [C.sizeof(RJ.RdoFrame), RJ.RDO_BLK.itemsize, RJ.RDO_LEAF.itemsize, RJ.TB_RDO_MAX_REF, RJ.TB_RDO_MAX_LEAVES, RJ.TB_RDO_SB_COEFFS]
+    py = {"lambda": "lambda_"}
+    assert [int(v) for v in out[6:6 + len(fields)]] == [getattr(RJ.RdoFrame, py.get(f, f)).offset for f in fields]
+    assert [int(v) for v in out[6 + len(fields):]] == [RJ.RDO_LEAF.fields["mv_arr0"][1], RJ.RDO_LEAF.fields["coeff_ofs"][1], RJ.RDO_LEAF.fields["cost"][1]]
+    for sym in ("tb_rdo_encode_frame", "tb_rdo_encode_frames", "tb_rdo_batch_create", "tb_rdo_batch_upload", "tb_rdo_batch_run", "tb_rdo_batch_download", "tb_rdo_batch_sync",
+                "tb_rdo_batch_stats", "tb_rdo_batch_grid", "tb_rdo_batch_destroy", "tb_rdo_last_error", "tb_rdo_launch_count"):
+        assert hasattr(t.lib, sym), sym
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:  # no CPU path: the RD loop refuses without a device
+        t.lib.tb_rdo_batch_create.restype = C.c_void_p
+        assert t.lib.tb_rdo_batch_create(1, 1) is None
+        f = RJ.RdoFrame()
+        f.width, f.height, f.log2_sb_size, f.sample_bytes, f.bitdepth, f.qp = 64, 64, 7, 1, 8, 32
+        dummy = (C.c_uint8 * 64)()
+        f.blk = f.leaves = f.leaf_count = f.coeffs = C.addressof(dummy)
+        assert t.lib.tb_rdo_encode_frame(C.byref(f)) == t.TB_ERR_CUDA
