@@ -282,7 +282,7 @@ typedef struct {
   const void *orig[3];
   int32_t orig_stride[2]; /* luma, chroma pitch in samples */
   const void *ref[TB_RDO_MAX_REF][3];
-  int32_t ref_stride[2], ref_pad; /* ref_pad: luma border (the whole padded plane is uploaded) */
+  int32_t ref_stride[2], ref_pad; /* ref_pad: luma border, >= 160 = the reference's PADDING_Y (the whole padded plane is uploaded) */
   void *rec[3];           /* out: reconstruction before the in-loop filters (visible area) */
   int32_t rec_stride[2];
   tb_rdo_blk_t *blk;      /* out: (height/4) x (width/4), raster */

@@ -805,7 +805,8 @@ template <class S> void fill_ctx(FrameCtx<S> &C, const Slot &D, const tb_rdo_fra
 int check_desc(const tb_rdo_frame_t *f) {
   if (!f || f->num_ref > TB_RDO_MAX_REF || f->num_ref < 0 || f->log2_sb_size > 7 || f->log2_sb_size < 4 || (f->sample_bytes != 1 && f->sample_bytes != 2) || f->width <= 0 ||
       f->height <= 0 || (f->width & 7) || (f->height & 7) || f->interp_ref == 2 || f->qp < 0 || f->qp > 51 ||
-      (f->num_ref > 0 && (f->ref_pad < 16 || f->ref_stride[0] < f->width + 2 * f->ref_pad))) {
+      (f->num_ref > 0 && (f->ref_pad < 160 /* clip_mv admits vectors 144 samples outside the frame (+ filter taps): the reference's PADDING_Y */ ||
+                          f->ref_stride[0] < f->width + 2 * f->ref_pad))) {
     snprintf(g_err, sizeof(g_err), "unsupported frame description (%dx%d, %d refs, sb %d, interp_ref %d, qp %d, pad %d)", f ? f->width : 0, f ? f->height : 0,
              f ? f->num_ref : 0, f ? f->log2_sb_size : 0, f ? f->interp_ref : 0, f ? f->qp : 0, f ? f->ref_pad : 0);
     return TB_ERR_ARG;
