@@ -76,3 +76,51 @@ def test_batched_rd_loop_equals_reference_decisions(tmp_path, name, flags, w, h,
     for k, hf in enumerate(hosts):
         r = hf.check()
         assert r == {"rec": True, "blk": True, "sb_cost": True}, (name, "frame", hf.job.frame_num, "copy", k // len(jobs), r)
+
+
+# ---- committed golden jobs (tests/golden/rdo_jobs_hdb_128x136.xz, generated from the reference by tests/golden/make_golden_rdo.py)
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rdo_jobs_hdb_128x136.xz")
+
+
+def golden_jobs(tmp):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_rdo", os.path.join(os.path.dirname(GOLDEN), "make_golden_rdo.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    n = m.unpack(open(GOLDEN, "rb").read(), tmp)
+    return m, n
+
+
+@needs
+def test_golden_rdo_jobs_are_what_the_reference_writes_today(tmp_path):
+    """the fixture is pinned: a fresh capture with the compiled reference reproduces it byte for byte"""
+    m, n = golden_jobs(str(tmp_path))
+    fresh_dir = tmp_path / "fresh"
+    fresh_dir.mkdir()
+    fresh = m.capture(str(fresh_dir))
+    assert n == len(fresh) == 9
+    for k in range(n):
+        assert open(os.path.join(str(tmp_path), "frame_%03d.job" % k), "rb").read() == fresh[k], "job %d differs from a fresh capture" % k
+
+
+@pytest.mark.gpu
+def test_batched_rd_loop_on_the_golden_jobs(tmp_path):
+    """the device RD loop against the committed decisions of the reference (no oracle/_ref needed on the GPU box): all nine frames in one launch"""
+    import thor_b200 as tb
+    from thor_b200 import rdo_jobs as RJ
+    golden_jobs(str(tmp_path))
+    jobs = RJ.load_jobs(str(tmp_path))
+    assert len(jobs) == 9 and [j.hdr.frame_type for j in jobs].count(2) == 7
+    L = tb.lib
+    L.tb_rdo_encode_frames.argtypes = [C.c_void_p, C.c_int]
+    L.tb_rdo_last_error.restype = C.c_char_p
+    keep = []
+
+    def alloc(nbytes):
+        a = np.zeros(max(nbytes, 16), np.uint8); keep.append(a)
+        return a.ctypes.data
+    hosts = [RJ.HostFrame(j, alloc) for j in jobs]
+    descs = (RJ.RdoFrame * len(hosts))(*[hf.desc for hf in hosts])
+    assert L.tb_rdo_encode_frames(descs, len(hosts)) == 0, L.tb_rdo_last_error()
+    for hf in hosts:
+        assert hf.check() == {"rec": True, "blk": True, "sb_cost": True}, ("frame", hf.job.frame_num)
