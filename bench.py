@@ -504,6 +504,18 @@ def cpu_arm(args, cfg, brief=False):
     ps = [subprocess.Popen([exe] + cfg.enc_flags(cfg.W, cfg.H, nfr) + ["-if", clip, "-of", os.path.join(tmp, "o%d.bit" % i)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
                            env=dict(os.environ, TB_RDO_PROGRESS=prog[i])) for i in range(nproc)]
 
+    tick = os.sysconf("SC_CLK_TCK")
+
+    def cpu_seconds():  # CPU time the encoders have consumed so far (utime + stime of /proc/<pid>/stat)
+        tot = 0.0
+        for p in ps:
+            try:
+                f = open("/proc/%d/stat" % p.pid).read().rsplit(")", 1)[1].split()
+                tot += (int(f[11]) + int(f[12])) / tick
+            except Exception:
+                pass
+        return tot
+
     def read():
         out = []
         for f in prog:
@@ -527,6 +539,7 @@ def cpu_arm(args, cfg, brief=False):
             time.sleep(0.25)
         settle_s = time.time() - t_start
         prev, t_prev = read(), time.time()
+        cpu_prev, cpu_used, cpu_wall = cpu_seconds(), 0.0, 0.0
         for k in range(n_warm + n_timed):
             if early:
                 break
@@ -535,11 +548,13 @@ def cpu_arm(args, cfg, brief=False):
             if any(p.poll() is not None for p in ps):
                 early = True  # an encoder finished its clip (development sizes): the slice is not a steady-state sample
                 break
+            cpu_cur = cpu_seconds()
             if k >= n_warm:
                 rd = sum((c[0] - a[0]) / (c[1] - a[1]) for a, c in zip(prev, cur) if c[1] > a[1]) / 1e6
                 wall = sum(c[0] - a[0] for a, c in zip(prev, cur)) / (t_cur - t_prev) / 1e6
                 slices.append((rd, wall, t_cur - t_prev))
-            prev, t_prev = cur, t_cur
+                cpu_used += cpu_cur - cpu_prev; cpu_wall += t_cur - t_prev
+            prev, t_prev, cpu_prev = cur, t_cur, cpu_cur
         if not slices:  # fall back: everything the encoders did so far (or do until they finish, for tiny development clips)
             for p in ps:
                 p.wait()
@@ -562,6 +577,17 @@ def cpu_arm(args, cfg, brief=False):
            "seconds": round(sum(s[2] for s in slices), 2), "slices_rd_loop_mpixel_s": [round(s[0], 4) for s in slices],
            "wall_clock_value": round(float(np.mean([s[1] for s in slices])), 4),
            "per_thread_mpixel_s": round(value / nproc, 5)}
+    # how much CPU the box actually granted: CPU seconds the encoders consumed per wall second of the timed slices; far below `cores` = a shared or quota-limited host
+    if not early and cpu_wall > 0:
+        eff = cpu_used / cpu_wall
+        res["effective_cores"] = round(eff, 1)
+        res["mpixel_s_per_effective_core"] = round(value / eff, 4) if eff > 0 else None
+    try:
+        res["cgroup_cpu_max"] = open("/sys/fs/cgroup/cpu.max").read().strip()
+    except Exception:
+        pass
+    res["note"] = ("value = what this host delivered with one encoder per hardware thread; effective_cores = CPU seconds consumed / wall seconds in the timed slices. "
+                   "An unconstrained host scales the one-thread rate (single_stream_reference in the GPU arm's line) by its physical cores at best.")
     try:  # the two arms run back to back on one box: the other arm may reuse this measurement instead of holding the box for minutes again
         json.dump({"time": time.time(), "res": res}, open(os.path.join(tmp, "last_result.json"), "w"))
     except Exception:
