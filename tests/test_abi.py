@@ -122,7 +122,7 @@ def test_binding_example_compiles_against_reference_headers():
     """examples/*.c (INTEGRATION.md §2.1 / §2.2 as real C) use the reference's own types (deblock_data_t, yuv_frame_t)
     and the C ABI header: it must compile, warning-free, for both sample widths"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for src in ("frame_filters_binding.c", "motion_search_binding.c"):
+    for src in ("frame_filters_binding.c", "motion_search_binding.c", "rdo_batch_server.c"):
         for extra in ([], ["-DHBD"]):
             r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-I", "/root/reference/common", "-I", "/root/reference/enc", "-I", os.path.join(root, "include")]
                                + extra + [os.path.join(root, "examples", src)], capture_output=True, text=True)
