@@ -43,4 +43,12 @@ int X(motion_estimate_bi)(SAMPLE *orig, SAMPLE *ref0, SAMPLE *ref1, int size, in
   int n = mvcand_num;
   return motion_estimate_bi(orig, ref0, ref1, size, stride_r, width, height, mv, mvc, mvp, lambda, &p, sign, fwidth, fheight, xpos, ypos, list, &n, enable_bipred);
 }
+int X(motion_estimate_sync)(SAMPLE *orig, SAMPLE *ref, int size, int stride_r, int width, int height, mv_t *mv, mv_t *mvc, mv_t *mvp, double lambda, int bitdepth, int sign,
+                            int fwidth, int fheight, int xpos, int ypos, mv_t *mvcand, int enable_bipred) {
+  enc_params p;
+  memset(&p, 0, sizeof(p));
+  p.bitdepth = bitdepth;
+  int n = 6;
+  return motion_estimate_sync(orig, ref, size, stride_r, width, height, mv, mvc, mvp, lambda, &p, sign, fwidth, fheight, xpos, ypos, mvcand, &n, enable_bipred);
+}
 void X(set_use_simd)(int v) { use_simd = v; }

@@ -89,6 +89,7 @@ void orc_interpolate_frames_##SFX(S *outY, S *outU, S *outV, int so_y, int so_c,
 uint64_t orc_dist_8x8_##SFX(const S *dst, int dstride, const S *src, int sstride, int coeff_shift); \
 void orc_cdef_search_mse_##SFX(const S *recY, const S *recU, const S *recV, const S *orgY, const S *orgU, const S *orgV, int sy, int sc, int width, int height, const orc_blkinfo_t *bi, int speed, int pri_damping, int bitdepth, uint64_t *mse, int *dirs, int *vars, uint8_t *allskip_out); \
 int  orc_motion_estimate_bi_##SFX(const S *orig, const S *ref0, const S *ref1, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred); \
+int  orc_motion_estimate_sync_##SFX(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, orc_mv_t *mvcand, int enable_bipred); \
 void orc_block_combine_##SFX(S *dst, int ds, const S *a, int as, const S *b, int bs, int w, int h, int op, int bitdepth); \
 int  orc_motion_estimate_##SFX(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp, double lambda, int encoder_speed, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, const orc_mv_t *mvcand, int mvcand_num, int enable_bipred);
 

@@ -1118,6 +1118,52 @@ int FN(orc_motion_estimate_bi)(const S *orig, const S *ref0, const S *ref1, int 
   return (int)min_sad;
 }
 
+/* ---- a5: motion_estimate_sync, the search used with -sync 1.  enc/encode_block.c:713-796.  The same 3x3 telescope (steps 32..1 quarter-pels, the legal positions only
+ * at step 1) and six candidates as the bi-directional search, on ONE reference with every probe truly interpolated; the candidate list is used AS quarter-pel vectors and
+ * entries 4 / 5 are overwritten with the predictor / zero (the caller's list is scribbled on like in motion_estimate_bi: pass a writable copy of >= 6 entries).
+ * ORACLE ONLY so far: libthor_b200 has no CUDA form of it (the RD-loop binding leaves -sync 1 to the reference's own loop). ---- */
+int FN(orc_motion_estimate_sync)(const S *orig, const S *ref, int size, int stride_r, int width, int height, orc_mv_t *mv, const orc_mv_t *mvc, const orc_mv_t *mvp,
+                                 double lambda, int bitdepth, int sign, int fwidth, int fheight, int xpos, int ypos, orc_mv_t *mvcand, int enable_bipred) {
+  static S rf[128 * 128];
+  uint32_t min_sad = 1u << 31, sad;
+  orc_mv_t cand, opt = {0, 0}, mref;
+  mref.y = (int16_t)(((mvc->y + 2) >> 2) << 2);
+  mref.x = (int16_t)(((mvc->x + 2) >> 2) << 2);
+  for (int step = 32; step > 0; step >>= 1) {
+    for (int k = -step; k <= step; k += step)
+      for (int l = -step; l <= step; l += step) {
+        if (step < 32 && k == 0 && l == 0) continue;
+        if (step == 1) {
+          int vf = mref.y & 3, hf = mref.x & 3, skip;
+          if (vf == 0 && hf == 0) skip = abs(k) != abs(l);
+          else if (vf == 2 && hf == 2) skip = 1;
+          else skip = abs(k) == abs(l);
+          if (skip) continue;
+        }
+        cand.y = (int16_t)(mref.y + k);
+        cand.x = (int16_t)(mref.x + l);
+        orc_clip_mv(&cand, ypos, xpos, fwidth, fheight, size, size, sign);
+        FN(orc_get_inter_prediction_luma)(rf, ref, width, height, stride_r, width, &cand, sign, enable_bipred, fwidth, fheight, xpos, ypos, bitdepth);
+        sad = FN(orc_sad)(orig, rf, size, width, width, height) >> (bitdepth - 8);
+        sad += (unsigned)(int)(lambda * (double)orc_quote_mv_bits((int16_t)(cand.y - mvp->y), (int16_t)(cand.x - mvp->x)) + 0.5);
+        if (sad < min_sad) { min_sad = sad; opt = cand; }
+      }
+    mref = opt;
+  }
+  mvcand[4] = *mvp;
+  mvcand[5].y = 0; mvcand[5].x = 0;
+  for (int idx = 0; idx < 6; idx++) {  /* ME_CANDIDATES */
+    cand = mvcand[idx];
+    orc_clip_mv(&cand, ypos, xpos, fwidth, fheight, size, size, sign);
+    FN(orc_get_inter_prediction_luma)(rf, ref, width, height, stride_r, width, &cand, sign, enable_bipred, fwidth, fheight, xpos, ypos, bitdepth);
+    sad = FN(orc_sad)(orig, rf, size, width, width, height) >> (bitdepth - 8);
+    sad += (unsigned)(int)(lambda * (double)orc_quote_mv_bits((int16_t)(cand.y - mvp->y), (int16_t)(cand.x - mvp->x)) + 0.5);
+    if (sad < min_sad) { min_sad = sad; opt = cand; }
+  }
+  *mv = opt;
+  return (int)min_sad;
+}
+
 /* ---- a9/a5 element-wise block combinations: op 0 average_blocks_all (a+b)>>1 (common/inter_prediction.c:228-247),
  * op 1 bipred search target sat(2a - b) (enc/encode_block.c:1780-1782), op 2 block_avg (a+b+1)>>1 ---- */
 void FN(orc_block_combine)(S *dst, int ds, const S *a, int as, const S *b, int bs, int w, int h, int op, int bitdepth) {

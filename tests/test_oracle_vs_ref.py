@@ -670,3 +670,35 @@ def test_coeff_bits():
                 assert O.orc_coeff_bits(P(c), size, typ) == R.get_bit_pos(C.byref(st)), (size, typ, trial)
                 n += 1
     assert n > 1500
+
+
+@pytest.mark.parametrize("hbd,bd", [(0, 8), (1, 10)])
+def test_motion_estimate_sync(hbd, bd):
+    """a5 gap of round 1: motion_estimate_sync (enc/encode_block.c:713-796, -sync 1) restated in the oracle and pinned against the reference's file-static function
+    through the trampoline.  (No CUDA form yet: the RD-loop binding leaves -sync 1 to the reference's own loop.)"""
+    rng = np.random.default_rng(21)
+    s = sfx(hbd)
+    E = ref_enc(hbd)
+    fw, fh = 192, 128
+    f0 = Frame(fw, fh, bd, hbd); f0.randomize(rng)
+    getattr(R, "pad_yuv_frame_" + s)(C.byref(f0.s))
+    cur = np.clip(np.roll(f0.y.astype(int), (1, -2), axis=(0, 1)) + rng.integers(-3, 4, f0.y.shape), 0, (1 << bd) - 1)
+    for trial in range(40):
+        size = int(rng.choice([8, 16, 32, 64]))
+        w, h = size, size
+        if trial % 3 == 1: h = size // 2      # PART_HOR
+        if trial % 3 == 2: w = size // 2      # PART_VER
+        xpos, ypos = int(rng.integers(0, fw // size)) * size, int(rng.integers(0, fh // size)) * size
+        org = aligned((size, size), sdt(hbd))
+        org[...] = cur[ypos:ypos + size, xpos:xpos + size]
+        sign = int(rng.integers(0, 2)); lam = float(rng.uniform(2.0, 40.0)); bip = int(rng.integers(0, 2))
+        mvc = (C.c_int16 * 2)(int(rng.integers(-30, 30)), int(rng.integers(-30, 30)))
+        mvp = (C.c_int16 * 2)(int(rng.integers(-30, 30)), int(rng.integers(-30, 30)))
+        base = [int(v) for v in rng.integers(-40, 40, 16)]
+        ca = (C.c_int16 * 16)(*base); cb = (C.c_int16 * 16)(*base)   # both sides scribble on entries 4 and 5
+        m0 = (C.c_int16 * 2)(0, 0); m1 = (C.c_int16 * 2)(0, 0)
+        p0 = P(f0.Y, f0.origin(0) + ypos * f0.sy + xpos)
+        a = getattr(O, "orc_motion_estimate_sync_" + s)(P(org), p0, size, f0.sy, w, h, m0, mvc, mvp, C.c_double(lam), bd, sign, fw, fh, xpos, ypos, ca, bip)
+        b = getattr(E, "ref_motion_estimate_sync_" + s)(P(org), p0, size, f0.sy, w, h, m1, mvc, mvp, C.c_double(lam), bd, sign, fw, fh, xpos, ypos, cb, bip)
+        assert (a, m0[0], m0[1]) == (b, m1[0], m1[1]), (trial, size, w, h, sign)
+        assert list(ca) == list(cb)
