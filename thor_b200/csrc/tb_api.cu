@@ -70,6 +70,12 @@ inline void need_ctx(const char *where) {
 inline void ck(cudaError_t e, const char *where) {
   if (e != cudaSuccess) { set_err(where, e); die(where); }
 }
+// the batched (B) entry points promise TB_ERR_CUDA, not abort(): only the drop-in symbols (no error channel in the reference's ABI) die
+#define CKB(x, where)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (x);                                                   \
+    if (e__ != cudaSuccess) { set_err(where, e__); return TB_ERR_CUDA; }     \
+  } while (0)
 void *slot_buf(int s, size_t bytes) {
   if (g.cap[s] < bytes) {
     if (g.slot[s]) { ck(cudaStreamSynchronize(g.stream), "sync"); cudaFree(g.slot[s]); }
@@ -391,9 +397,9 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
   if (n <= 0) return TB_OK;
   // stream-ordered scratch: the sorted item list and the scheduler's counters (see me_batch_kernel)
   int *meta = nullptr, *idx = nullptr;
-  ck(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "me scratch");
+  CKB(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "me scratch");
   idx = meta + 128;
-  ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "me scratch");
+  CKB(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "me scratch");
   const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
   const MeClassOf cls{speed, (TB_ME_QUAD && sample_bytes == 1 && speed == 0) ? 1 : 0};
   LAUNCH((sched_hist_kernel<tb_me_item_t, MeClassOf>), sgrid, 256, 0, items, n, cls, meta);
@@ -402,7 +408,7 @@ int tb_motion_estimate_batch(const tb_me_item_t *items, int n, const int16_t *ca
   const int grid = std::min((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, g.sm_count * TB_ME_MINBLOCKS);  // persistent: every CTA resident
   if (sample_bytes == 1) LAUNCH(me_batch_kernel<uint8_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
   else LAUNCH(me_batch_kernel<uint16_t>, grid, CTA_THREADS, 0, items, n, idx, meta, cand, bitdepth, speed, bip, fw, fh, out, g.me_stats);
-  ck(cudaFreeAsync(meta, g.stream), "me scratch");
+  CKB(cudaFreeAsync(meta, g.stream), "me scratch");
   API_END();
 }
 int tb_motion_estimate_bi_batch(const tb_me_bi_item_t *items, int n, const int16_t *cand, int sample_bytes, int bitdepth, int bip, int fw, int fh, tb_me_result_t *out) {
@@ -439,9 +445,9 @@ int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, in
   if (n <= 0) return TB_OK;
   size_t smem = TX_TABLE_BYTES + sizeof(TxScratch) * WARPS_PER_CTA;
   int *meta = nullptr, *idx = nullptr;
-  ck(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "txfm scratch");
+  CKB(cudaMallocAsync((void **)&meta, 128 * sizeof(int) + (size_t)n * sizeof(int), g.stream), "txfm scratch");
   idx = meta + 128;
-  ck(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "txfm scratch");
+  CKB(cudaMemsetAsync(meta, 0, 128 * sizeof(int), g.stream), "txfm scratch");
   const int sgrid = std::min((n + 255) / 256, g.sm_count * 8);
   const TxClassOf cls{};
   LAUNCH((sched_hist_kernel<tb_txfm_item_t, TxClassOf>), sgrid, 256, 0, items, n, cls, meta);
@@ -450,7 +456,7 @@ int tb_txfm_chain_batch(const tb_txfm_item_t *items, int n, int sample_bytes, in
   const int grid = std::min((n + 31) / 32, g.sm_count * TB_TX_MINBLOCKS);  // persistent: every CTA resident
   if (sample_bytes == 1) LAUNCH(txfm_chain_kernel<uint8_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
   else LAUNCH(txfm_chain_kernel<uint16_t>, grid, CTA_THREADS, smem, items, n, idx, meta, bitdepth, out);
-  ck(cudaFreeAsync(meta, g.stream), "txfm scratch");
+  CKB(cudaFreeAsync(meta, g.stream), "txfm scratch");
   API_END();
 }
 int tb_intra_batch(const tb_intra_item_t *items, int n, int sample_bytes, int bitdepth) {
