@@ -496,7 +496,7 @@ def cpu_arm(args, cfg, brief=False):
     reference = args.impl == "reference"
     n_warm = args.warmup if reference else 1
     n_timed = max(1, args.steps) if reference else args.cpu_slices
-    slice_s = args.cpu_slice
+    slice_s = args.cpu_slice if args.cpu_slice > 0 else min(4.0, max(1.5, 60.0 / (n_warm + n_timed)))
     prog = [os.path.join(tmp, "progress_%d" % i) for i in range(nproc)]
     for f in prog:
         if os.path.exists(f):
@@ -614,7 +614,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="clip length override")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps (GOPs) of the end-to-end launch: min(--steps, this); 0 = --steps")
     ap.add_argument("--cpu-procs", type=int, default=0, help="CPU arm: concurrent reference encoders (0 = one per host thread)")
-    ap.add_argument("--cpu-slice", type=float, default=4.0, help="CPU arm: wall-clock seconds per slice (= one step of --impl reference)")
+    ap.add_argument("--cpu-slice", type=float, default=0.0, help="CPU arm: wall-clock seconds per slice (= one step of --impl reference); 0 = 60 s spread over warm-up + steps, "
+                                                                  "between 1.5 and 4 s")
     ap.add_argument("--cpu-slices", type=int, default=3, help="CPU arm inside the GPU run (cpu_baseline): timed slices")
     ap.add_argument("--cpu-settle-limit", type=float, default=240.0, help="CPU arm: give up waiting for the steady state after this many seconds")
     ap.add_argument("--cache", default=os.environ.get("THOR_B200_CACHE", "/tmp/thor_b200_bench"))
